@@ -1,0 +1,80 @@
+"""Generate tests/golden/*.npz|json from the UNMODIFIED reference (dev container only).
+
+    python -m oracle.make_golden
+
+Fixtures (all produced by code under /root/reference, imported in place by oracle/ref_loader.py):
+  norm_logits.npz   (logits, T, k, p) -> probs  by reference sampling/utils.py:norm_logits
+  max_fn.npz        x -> max_fn(x)              by reference sampling/utils.py:max_fn
+  spec_runs.json    end-to-end sampling.speculative_sampling on the replay models with the
+                    uniform tape: emitted token ids, acc_len per iteration, acc_rate
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import ref_loader, replay_model, tape
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+NORM_CASES = [  # (V, rows, T, top_k, top_p, scale, seed, dtype)
+    (17, 3, 1.0, 0, 0.0, 2.0, 1, "f32"), (17, 3, 0.7, 5, 0.0, 2.0, 2, "f32"), (17, 3, 1.3, 0, 0.8, 2.0, 3, "f32"),
+    (1000, 4, 0.8, 20, 0.9, 3.8, 4, "f32"), (1000, 4, 1.0, 1, 0.9, 3.0, 5, "f32"), (1000, 2, 1.0, 1000, 0.5, 3.0, 6, "f32"),
+    (1000, 2, 0.5, 0, 0.9, 1.0, 7, "f32"), (1000, 2, 2.0, 50, 1.0, 3.0, 8, "f32"), (4099, 2, 0.8, 20, 0.9, 3.8, 9, "bf16"),
+    (4099, 2, 1.0, 0, 0.0, 0.55, 10, "bf16"), (4099, 2, 1.0, 40, 0.95, 3.0, 11, "f16"),
+    (32000, 2, 0.8, 20, 0.9, 3.8, 12, "f32"), (32000, 1, 1.0, 0, 0.0, 0.55, 13, "f32"),
+    (50272, 1, 0.8, 20, 0.9, 3.8, 14, "bf16"), (32000, 1, 1.0, 0, 0.9, 2.0, 15, "f32"),
+]
+
+
+def _logits(V, rows, scale, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, V, generator=g) * scale
+    dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[dtype]
+    return x.to(dt)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    utils = ref_loader.load_utils()
+    blob = {}
+    for ci, (V, rows, T, k, p, scale, seed, dtype) in enumerate(NORM_CASES):
+        x = _logits(V, rows, scale, seed, dtype)
+        probs = torch.cat([utils.norm_logits(x[i:i + 1].float(), T, k, p) for i in range(rows)], 0)
+        # fixtures keep only the non-zero entries of the big rows (probs are sparse after top-k)
+        nz = probs.nonzero()
+        blob[f"c{ci}_meta"] = np.array([V, rows, T, k, p, scale, seed, {"f32": 0, "bf16": 1, "f16": 2}[dtype]], dtype=np.float64)
+        blob[f"c{ci}_nz_idx"] = nz.numpy().astype(np.int32)
+        blob[f"c{ci}_nz_val"] = probs[nz[:, 0], nz[:, 1]].numpy()
+    np.savez_compressed(os.path.join(OUT, "norm_logits.npz"), **blob)
+
+    g = torch.Generator().manual_seed(99)
+    xs = torch.randn(6, 2000, generator=g) * 0.01
+    xs[5] = -xs[5].abs()                                        # all-negative row -> all zeros
+    np.savez_compressed(os.path.join(OUT, "max_fn.npz"), x=xs.numpy(), y=utils.max_fn(xs).numpy())
+
+    runs = []
+    for (V, k, p, T, gamma, max_len, seed, noise) in [
+        (1000, 20, 0.9, 0.8, 4, 48, 11, 0.5), (32000, 20, 0.9, 1.0, 4, 40, 12, 0.5), (500, 0, 0.0, 1.0, 4, 40, 13, 0.5),
+        (777, 0, 0.9, 1.3, 3, 40, 14, 0.3), (900, 5, 0.0, 0.7, 5, 40, 15, 0.8), (2048, 20, 0.9, 1.0, 1, 24, 16, 0.5),
+        (1000, 20, 0.9, 1.0, 8, 48, 17, 0.0), (1500, 10, 0.5, 1.0, 4, 40, 18, 2.0),
+    ]:
+        d, t = replay_model.make_pair(V, seed=seed, noise=noise)
+        prefix = torch.randint(3, V, (1, 7), generator=torch.Generator().manual_seed(seed))
+        tp = tape.make_tape(seed, max_len + 1, gamma)
+        out, det = ref_loader.run_reference(prefix, d, t, max_len, gamma, T, k, p, tape=tp)
+        runs.append(dict(V=V, top_k=k, top_p=p, temperature=T, gamma=gamma, max_len=max_len, seed=seed, noise=noise,
+                         prefix=prefix[0].tolist(), tokens=out[0].tolist(), acc_len=[int(a) for a in det["acc_len"]],
+                         acc_rate=float(det["acc_rate"])))
+        print("run", V, k, p, T, gamma, "mean acc", np.mean(det["acc_len"]))
+    with open(os.path.join(OUT, "spec_runs.json"), "w") as f:
+        json.dump(runs, f)
+    print("wrote", os.listdir(OUT))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+"""Import the UNMODIFIED reference from /root/reference and make it deterministic
+(TEST INFRASTRUCTURE ONLY; dev container only — the path does not exist on the GPU box).
+
+Nothing is copied: the reference modules are imported in place.  Two compatibility shims
+ are needed because the container has transformers 5.x while the reference pins
+4.35.2:
+
+* shim 1 — four class names that ``sampling/kvcache_model.py:8,12`` imports (used only by the
+  out-of-scope beam code) were removed from transformers 5; stubs are registered before import.
+* shim 2 — ``LegacyCacheAdapter`` converts between the 4.35 tuple-of-(k, v) cache that
+  ``kvcache_model.py:175,381-382`` indexes/slices and the ``DynamicCache`` object HF 5 models use.
+
+Determinism: ``TapeRNG`` replaces ``sample`` in the three modules that bound the name
+(``sampling.utils``, ``sampling.kvcache_model``, ``sampling.speculative_sampling``) by the
+inverse-CDF rule of ``oracle.ref_ops.icdf_sample`` and ``torch.rand`` inside
+``speculative_sampling`` by reads from the same tape (layout: oracle/tape.py).
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib
+import importlib.util
+import os
+import sys
+import warnings
+from types import SimpleNamespace
+
+import torch
+
+from . import ref_ops, tape as tape_mod
+
+REFERENCE_ROOT = os.environ.get("SPECDEC_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "sampling", "utils.py"))
+
+
+def load_utils():
+    """``sampling/utils.py`` loaded standalone (it only needs torch) — no shim."""
+    path = os.path.join(REFERENCE_ROOT, "sampling", "utils.py")
+    spec = importlib.util.spec_from_file_location("_reference_sampling_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_PKG = None
+
+
+def load_package():
+    """The whole reference ``sampling`` package (shim 1)."""
+    global _PKG
+    if _PKG is not None:
+        return _PKG
+    import transformers
+    import transformers.generation                       # noqa: F401  (lazy module must be realised first)
+    import transformers.models.bloom.modeling_bloom      # noqa: F401
+    for name in ("BeamSearchScorer", "BeamScorer"):
+        if not hasattr(transformers, name):
+            setattr(sys.modules["transformers"], name, type(name, (), {}))
+    for name in ("BeamSampleDecoderOnlyOutput", "BeamSampleEncoderDecoderOutput"):
+        if not hasattr(transformers.generation, name):
+            setattr(sys.modules["transformers.generation"], name, type(name, (), {}))
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)                # also needed for `from globals import Decoder`
+    for shadow in ("sampling", "globals"):
+        m = sys.modules.get(shadow)
+        if m is not None and not str(getattr(m, "__file__", "")).startswith(REFERENCE_ROOT):
+            raise RuntimeError(f"module {shadow!r} already imported from elsewhere: {m.__file__}")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _PKG = importlib.import_module("sampling")
+    return _PKG
+
+
+class LegacyCacheAdapter(torch.nn.Module):
+    """shim 2: HF-5 causal LM behind the transformers-4.35 cache calling convention."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.inner = model
+        self.config = model.config
+
+    @property
+    def device(self):
+        return next(self.inner.parameters()).device
+
+    def forward(self, input_ids, past_key_values=None, use_cache=True, **kw):
+        from transformers.cache_utils import DynamicCache
+        cache = None
+        if past_key_values is not None:
+            cache = DynamicCache(ddp_cache_data=[(k.contiguous(), v.contiguous()) for k, v in past_key_values])
+        out = self.inner(input_ids, past_key_values=cache, use_cache=True)
+        legacy = tuple((layer.keys, layer.values) for layer in out.past_key_values.layers)
+        return SimpleNamespace(logits=out.logits, past_key_values=legacy)
+
+
+class TapeRNG:
+    """Feeds the reference's ``sample`` / ``torch.rand`` calls from a (iterations, 2*gamma+2) tape."""
+
+    def __init__(self, tape: torch.Tensor, gamma: int):
+        self.tape, self.gamma = tape, gamma
+        self.it = 0
+        self.n_sample = 0
+        self.n_rand = 0
+
+    def sample(self, probs: torch.Tensor, num_samples: int = 1):
+        g = self.gamma
+        c = self.n_sample
+        if c < g:
+            u = self.tape[self.it, c]                     # u_draft
+        elif c == g:
+            u = self.tape[self.it, g]                     # u_discard
+        else:
+            u = self.tape[self.it, 2 * g + 1]             # u_final
+        tok = ref_ops.icdf_sample(probs.reshape(-1), float(u))
+        self.n_sample += 1
+        if c == g + 1:                                    # iteration finished
+            self.it += 1
+            self.n_sample = 0
+            self.n_rand = 0
+        return torch.tensor([[tok]], dtype=torch.long, device=probs.device)
+
+    def rand(self, *size, **kw):
+        u = self.tape[self.it, self.gamma + 1 + self.n_rand]
+        self.n_rand += 1
+        return u.reshape(1).clone().to(kw.get("device", "cpu"))
+
+
+@contextlib.contextmanager
+def patched(rng: TapeRNG):
+    pkg = load_package()
+    mods = [sys.modules["sampling.utils"], sys.modules["sampling.kvcache_model"],
+            sys.modules["sampling.speculative_sampling"]]
+    saved = [m.sample for m in mods]
+    ss = sys.modules["sampling.speculative_sampling"]
+    real_torch = ss.torch
+
+    class _TorchProxy:
+        def __getattr__(self, name):
+            return rng.rand if name == "rand" else getattr(real_torch, name)
+
+    try:
+        for m in mods:
+            m.sample = rng.sample
+        ss.torch = _TorchProxy()
+        yield pkg
+    finally:
+        for m, s in zip(mods, saved):
+            m.sample = s
+        ss.torch = real_torch
+
+
+def run_reference(prefix, approx_model, target_model, max_len, gamma, temperature, top_k, top_p,
+                  tape=None, seed=0, eos_token_id=-1, legacy_models=True):
+    """Run the real ``sampling.speculative_sampling`` on the tape.  Returns (tokens, details)."""
+    if tape is None:
+        tape = tape_mod.make_tape(seed, max_len + 1, gamma)
+    rng = TapeRNG(tape, gamma)
+    a = approx_model if legacy_models else LegacyCacheAdapter(approx_model)
+    t = target_model if legacy_models else LegacyCacheAdapter(target_model)
+    with patched(rng) as pkg:
+        out, d = pkg.speculative_sampling(prefix, a, t, eos_token_id, None, max_len, gamma=gamma,
+                                          temperature=temperature, top_k=top_k, top_p=top_p, details=True)
+    return out, d

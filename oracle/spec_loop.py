@@ -1,0 +1,185 @@
+"""Batch-1 restatement of the reference's KV-cached stepping and speculative loop
+(TEST INFRASTRUCTURE ONLY).
+
+* ``OracleStepper``           -> /root/reference/sampling/kvcache_model.py:23-36 (state),
+                                 :141-252 (_forward_with_kvcache, decoder-only branch),
+                                 :255-310 (generate, multi=1), :360-384,429-431 (rollback, choice=None)
+* ``speculative_sampling``    -> /root/reference/sampling/speculative_sampling.py:1934-2043
+* ``speculative_sampling_v2`` -> /root/reference/sampling/speculative_sampling.py:2118-2185
+* ``autoregressive_sampling`` -> /root/reference/sampling/autoregressive_sampling.py:9-61
+
+Randomness comes from a uniform tape (oracle/tape.py) instead of torch's global RNG.
+Works with ``oracle.replay_model.ReplayLM`` (legacy tuple cache) and with stock Hugging Face
+causal LMs (``DynamicCache``; cropped with ``.crop``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import ref_ops, tape as tape_mod
+
+
+def _cached_len(kv) -> int:
+    if hasattr(kv, "get_seq_length"):
+        return int(kv.get_seq_length())
+    return kv[0][0].shape[2]                                                # kvcache_model.py:175
+
+
+def _crop(kv, end_pos: int):
+    if hasattr(kv, "crop"):
+        if _cached_len(kv) > end_pos:
+            kv.crop(end_pos)
+        return kv
+    return tuple((k[:, :, :end_pos, :], v[:, :, :end_pos, :]) for k, v in kv)   # :381-382
+
+
+class OracleStepper:
+    def __init__(self, model, temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0):
+        self.model = model
+        self.kv = None
+        self.hist: Optional[torch.Tensor] = None                            # (seq, V) fp32 probs
+        self.temperature, self.top_k, self.top_p = temperature, top_k, top_p
+
+    @torch.no_grad()
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        if self.kv is None:                                                 # prefill, :151-171
+            out = self.model(ids, use_cache=True)
+        else:                                                               # incremental, :173-214
+            out = self.model(ids[:, _cached_len(self.kv):], past_key_values=self.kv, use_cache=True)
+        logits = out.logits[0].to(torch.float32)
+        rows = [ref_ops.norm_probs(logits[i:i + 1], self.temperature, self.top_k, self.top_p)
+                for i in range(logits.shape[0])]                            # one row per call, :166-168/:235-236
+        new = torch.cat(rows, dim=0)
+        self.hist = new if self.hist is None else torch.cat([self.hist, new], dim=0)   # :246
+        self.kv = out.past_key_values
+        return new[-1]
+
+    def generate(self, ids: torch.Tensor, gamma: int, uniforms) -> torch.Tensor:
+        x = ids
+        for i in range(gamma):                                              # :279-293
+            q = self.forward(x)
+            tok = ref_ops.icdf_sample(q, float(uniforms[i]))
+            x = torch.cat([x, torch.tensor([[tok]], dtype=x.dtype, device=x.device)], dim=1)
+        return x
+
+    def rollback(self, end_pos: int) -> None:                               # :360-431
+        self.kv = _crop(self.kv, end_pos)
+        if self.hist is not None:
+            self.hist = self.hist[:end_pos]
+
+
+@torch.no_grad()
+def speculative_sampling(prefix: torch.Tensor, approx_model, target_model, max_len: int, gamma: int = 4,
+                         temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0,
+                         eos_token_id: Optional[int] = None, tape: Optional[torch.Tensor] = None,
+                         seed: int = 0, residual: str = "raw", record: Optional[list] = None):
+    """Returns (tokens (1, n), details).  One tape row (2*gamma+2 uniforms) per iteration."""
+    assert prefix.shape[0] == 1, "input batch size must be 1"               # :1905
+    seq_len = prefix.shape[1]
+    T = seq_len + max_len
+    if tape is None:
+        tape = tape_mod.make_tape(seed, max_len + 1, gamma)
+    ori_eos = int((prefix == eos_token_id).sum()) if eos_token_id is not None else 0
+    approx = OracleStepper(approx_model, temperature, top_k, top_p)
+    target = OracleStepper(target_model, temperature, top_k, top_p)
+    acc_len: List[int] = []
+    acc_rate: List[float] = []
+    ties = 0
+    min_margin = 1.0
+    it = 0
+    out = prefix
+    while prefix.shape[1] < T:                                              # :1934
+        u_draft, u_discard, u_acc, u_final = tape_mod.split(tape[it], gamma)
+        x = approx.generate(prefix, gamma, u_draft)                         # :1943
+        L = prefix.shape[1]
+        _ = target.generate(x, 1, [u_discard])                              # :1956 (sample discarded)
+        p_rows = target.hist[L - 1:L + gamma]                               # gamma+1 rows
+        q_rows = approx.hist[L - 1:L + gamma - 1]                           # gamma rows
+        draft = x[0, L:L + gamma]
+        n_acc, tok, ratio, t, margin = ref_ops.verify_request(
+            p_rows, q_rows, draft, u_acc.numpy(), float(u_final), strict=False,
+            residual=residual, return_margin=True)
+        ties += t
+        min_margin = min(min_margin, margin)
+        acc_rate.extend(np.minimum(1.0, ratio.astype(np.float64)).tolist())  # :1966-1971
+        acc_len.append(n_acc)                                               # :1991
+        if record is not None:
+            record.append(dict(p=p_rows.clone(), q=q_rows.clone(), draft=draft.clone(),
+                               u_acc=u_acc.clone(), u_final=float(u_final), n_acc=n_acc, tok=tok))
+        n = L + n_acc - 1
+        prefix = x[:, :n + 1]                                               # :1996
+        approx.rollback(n + 1)                                              # :2000
+        target.rollback(n + 1 if n_acc < gamma else n + 2)                  # :2015 / :2023
+        prefix = torch.cat([prefix, torch.tensor([[tok]], dtype=prefix.dtype)], dim=1)   # :2027
+        out = prefix
+        it += 1
+        if eos_token_id is not None:                                        # :2033-2041
+            mask = out == eos_token_id
+            if int(mask.sum()) > ori_eos:
+                keep = torch.cumsum(mask.float(), dim=1) < ori_eos + 1
+                end = int(keep.sum())
+                if end < keep.shape[1]:
+                    keep[:, end] = True
+                out = out[keep][None, :]
+                break
+    details = dict(acc_len=acc_len, acc_rate=float(np.mean(acc_rate)) if acc_rate else 0.0,
+                   iterations=it, target_call_times=it, approx_call_times=it,
+                   exact_ties=ties, min_sample_margin=min_margin)
+    return out, details
+
+
+@torch.no_grad()
+def speculative_sampling_v2(prefix: torch.Tensor, approx_model, target_model, max_len: int, gamma: int = 4,
+                            temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0,
+                            tape: Optional[torch.Tensor] = None, seed: int = 0, residual: str = "raw"):
+    """DeepMind variant without KV cache (full re-forward), strict accept test.  Tape layout as
+    above except that slot ``gamma`` (u_discard) is unused."""
+    assert prefix.shape[0] == 1
+    T = prefix.shape[1] + max_len
+    if tape is None:
+        tape = tape_mod.make_tape(seed, max_len + 1, gamma)
+    acc_len, acc_rate, it = [], [], 0
+
+    def rows_of(model, ids):
+        lg = model(ids).logits[0].to(torch.float32)
+        return torch.cat([ref_ops.norm_probs(lg[i:i + 1], temperature, top_k, top_p) for i in range(lg.shape[0])], 0)
+
+    while prefix.shape[1] < T:                                              # :2118
+        u_draft, _, u_acc, u_final = tape_mod.split(tape[it], gamma)
+        x, L = prefix, prefix.shape[1]
+        for i in range(gamma):                                              # :2123-2128
+            q_last = rows_of(approx_model, x)[-1]
+            tok = ref_ops.icdf_sample(q_last, float(u_draft[i]))
+            x = torch.cat([x, torch.tensor([[tok]], dtype=x.dtype)], dim=1)
+        q = rows_of(approx_model, x[:, :-1])                                # rows of the last draft forward, :2131-2133
+        p = rows_of(target_model, x)                                        # :2137-2140
+        n_acc, tok, ratio, _ = ref_ops.verify_request(p[L - 1:L + gamma], q[L - 1:L + gamma - 1], x[0, L:L + gamma],
+                                                      u_acc.numpy(), float(u_final), strict=True, residual=residual)
+        acc_rate.extend(np.minimum(1.0, ratio.astype(np.float64))[:min(n_acc + 1, gamma)].tolist())   # :2155 (lazy)
+        acc_len.append(n_acc)
+        prefix = torch.cat([x[:, :L + n_acc], torch.tensor([[tok]], dtype=x.dtype)], dim=1)
+        it += 1
+    return prefix, dict(acc_len=acc_len, acc_rate=float(np.mean(acc_rate)) if acc_rate else 0.0, iterations=it)
+
+
+@torch.no_grad()
+def autoregressive_sampling(x: torch.Tensor, model, N: int, eos_token_id: Optional[int] = None,
+                            temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0,
+                            uniforms: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+    """Target-only loop, one uniform per generated token.  autoregressive_sampling.py:9-61."""
+    if uniforms is None:
+        uniforms = tape_mod.make_tape(seed, N, 0).reshape(-1)[:N] if N > 0 else torch.zeros(0)
+        uniforms = torch.rand(N, generator=torch.Generator().manual_seed(int(seed)))
+    kv = None
+    for i in range(N):                                                      # n = len(x) = 1 -> exactly N tokens (:13-21)
+        out = model(x, use_cache=True) if kv is None else model(x[:, -1:], past_key_values=kv, use_cache=True)
+        kv = out.past_key_values
+        probs = ref_ops.norm_probs(out.logits[:, -1, :].to(torch.float32), temperature, top_k, top_p)
+        tok = ref_ops.icdf_sample(probs[0], float(uniforms[i]))
+        x = torch.cat([x, torch.tensor([[tok]], dtype=x.dtype)], dim=1)
+        if eos_token_id is not None and tok == eos_token_id:
+            break
+    return x
