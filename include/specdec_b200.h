@@ -1,0 +1,131 @@
+/* specdec_b200.h — C ABI of libspecdec_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the speculative-decoding draft-and-verify hot path of
+ * ZongyueQin/LLMSpeculativeSampling.  The reference has NO native/FFI boundary of its own (it is pure
+ * Python; its boundary is the `sampling` package), so every entry point below cites the
+ * reference Python code it replaces, as /root/reference/<file>:<lines>.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch tensors in the Python host code);
+ *    the library allocates nothing, frees nothing, keeps no global state besides the sd_set_tuning knobs;
+ *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, never synchronise,
+ *    and are CUDA-graph capturable;
+ *  - return value: SD_OK (0), SD_EINVAL (-1, argument error) or a positive cudaError_t;
+ *    sd_last_error() gives the text (thread local);
+ *  - numerical faults do not fail the call: kernels OR bits into the caller's device word `err_flag`
+ *    (SD_ERR_*), which the host checks once per public-API call and turns into the reference's
+ *    exceptions (RuntimeError('norm logits error') utils.py:207, RuntimeError('prob error')
+ *    utils.py:224, RuntimeError('s') speculative_sampling.py:2046);
+ *  - strides / leading dimensions are in ELEMENTS;
+ *  - inverse-CDF rule for every sampled token (replaces torch.multinomial, utils.py:221):
+ *        e = frexp exponent of the row maximum, w_i = floor(p_i * 2^(40-e)), m = floor(u * 2^24),
+ *        t = (sum_i w_i * m) >> 24, token = first i with w_0 + .. + w_i > t,
+ *        then the reference's guard: if p[token] < 1e-9 take argmax(p) (utils.py:228-230).
+ */
+#ifndef SPECDEC_B200_H_
+#define SPECDEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_VERSION 100
+#define SD_OK 0
+#define SD_EINVAL (-1)
+
+/* logits dtypes */
+#define SD_F32 0
+#define SD_BF16 1
+#define SD_F16 2
+
+/* bits OR-ed into *err_flag by the kernels */
+#define SD_ERR_NORM_LOGITS 1 /* NaN / +inf logit or non-finite probability   -> 'norm logits error' */
+#define SD_ERR_PROB 2        /* no positive weight to sample from, or p < 0   -> 'prob error'        */
+#define SD_ERR_ZERO_Q 4      /* q[drafted token] == 0 (ZeroDivisionError)     -> 's'                 */
+#define SD_ERR_BAD_TOKEN 8   /* drafted token id outside [0, V)                                       */
+
+int sd_version(void);
+const char* sd_last_error(void);
+
+/* Benchmark / test knobs: cluster size (1,2,4,8; 0 = heuristic) and threads per CTA (256/512/1024;
+ * 0 = heuristic) of the norm kernel, cluster size of the verify kernel. */
+void sd_set_tuning(int norm_cluster, int norm_threads, int verify_cluster);
+
+/* Kernel 1 — fused  logits / T -> top-k -> top-p -> softmax  for `rows` rows of V logits.
+ * Replaces sampling/utils.py:152-179 (top_k_top_p_filter) + :182-210 (norm_logits), called once per row
+ * from sampling/kvcache_model.py:166-168 and :235-236.
+ *   logits  (rows, V) of dtype SD_F32/SD_BF16/SD_F16, row stride ld_in; read once (TMA bulk copy when
+ *           base and row stride are 16-byte aligned, plain loads otherwise); not modified
+ *   top_k   <= 0 disables; ties with the k-th value are kept (utils.py:169)
+ *   top_p   <= 0 disables; keeps the smallest prefix of the descending order whose mass exceeds top_p,
+ *           crossing entry included; equal values are ordered by ascending index (utils.py:171-178)
+ *   probs   (rows, V) fp32, row stride ld_out: exp(log_softmax(filtered)) (utils.py:199), 0 outside
+ * Sets SD_ERR_NORM_LOGITS where the reference raises 'norm logits error' (utils.py:203-207). */
+int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
+                  float top_p, float* probs, int64_t ld_out, int* err_flag, void* stream);
+
+/* Kernel 1b — same, plus one inverse-CDF sample per row from the uniform u[row] (draft step):
+ * replaces norm_logits + sample(q) of sampling/kvcache_model.py:280-283 and
+ * sampling/autoregressive_sampling.py:41-44.  `probs` may be NULL (token only). */
+int sd_norm_sample(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
+                   float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out, int* err_flag,
+                   void* stream);
+
+/* Test hook: as sd_norm_sample (u / tok_out may be NULL) but forces the general sort-free path that
+ * normally only serves top_k = 0, top_k > 128 or rows with massive ties. */
+int sd_norm_general(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
+                    int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                    int* err_flag, void* stream);
+
+/* sample — one inverse-CDF draw per row of non-negative weights.  Replaces sampling/utils.py:213-233. */
+int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const float* u, int64_t* tok_out, int* err_flag,
+              void* stream);
+
+/* Kernel 2 — fused verify for B requests.  Replaces sampling/speculative_sampling.py:1966-2027 (accept
+ * loop :1975-1990, residual sample(max_fn(p-q)) :2005-2015 with its fall-back to sample(p) :2009-2010,
+ * bonus sample :2016-2023, append :2027) and, with strict = 1, speculative_sampling_v2 :2152-2181.
+ *   p_probs  target probabilities, request b row i at p_probs + b*p_req_stride + i*p_row_stride, i = 0..gamma
+ *   q_probs  draft probabilities, rows i = 0..gamma-1
+ *   draft_tok (B, gamma) int64 drafted ids, row stride draft_stride
+ *   u_acc    (B, gamma) accept uniforms (row stride u_acc_stride), u_final (B,) resample/bonus uniform
+ *   strict   0: accept iff !(u > p/q)  (:1981)      1: accept iff u < min(1, p/q)  (:2156)
+ *   n_accepted (B,) int32, next_tok (B,) int64
+ *   ratios   optional (B, gamma) fp32 p/q of every drafted token (acc_rate statistic, :1966-1971)
+ *   tie_count optional device int32, += number of tested positions with u == threshold exactly
+ *   tokens / seq_len  optional fused append: tokens[b, seq_len[b] + n_acc] = next_tok;
+ *            seq_len[b] += n_acc + 1  — with static caches this counter write IS the rollback of
+ *            sampling/kvcache_model.py:360-431 (approx rollback(n+1) :2000, target :2015/:2023)
+ *   active   optional (B,) int32; requests with active[b] == 0 are skipped entirely. */
+int sd_verify(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const float* q_probs,
+              int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
+              const float* u_acc, int64_t u_acc_stride, const float* u_final, int B, int gamma, int64_t V, int strict,
+              int32_t* n_accepted, int64_t* next_tok, float* ratios, int32_t* tie_count, int64_t* tokens,
+              int64_t tokens_stride, int32_t* seq_len, const int32_t* active, int* err_flag, void* stream);
+
+/* max_fn — out = max(x,0) / (sum(max(x,0)) + 1e-6) per row.  Replaces sampling/utils.py:236-245. */
+int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream);
+
+/* Kernel 3a — static KV-cache append at per-request offsets: for every request b, head h, new row j:
+ *   cache[b, h, write_pos[b] + j, :] = new[b, h, j, :]   for both K and V  (caches are (B, H, S, D) contiguous,
+ *   new tensors have element strides stride_b/h/q and a contiguous last dim).  Replaces the torch.cat growth of
+ *   the legacy cache (sampling/models/modeling_llama.py:337-338) and makes KVCacheModel.rollback
+ *   (sampling/kvcache_model.py:379-384) a no-op on data: stale rows are overwritten by the next append. */
+int sd_kv_append(const void* k_new, const void* v_new, int64_t stride_b, int64_t stride_h, int64_t stride_q,
+                 void* k_cache, void* v_cache, const int32_t* write_pos, int B, int H, int q, int D, int S,
+                 int elem_size, void* stream);
+
+/* Kernel 3b — per-step input builder for the graph-captured draft/target steps.  For request b the step
+ * consumes the q tokens at positions start..start+q-1, start = seq_len[b] + offset; prev_tok (optional)
+ * is stored at the last of them first (token append of sampling/kvcache_model.py:293).  Emits input_ids
+ * (B,q), position_ids (B,q), write_pos (B,) and mask (B,1,q,S) uint8: key s visible to query j iff
+ * s <= start + j.  Replaces `input_ids[:, cached_len:]` (kvcache_model.py:175,206). */
+int sd_build_step(int64_t* tokens, int64_t tokens_stride, const int32_t* seq_len, int offset, int q,
+                  const int64_t* prev_tok, int B, int S, int64_t* input_ids, int64_t* position_ids, int32_t* write_pos,
+                  uint8_t* mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECDEC_B200_H_ */

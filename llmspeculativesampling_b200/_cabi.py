@@ -1,0 +1,54 @@
+"""ctypes binding of include/specdec_b200.h — the only way the Python host code reaches the kernels.
+
+There is deliberately no fallback: if the shared library is missing or a CUDA device is absent, the
+product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspecdec_b200.so")
+
+i32, i64, f32, vp = C.c_int, C.c_int64, C.c_float, C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/specdec_b200.h declares
+SIGNATURES = {
+    "sd_version": (i32, []),
+    "sd_last_error": (C.c_char_p, []),
+    "sd_set_tuning": (None, [i32, i32, i32]),
+    "sd_norm_probs": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp]),
+    "sd_norm_sample": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp]),
+    "sd_norm_general": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp]),
+    "sd_sample": (i32, [vp, i64, i64, i64, vp, vp, vp, vp]),
+    "sd_verify": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, vp, i32, i32, i64, i32,
+                        vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]),
+    "sd_max_fn": (i32, [vp, i64, i64, i64, vp, i64, vp]),
+    "sd_kv_append": (i32, [vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "sd_build_step": (i32, [vp, i64, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m llmspeculativesampling_b200.build` "
+                "(there is no CPU or PyTorch fallback for the speculative-decoding kernels)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().sd_last_error().decode()
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")

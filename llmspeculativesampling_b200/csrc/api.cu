@@ -1,0 +1,140 @@
+// C ABI of libspecdec_b200.so — see include/specdec_b200.h for the contract of every entry point.
+// All pointers are device pointers owned by the caller; nothing is allocated, freed or synchronised
+// here, every call is asynchronous on the caller's stream and CUDA-graph capturable.
+#include "specdec_internal.h"
+#include "../../include/specdec_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+thread_local char g_err[256] = "";
+int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+  if (ce != cudaSuccess)
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(ce));
+  else
+    snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+int done(const char* what, cudaError_t ce) {
+  if (ce == cudaSuccess) return SD_OK;
+  return fail(static_cast<int>(ce), what, ce);
+}
+}  // namespace
+
+extern "C" {
+
+int sd_version(void) { return SD_VERSION; }
+const char* sd_last_error(void) { return g_err; }
+
+void sd_set_tuning(int norm_cluster, int norm_threads, int verify_cluster) {
+  sd::set_norm_tuning(norm_cluster, norm_threads);
+  sd::set_verify_tuning(verify_cluster);
+}
+
+static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
+                       int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                       int* err_flag, int force_general, void* stream) {
+  if (rows == 0) return SD_OK;
+  if (logits == nullptr || err_flag == nullptr || rows < 0 || V <= 0 || ld_in < V) return fail(SD_EINVAL, "sd_norm: bad logits/shape");
+  if (!(temperature > 0.f) || std::isinf(temperature)) return fail(SD_EINVAL, "sd_norm: temperature must be finite and > 0");
+  if (probs != nullptr && ld_out < V) return fail(SD_EINVAL, "sd_norm: ld_out < V");
+  if ((u == nullptr) != (tok_out == nullptr)) return fail(SD_EINVAL, "sd_norm: u and tok_out go together");
+  if (probs == nullptr && u == nullptr) return fail(SD_EINVAL, "sd_norm: nothing to produce");
+  if (V >= (1LL << 24) || rows >= (1LL << 28)) return fail(SD_EINVAL, "sd_norm: shape too large");
+  sd::NormParams p = {};
+  p.logits = logits; p.ld_in = ld_in; p.V = V;
+  p.temperature = temperature; p.top_k = top_k < 0 ? 0 : top_k; p.top_p = top_p;
+  p.probs = probs; p.ld_out = ld_out;
+  p.u = u; p.tok_out = reinterpret_cast<long long*>(tok_out);
+  p.err_flag = err_flag; p.force_general = force_general;
+  return done("sd_norm launch", sd::launch_norm(p, dtype, static_cast<int>(rows), static_cast<cudaStream_t>(stream)));
+}
+
+int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
+                  float top_p, float* probs, int64_t ld_out, int* err_flag, void* stream) {
+  if (probs == nullptr) return fail(SD_EINVAL, "sd_norm_probs: probs is null");
+  return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, nullptr, nullptr,
+                     err_flag, 0, stream);
+}
+
+int sd_norm_sample(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
+                   float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out, int* err_flag,
+                   void* stream) {
+  if (u == nullptr || tok_out == nullptr) return fail(SD_EINVAL, "sd_norm_sample: u/tok_out is null");
+  return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, err_flag, 0,
+                     stream);
+}
+
+int sd_norm_general(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
+                    int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                    int* err_flag, void* stream) {
+  return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, err_flag, 1,
+                     stream);
+}
+
+int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const float* u, int64_t* tok_out, int* err_flag,
+              void* stream) {
+  if (rows == 0) return SD_OK;
+  if (probs == nullptr || u == nullptr || tok_out == nullptr || err_flag == nullptr || V <= 0 || ld < V)
+    return fail(SD_EINVAL, "sd_sample: bad argument");
+  sd::VerifyParams p = {};
+  p.p = probs; p.p_req_stride = ld; p.p_row_stride = 0;
+  p.u_final = u; p.B = static_cast<int>(rows); p.gamma = 0; p.V = V;
+  p.next_tok = reinterpret_cast<long long*>(tok_out); p.err_flag = err_flag;
+  return done("sd_sample launch", sd::launch_verify(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sd_verify(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const float* q_probs,
+              int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
+              const float* u_acc, int64_t u_acc_stride, const float* u_final, int B, int gamma, int64_t V, int strict,
+              int32_t* n_accepted, int64_t* next_tok, float* ratios, int32_t* tie_count, int64_t* tokens,
+              int64_t tokens_stride, int32_t* seq_len, const int32_t* active, int* err_flag, void* stream) {
+  if (B == 0) return SD_OK;
+  if (!p_probs || !q_probs || !draft_tok || !u_acc || !u_final || !n_accepted || !next_tok || !err_flag)
+    return fail(SD_EINVAL, "sd_verify: null argument");
+  if (B < 0 || gamma < 1 || gamma > 32 || V <= 0 || V >= (1LL << 24)) return fail(SD_EINVAL, "sd_verify: bad shape (1 <= gamma <= 32)");
+  if ((tokens == nullptr) != (seq_len == nullptr)) return fail(SD_EINVAL, "sd_verify: tokens and seq_len go together");
+  sd::VerifyParams p = {};
+  p.p = p_probs; p.p_req_stride = p_req_stride; p.p_row_stride = p_row_stride;
+  p.q = q_probs; p.q_req_stride = q_req_stride; p.q_row_stride = q_row_stride;
+  p.draft = reinterpret_cast<const long long*>(draft_tok); p.draft_stride = draft_stride;
+  p.u_acc = u_acc; p.u_acc_stride = u_acc_stride; p.u_final = u_final;
+  p.B = B; p.gamma = gamma; p.V = V; p.strict = strict;
+  p.n_accepted = n_accepted; p.next_tok = reinterpret_cast<long long*>(next_tok); p.ratios = ratios;
+  p.tie_count = tie_count; p.err_flag = err_flag;
+  p.tokens = reinterpret_cast<long long*>(tokens); p.tokens_stride = tokens_stride; p.seq_len = seq_len; p.active = active;
+  return done("sd_verify launch", sd::launch_verify(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream) {
+  if (rows == 0) return SD_OK;
+  if (!x || !out || V <= 0 || ld < V || ld_out < V) return fail(SD_EINVAL, "sd_max_fn: bad argument");
+  return done("sd_max_fn launch", sd::launch_max_fn(x, rows, V, ld, out, ld_out, static_cast<cudaStream_t>(stream)));
+}
+
+int sd_kv_append(const void* k_new, const void* v_new, int64_t stride_b, int64_t stride_h, int64_t stride_q,
+                 void* k_cache, void* v_cache, const int32_t* write_pos, int B, int H, int q, int D, int S,
+                 int elem_size, void* stream) {
+  if (!k_new || !v_new || !k_cache || !v_cache || !write_pos) return fail(SD_EINVAL, "sd_kv_append: null argument");
+  if (elem_size != 2 && elem_size != 4) return fail(SD_EINVAL, "sd_kv_append: elem_size must be 2 or 4");
+  if ((D * elem_size) % 16 != 0 || (stride_b * elem_size) % 16 || (stride_h * elem_size) % 16 || (stride_q * elem_size) % 16)
+    return fail(SD_EINVAL, "sd_kv_append: rows must be 16-byte aligned");
+  return done("sd_kv_append launch",
+              sd::launch_kv_append(k_new, v_new, stride_b, stride_h, stride_q, k_cache, v_cache, write_pos, B, H, q, D,
+                                   S, elem_size, static_cast<cudaStream_t>(stream)));
+}
+
+int sd_build_step(int64_t* tokens, int64_t tokens_stride, const int32_t* seq_len, int offset, int q,
+                  const int64_t* prev_tok, int B, int S, int64_t* input_ids, int64_t* position_ids, int32_t* write_pos,
+                  uint8_t* mask, void* stream) {
+  if (!tokens || !seq_len || !input_ids || !position_ids || !write_pos) return fail(SD_EINVAL, "sd_build_step: null argument");
+  return done("sd_build_step launch",
+              sd::launch_build_step(reinterpret_cast<long long*>(tokens), tokens_stride, seq_len, offset, q,
+                                    reinterpret_cast<const long long*>(prev_tok), B, S,
+                                    reinterpret_cast<long long*>(input_ids), reinterpret_cast<long long*>(position_ids),
+                                    write_pos, mask, static_cast<cudaStream_t>(stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// Internal launch interfaces between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sd {
+
+struct NormParams {
+  const void* logits; long long ld_in; long long V;
+  float temperature; int top_k; float top_p;
+  float* probs; long long ld_out;          // nullable: no dense write (sample only)
+  const float* u; long long* tok_out;      // nullable pair: per-row uniform -> sampled token
+  int* err_flag;
+  // filled by the launcher
+  int cluster, slice_elems, slice_smem_bytes, use_tma, vec_out;
+  int force_general;                       // test knob: skip the fast top-k path
+};
+cudaError_t launch_norm(const NormParams& p, int dtype, int rows, cudaStream_t st);
+void set_norm_tuning(int cluster, int threads);
+
+struct VerifyParams {
+  const float* p; long long p_req_stride, p_row_stride;     // target probs  (B, gamma+1, V)
+  const float* q; long long q_req_stride, q_row_stride;     // draft probs   (B, gamma,   V); null => plain sample of p row 0
+  const long long* draft; long long draft_stride;           // drafted ids   (B, gamma)
+  const float* u_acc; long long u_acc_stride;               // (B, gamma)
+  const float* u_final;                                     // (B,)
+  int B, gamma; long long V; int strict;
+  int* n_accepted; long long* next_tok; float* ratios;      // outputs (ratios nullable, (B, gamma))
+  int* tie_count; int* err_flag;
+  // optional fused token append / length update ("rollback" of the static caches is this counter write)
+  long long* tokens; long long tokens_stride; int* seq_len; const int* active;
+  // filled by the launcher
+  int cluster, slice_elems, use_tma;
+};
+cudaError_t launch_verify(const VerifyParams& p, cudaStream_t st);
+void set_verify_tuning(int cluster);
+
+cudaError_t launch_max_fn(const float* x, long long rows, long long V, long long ld, float* out, long long ld_out,
+                          cudaStream_t st);
+cudaError_t launch_kv_append(const void* k_new, const void* v_new, long long sb, long long sh, long long sq,
+                             void* k_cache, void* v_cache, const int* pos, int B, int H, int q, int D, int S,
+                             int elem_size, cudaStream_t st);
+cudaError_t launch_build_step(long long* tokens, long long tokens_stride, const int* seq_len, int offset, int q,
+                              const long long* prev_tok, int B, int S, long long* input_ids, long long* position_ids,
+                              int* write_pos, unsigned char* mask, cudaStream_t st);
+
+}  // namespace sd

@@ -1,0 +1,198 @@
+// Kernel 2: fused verify — accept test, first rejection (warp ballot), residual max(0, p - q) with
+// its normaliser, inverse-CDF draw from a pre-drawn uniform, token append and length update.
+// One thread-block cluster per request; the two probability rows that matter (p_n and q_n) are
+// staged once through 1-D TMA bulk copies and never re-read from HBM.
+//
+// Replaces /root/reference/sampling/speculative_sampling.py:1966-2027 (accept loop with ~7 host
+// syncs per drafted token, max_fn + sample, rollback bookkeeping, torch.cat append) and, with
+// strict = 1, the accept rule of speculative_sampling_v2 (:2152-2181).  With q == nullptr the
+// kernel is the drop-in for sampling/utils.py:213-233 (sample) on rows of p.
+#include "rowops.cuh"
+#include "specdec_internal.h"
+
+namespace sd {
+
+template <int THREADS>
+struct alignas(16) VerifyShared {
+  RowScratch<THREADS> rs;
+  uint64_t bar;
+  int n_acc;
+};
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParams p) {
+  constexpr int PV = 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int slice_bytes = p.slice_elems * 4;
+  float* ps = reinterpret_cast<float*>(smem_raw);
+  float* qs = reinterpret_cast<float*>(smem_raw + slice_bytes);
+  VerifyShared<THREADS>& sh = *reinterpret_cast<VerifyShared<THREADS>*>(smem_raw + 2 * slice_bytes);
+  RowCtx<THREADS> cx(&sh.rs, p.cluster);
+  const int tid = cx.tid, lane = cx.lane, warp = cx.warp, C = cx.C;
+  const int b = blockIdx.x / C;
+  if (p.active != nullptr && p.active[b] == 0) return;       // whole cluster leaves together
+  const int V = static_cast<int>(p.V);
+  const int gamma = p.gamma;
+  const bool has_q = p.q != nullptr;
+
+  if (tid == 0 && p.use_tma) { mbar_init(&sh.bar, 1); fence_barrier_init(); }
+
+  // ---- accept scan: lane i tests drafted token i (speculative_sampling.py:1975-1990)
+  if (warp == 0) {
+    int n_acc = 0;
+    if (has_q) {
+      bool acc = true, tie = false;
+      float ratio = 0.f;
+      if (lane < gamma) {
+        long long tok = p.draft[b * p.draft_stride + lane];
+        if (tok < 0 || tok >= V) { atomicOr(p.err_flag, kErrBadToken); tok = 0; }
+        const float pv = p.p[b * p.p_req_stride + lane * p.p_row_stride + tok];
+        const float qv = p.q[b * p.q_req_stride + lane * p.q_row_stride + tok];
+        if (qv == 0.f) atomicOr(p.err_flag, kErrZeroQ);
+        ratio = __fdiv_rn(pv, qv);
+        const float u = p.u_acc[b * p.u_acc_stride + lane];
+        const float thr = p.strict ? fminf(1.0f, ratio) : ratio;
+        acc = p.strict ? (u < thr) : !(u > thr);
+        tie = (u == thr);
+        if (cx.crank == 0 && p.ratios != nullptr) p.ratios[b * gamma + lane] = ratio;
+      }
+      const unsigned rej = __ballot_sync(0xffffffffu, !acc);
+      n_acc = rej ? (__ffs(rej) - 1) : gamma;
+      if (cx.crank == 0 && p.tie_count != nullptr && tie && lane < gamma && lane <= n_acc) atomicAdd(p.tie_count, 1);
+    }
+    if (lane == 0) sh.n_acc = n_acc;
+  }
+  __syncthreads();
+  const int n_acc = sh.n_acc;
+  bool use_q = has_q && n_acc < gamma;
+
+  // ---- stage this CTA's slice of p_n (and q_n)
+  const long long start = static_cast<long long>(cx.crank) * p.slice_elems;
+  const int n = max(0, min(p.slice_elems, V - static_cast<int>(start)));
+  const int n_vec = (n + PV - 1) / PV;
+  const float* prow = p.p + b * p.p_req_stride + (has_q ? n_acc : 0) * p.p_row_stride + start;
+  const float* qrow = use_q ? p.q + b * p.q_req_stride + n_acc * p.q_row_stride + start : nullptr;
+  if (p.use_tma) {
+    if (tid == 0 && n > 0) {
+      const uint32_t bytes = static_cast<uint32_t>(n) * 4u;
+      mbar_expect_tx(&sh.bar, use_q ? 2u * bytes : bytes);
+      tma_load_1d(ps, prow, bytes, &sh.bar);
+      if (use_q) tma_load_1d(qs, qrow, bytes, &sh.bar);
+    }
+    if (n > 0) mbar_wait(&sh.bar, 0);
+  } else {
+    for (int i = tid; i < n_vec * PV; i += THREADS) {
+      ps[i] = i < n ? prow[i] : 0.f;
+      if (use_q) qs[i] = i < n ? qrow[i] : 0.f;
+    }
+    __syncthreads();
+  }
+
+  // weights of one 16-byte vector: residual max(0, p - q)  (utils.py:240) or the target row itself
+  auto vecw = [&](int v, float (&w)[PV]) {
+    const float4 a = reinterpret_cast<const float4*>(ps)[v];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    if (use_q) {
+      const float4 c = reinterpret_cast<const float4*>(qs)[v];
+      w[0] = fmaxf(w[0] - c.x, 0.f); w[1] = fmaxf(w[1] - c.y, 0.f);
+      w[2] = fmaxf(w[2] - c.z, 0.f); w[3] = fmaxf(w[3] - c.w, 0.f);
+    }
+  };
+  unsigned long long best = 0ull;
+  float rmax = 0.f;
+  int argmax = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    unsigned long long mine = 0ull;
+    bool bad = false;
+    for (int v = tid; v < n_vec; v += THREADS) {
+      float w[PV];
+      vecw(v, w);
+#pragma unroll
+      for (int j = 0; j < PV; ++j) {
+        const int g = static_cast<int>(start) + v * PV + j;
+        bad |= !(w[j] >= 0.f) || isinf(w[j]);
+        if (w[j] > 0.f) {
+          const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(g));
+          mine = pk > mine ? pk : mine;
+        }
+      }
+    }
+    if (bad) atomicOr(p.err_flag, kErrEmptyRow);               // negative / NaN / inf weights: 'prob error'
+    best = cx.allreduce_max(mine);
+    if (best != 0ull || !use_q || p.strict) break;
+    use_q = false;                                             // empty residual: resample from p_n (:2009-2010)
+  }
+  if (best == 0ull) {
+    if (tid == 0 && cx.crank == 0) {
+      atomicOr(p.err_flag, kErrEmptyRow);
+      p.next_tok[b] = 0;
+      if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc;
+    }
+  } else {
+    rmax = key2f(static_cast<uint32_t>(best >> 32));
+    argmax = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffu));
+    unsigned long long total = 0ull;
+    float psel = 1.f;
+    const int tok = cluster_icdf<PV, THREADS>(cx, n_vec, start, rmax, p.u_final[b], vecw, &total, &psel);
+    if (tok >= 0) {
+      float guard_val = psel;
+      if (use_q) {                                             // sample(max_fn(p - q)): guard sees the normalised value
+        const float s = ldexpf(__ull2float_rn(total), frexp_exp(rmax) - kScaleBits);
+        guard_val = __fdiv_rn(psel, s + 1e-6f);
+      }
+      const long long out = guard_val < kProbGuard ? argmax : tok;
+      p.next_tok[b] = out;
+      if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc;
+      if (p.tokens != nullptr) {                               // append + "rollback": one counter write
+        const int L = p.seq_len[b];
+        p.tokens[b * p.tokens_stride + L + n_acc] = out;
+        p.seq_len[b] = L + n_acc + 1;
+      }
+    }
+  }
+  if (C > 1) cx.cluster.sync();
+}
+
+static int g_verify_cluster = 0;
+void set_verify_tuning(int cluster) { g_verify_cluster = cluster; }
+
+cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
+  VerifyParams p = pin;
+  constexpr int THREADS = 256;
+  if (p.gamma > 32 || (p.q != nullptr && p.gamma < 1)) return cudaErrorInvalidValue;
+  const long long row_bytes = p.V * 4;
+  int C = 1;
+  while (C < kMaxCluster && (row_bytes + C - 1) / C > 32 * 1024) C <<= 1;
+  while (C < kMaxCluster && static_cast<long long>(p.B) * C < 148 && row_bytes / (2 * C) >= 4096) C <<= 1;
+  if (g_verify_cluster > 0) C = g_verify_cluster;
+  long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
+  while (C > 1 && slice * (C - 1) >= p.V) { C >>= 1; slice = ((p.V + C - 1) / C + 127) & ~127LL; }
+  p.cluster = C;
+  p.slice_elems = static_cast<int>(slice);
+  auto al = [](const void* ptr, long long s1, long long s2) {
+    return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && s1 % 4 == 0 && s2 % 4 == 0;
+  };
+  p.use_tma = (al(p.p, p.p_req_stride, p.p_row_stride) && (p.q == nullptr || al(p.q, p.q_req_stride, p.q_row_stride)) &&
+               p.V % 4 == 0) ? 1 : 0;
+  const size_t smem = static_cast<size_t>(slice) * 8 + sizeof(VerifyShared<THREADS>);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  auto kern = verify_kernel<THREADS, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(p.B) * C);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+}  // namespace sd

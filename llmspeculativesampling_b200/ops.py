@@ -1,0 +1,207 @@
+"""Tensor-level wrappers over the C ABI (include/specdec_b200.h).
+
+Every function takes CUDA tensors, launches on torch's current stream and returns without
+synchronising.  Numerical faults are accumulated in a device-side flag word (`ErrFlag`) that the
+caller checks when it wants to (once per public-API call), mirroring where the reference raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+SD_F32, SD_BF16, SD_F16 = 0, 1, 2
+_DT = {torch.float32: SD_F32, torch.bfloat16: SD_BF16, torch.float16: SD_F16}
+
+ERR_NORM_LOGITS, ERR_PROB, ERR_ZERO_Q, ERR_BAD_TOKEN = 1, 2, 4, 8
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the speculative-decoding kernels have no CPU path")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class ErrFlag:
+    """Device int32 word the kernels OR error bits into."""
+
+    def __init__(self, device):
+        self.t = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+    def check(self) -> None:
+        """Synchronising read; raises the reference's exceptions and clears the flag."""
+        bits = int(self.t.item())
+        if bits == 0:
+            return
+        self.t.zero_()
+        if bits & ERR_NORM_LOGITS:
+            raise RuntimeError("norm logits error")          # reference sampling/utils.py:207
+        if bits & ERR_PROB:
+            raise RuntimeError("prob error")                 # reference sampling/utils.py:224
+        raise RuntimeError("s")                              # reference speculative_sampling.py:2046
+
+
+_flags = {}
+
+
+def default_flag(device) -> ErrFlag:
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _flags:
+        _flags[key] = ErrFlag(torch.device("cuda", key))
+    return _flags[key]
+
+
+def set_tuning(norm_cluster: int = 0, norm_threads: int = 0, verify_cluster: int = 0) -> None:
+    _cabi.load().sd_set_tuning(norm_cluster, norm_threads, verify_cluster)
+
+
+def _rows2d(logits: torch.Tensor) -> torch.Tensor:
+    if logits.dim() != 2:
+        raise AssertionError("logits must be 2-D (rows, vocab)")      # reference utils.py:194
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    return logits
+
+
+def norm_probs(logits: torch.Tensor, temperature: float, top_k: int, top_p: float,
+               out: Optional[torch.Tensor] = None, err: Optional[ErrFlag] = None,
+               general: bool = False) -> torch.Tensor:
+    """(rows, V) logits (fp32/bf16/fp16) -> (rows, V) fp32 probabilities.  Kernel 1."""
+    _require_cuda(logits, "logits")
+    x = _rows2d(logits)
+    rows, V = x.shape
+    if out is None:
+        out = torch.empty(rows, V, dtype=torch.float32, device=x.device)
+    assert out.dtype == torch.float32 and out.shape == (rows, V) and out.stride(1) == 1
+    err = err or default_flag(x.device)
+    lib = _cabi.load()
+    k = int(top_k) if top_k else 0
+    p = float(top_p) if top_p else 0.0
+    if general:
+        rc = lib.sd_norm_general(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), k, p,
+                                 out.data_ptr(), out.stride(0), None, None, err.ptr(), _stream())
+    else:
+        rc = lib.sd_norm_probs(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), k, p,
+                               out.data_ptr(), out.stride(0), err.ptr(), _stream())
+    _cabi.check(rc, "sd_norm_probs")
+    return out
+
+
+def norm_sample(logits: torch.Tensor, temperature: float, top_k: int, top_p: float, u: torch.Tensor,
+                probs_out: Optional[torch.Tensor] = None, tok_out: Optional[torch.Tensor] = None,
+                err: Optional[ErrFlag] = None, general: bool = False) -> torch.Tensor:
+    """Kernel 1b: probabilities (optional, written to probs_out) and one sampled token per row."""
+    _require_cuda(logits, "logits")
+    x = _rows2d(logits)
+    rows, V = x.shape
+    assert u.is_cuda and u.dtype == torch.float32 and u.numel() == rows and u.is_contiguous()
+    if tok_out is None:
+        tok_out = torch.empty(rows, dtype=torch.int64, device=x.device)
+    assert tok_out.dtype == torch.int64 and tok_out.numel() == rows and tok_out.is_contiguous()
+    if probs_out is not None:
+        assert probs_out.dtype == torch.float32 and probs_out.shape == (rows, V) and probs_out.stride(1) == 1
+    err = err or default_flag(x.device)
+    fn = _cabi.load().sd_norm_general if general else _cabi.load().sd_norm_sample
+    rc = fn(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), int(top_k or 0), float(top_p or 0.0),
+            _ptr(probs_out), probs_out.stride(0) if probs_out is not None else V, u.data_ptr(), tok_out.data_ptr(),
+            err.ptr(), _stream())
+    _cabi.check(rc, "sd_norm_sample")
+    return tok_out
+
+
+def sample_rows(probs: torch.Tensor, u: torch.Tensor, tok_out: Optional[torch.Tensor] = None,
+                err: Optional[ErrFlag] = None) -> torch.Tensor:
+    """One inverse-CDF draw per row of non-negative fp32 weights."""
+    _require_cuda(probs, "probs")
+    x = _rows2d(probs)
+    if x.dtype != torch.float32:
+        x = x.float()
+    rows, V = x.shape
+    assert u.is_cuda and u.dtype == torch.float32 and u.numel() == rows and u.is_contiguous()
+    if tok_out is None:
+        tok_out = torch.empty(rows, dtype=torch.int64, device=x.device)
+    err = err or default_flag(x.device)
+    rc = _cabi.load().sd_sample(x.data_ptr(), rows, V, x.stride(0), u.data_ptr(), tok_out.data_ptr(), err.ptr(), _stream())
+    _cabi.check(rc, "sd_sample")
+    return tok_out
+
+
+def max_fn(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "x")
+    squeeze = x.dim() == 1
+    x2 = x.unsqueeze(0) if squeeze else x
+    x2 = _rows2d(x2.float() if x2.dtype != torch.float32 else x2)
+    out = torch.empty_like(x2)
+    rc = _cabi.load().sd_max_fn(x2.data_ptr(), x2.shape[0], x2.shape[1], x2.stride(0), out.data_ptr(), out.stride(0), _stream())
+    _cabi.check(rc, "sd_max_fn")
+    return out[0] if squeeze else out
+
+
+def verify(p_probs: torch.Tensor, q_probs: torch.Tensor, draft_tok: torch.Tensor, u_acc: torch.Tensor,
+           u_final: torch.Tensor, strict: bool = False, n_accepted: Optional[torch.Tensor] = None,
+           next_tok: Optional[torch.Tensor] = None, ratios: Optional[torch.Tensor] = None,
+           tie_count: Optional[torch.Tensor] = None, tokens: Optional[torch.Tensor] = None,
+           seq_len: Optional[torch.Tensor] = None, active: Optional[torch.Tensor] = None,
+           err: Optional[ErrFlag] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Kernel 2.  p_probs (B, gamma+1, V), q_probs (B, gamma, V) fp32 (last dim contiguous),
+    draft_tok (B, gamma) int64, u_acc (B, gamma), u_final (B,).  Returns (n_accepted, next_tok)."""
+    _require_cuda(p_probs, "p_probs")
+    B, g1, V = p_probs.shape
+    gamma = g1 - 1
+    assert q_probs.shape == (B, gamma, V) and p_probs.dtype == q_probs.dtype == torch.float32
+    assert p_probs.stride(2) == 1 and q_probs.stride(2) == 1
+    assert draft_tok.dtype == torch.int64 and draft_tok.shape == (B, gamma) and draft_tok.stride(1) == 1
+    assert u_acc.dtype == torch.float32 and u_acc.shape == (B, gamma) and u_acc.stride(1) == 1
+    assert u_final.dtype == torch.float32 and u_final.numel() == B and u_final.is_contiguous()
+    dev = p_probs.device
+    if n_accepted is None:
+        n_accepted = torch.empty(B, dtype=torch.int32, device=dev)
+    if next_tok is None:
+        next_tok = torch.empty(B, dtype=torch.int64, device=dev)
+    err = err or default_flag(dev)
+    rc = _cabi.load().sd_verify(
+        p_probs.data_ptr(), p_probs.stride(0), p_probs.stride(1), q_probs.data_ptr(), q_probs.stride(0), q_probs.stride(1),
+        draft_tok.data_ptr(), draft_tok.stride(0), u_acc.data_ptr(), u_acc.stride(0), u_final.data_ptr(),
+        B, gamma, V, 1 if strict else 0, n_accepted.data_ptr(), next_tok.data_ptr(), _ptr(ratios), _ptr(tie_count),
+        _ptr(tokens), tokens.stride(0) if tokens is not None else 0, _ptr(seq_len), _ptr(active), err.ptr(), _stream())
+    _cabi.check(rc, "sd_verify")
+    return n_accepted, next_tok
+
+
+def kv_append(k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
+              write_pos: torch.Tensor) -> None:
+    """cache[b, h, write_pos[b] + j] = new[b, h, j] for K and V.  new: (B, H, q, D) any strides with a
+    contiguous last dim; caches: (B, H, S, D) contiguous."""
+    B, H, q, D = k_new.shape
+    S = k_cache.shape[2]
+    assert k_cache.is_contiguous() and v_cache.is_contiguous() and k_cache.shape == (B, H, S, D)
+    if k_new.stride(3) != 1 or v_new.stride() != k_new.stride():
+        k_new, v_new = k_new.contiguous(), v_new.contiguous()
+    if k_new.dtype != k_cache.dtype:
+        k_new, v_new = k_new.to(k_cache.dtype), v_new.to(v_cache.dtype)
+    rc = _cabi.load().sd_kv_append(k_new.data_ptr(), v_new.data_ptr(), k_new.stride(0), k_new.stride(1), k_new.stride(2),
+                                   k_cache.data_ptr(), v_cache.data_ptr(), write_pos.data_ptr(), B, H, q, D, S,
+                                   k_cache.element_size(), _stream())
+    _cabi.check(rc, "sd_kv_append")
+
+
+def build_step(tokens: torch.Tensor, seq_len: torch.Tensor, offset: int, q: int, prev_tok: Optional[torch.Tensor],
+               S: int, input_ids: torch.Tensor, position_ids: torch.Tensor, write_pos: torch.Tensor,
+               mask: Optional[torch.Tensor]) -> None:
+    B = tokens.shape[0]
+    rc = _cabi.load().sd_build_step(tokens.data_ptr(), tokens.stride(0), seq_len.data_ptr(), int(offset), int(q),
+                                    _ptr(prev_tok), B, int(S), input_ids.data_ptr(), position_ids.data_ptr(),
+                                    write_pos.data_ptr(), _ptr(mask), _stream())
+    _cabi.check(rc, "sd_build_step")
