@@ -24,9 +24,8 @@ __global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParam
   constexpr int PV = 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int slice_bytes = p.slice_elems * 4;
-  float* ps = reinterpret_cast<float*>(smem_raw);
-  float* qs = reinterpret_cast<float*>(smem_raw + slice_bytes);
-  VerifyShared<THREADS>& sh = *reinterpret_cast<VerifyShared<THREADS>*>(smem_raw + 2 * slice_bytes);
+  float* ps = reinterpret_cast<float*>(smem_raw);   // p_n slice, turned in place into max(0, p_n - q_n)
+  VerifyShared<THREADS>& sh = *reinterpret_cast<VerifyShared<THREADS>*>(smem_raw + slice_bytes);
   RowCtx<THREADS> cx(&sh.rs, p.cluster);
   const int tid = cx.tid, lane = cx.lane, warp = cx.warp, C = cx.C;
   const int b = blockIdx.x / C;
@@ -72,31 +71,40 @@ __global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParam
   const int n_vec = (n + PV - 1) / PV;
   const float* prow = p.p + b * p.p_req_stride + (has_q ? n_acc : 0) * p.p_row_stride + start;
   const float* qrow = use_q ? p.q + b * p.q_req_stride + n_acc * p.q_row_stride + start : nullptr;
-  if (p.use_tma) {
-    if (tid == 0 && n > 0) {
-      const uint32_t bytes = static_cast<uint32_t>(n) * 4u;
-      mbar_expect_tx(&sh.bar, use_q ? 2u * bytes : bytes);
-      tma_load_1d(ps, prow, bytes, &sh.bar);
-      if (use_q) tma_load_1d(qs, qrow, bytes, &sh.bar);
+  auto stage_p = [&](bool tma) {
+    if (tma) {
+      if (tid == 0 && n > 0) {
+        const uint32_t bytes = static_cast<uint32_t>(n) * 4u;
+        mbar_expect_tx(&sh.bar, bytes);
+        tma_load_1d(ps, prow, bytes, &sh.bar);
+      }
+      if (n > 0) mbar_wait(&sh.bar, 0);
+    } else {
+      for (int i = tid; i < n_vec * PV; i += THREADS) ps[i] = i < n ? prow[i] : 0.f;
+      __syncthreads();
     }
-    if (n > 0) mbar_wait(&sh.bar, 0);
-  } else {
-    for (int i = tid; i < n_vec * PV; i += THREADS) {
-      ps[i] = i < n ? prow[i] : 0.f;
-      if (use_q) qs[i] = i < n ? qrow[i] : 0.f;
+  };
+  stage_p(p.use_tma != 0);
+  // residual max(0, p - q) (utils.py:240) built in place: q_n is read from HBM exactly once, straight into registers
+  auto fold_q = [&]() {
+    if (p.use_tma) {
+      for (int v = tid; v < n_vec; v += THREADS) {
+        float4 a = reinterpret_cast<float4*>(ps)[v];
+        const uint4 cu = ld_nc_v4(reinterpret_cast<const uint4*>(qrow) + v);
+        a.x = fmaxf(a.x - __uint_as_float(cu.x), 0.f); a.y = fmaxf(a.y - __uint_as_float(cu.y), 0.f);
+        a.z = fmaxf(a.z - __uint_as_float(cu.z), 0.f); a.w = fmaxf(a.w - __uint_as_float(cu.w), 0.f);
+        reinterpret_cast<float4*>(ps)[v] = a;
+      }
+    } else {
+      for (int i = tid; i < n; i += THREADS) ps[i] = fmaxf(ps[i] - qrow[i], 0.f);
     }
     __syncthreads();
-  }
+  };
+  if (use_q) fold_q();
 
-  // weights of one 16-byte vector: residual max(0, p - q)  (utils.py:240) or the target row itself
   auto vecw = [&](int v, float (&w)[PV]) {
     const float4 a = reinterpret_cast<const float4*>(ps)[v];
     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    if (use_q) {
-      const float4 c = reinterpret_cast<const float4*>(qs)[v];
-      w[0] = fmaxf(w[0] - c.x, 0.f); w[1] = fmaxf(w[1] - c.y, 0.f);
-      w[2] = fmaxf(w[2] - c.z, 0.f); w[3] = fmaxf(w[3] - c.w, 0.f);
-    }
   };
   unsigned long long best = 0ull;
   float rmax = 0.f;
@@ -121,6 +129,8 @@ __global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParam
     best = cx.allreduce_max(mine);
     if (best != 0ull || !use_q || p.strict) break;
     use_q = false;                                             // empty residual: resample from p_n (:2009-2010)
+    __syncthreads();
+    stage_p(false);
   }
   if (best == 0ull) {
     if (tid == 0 && cx.crank == 0) {
@@ -162,7 +172,7 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
   if (p.gamma > 32 || (p.q != nullptr && p.gamma < 1)) return cudaErrorInvalidValue;
   const long long row_bytes = p.V * 4;
   int C = 1;
-  while (C < kMaxCluster && (row_bytes + C - 1) / C > 32 * 1024) C <<= 1;
+  while (C < kMaxCluster && (row_bytes + C - 1) / C > 48 * 1024) C <<= 1;
   while (C < kMaxCluster && static_cast<long long>(p.B) * C < 148 && row_bytes / (2 * C) >= 4096) C <<= 1;
   if (g_verify_cluster > 0) C = g_verify_cluster;
   long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
@@ -174,9 +184,9 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
   };
   p.use_tma = (al(p.p, p.p_req_stride, p.p_row_stride) && (p.q == nullptr || al(p.q, p.q_req_stride, p.q_row_stride)) &&
                p.V % 4 == 0) ? 1 : 0;
-  const size_t smem = static_cast<size_t>(slice) * 8 + sizeof(VerifyShared<THREADS>);
+  const size_t smem = static_cast<size_t>(slice) * 4 + sizeof(VerifyShared<THREADS>);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  auto kern = verify_kernel<THREADS, 2>;
+  auto kern = verify_kernel<THREADS, 3>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -47,15 +47,13 @@ def test_verify_all_accept_all_reject_and_fallback(cuda_lib):
     qq[0] = pp[0, :gamma]; qq[1] = pp[1, :gamma]
     draft[0] = torch.tensor([int(pp[0, i].argmax()) for i in range(gamma)])
     draft[1] = torch.tensor([int(pp[1, i].argmax()) for i in range(gamma)])
-    # request 2: p == q at the rejected row -> empty residual -> falls back to sample(p_n) (spec_sampling.py:2009-2010)
-    u_acc[2, 0] = 0.999999
-    qq[2, 0] = pp[2, 0]
+    # request 2: q >= p everywhere at the rejected row -> empty residual -> falls back to sample(p_n)
+    # (reference speculative_sampling.py:2009-2010)
     lo = int((pp[2, 0] > 0).nonzero()[-1])
-    draft[2, 0] = lo
-    pp2 = pp.clone()
-    # make ratio < u for request 2 without touching the row equality elsewhere: use a token whose p is tiny
+    qq[2, 0] = pp[2, 0]
     qq[2, 0, lo] = pp[2, 0, lo] * 4
-    qq[2, 0] = qq[2, 0]
+    draft[2, 0] = lo
+    u_acc[2, 0] = 0.999999
     # request 3: drafted token has zero target probability -> rejected at position 0
     zero_tok = int((pp[3, 0] == 0).nonzero()[0])
     qq[3, 0, zero_tok] = 0.25
@@ -98,7 +96,8 @@ def test_sample_rows_bit_exact(cuda_lib, V):
     rows = 40
     g = torch.Generator().manual_seed(V)
     probs = torch.rand(rows, V, generator=g) ** 8
-    probs[::3] *= (torch.rand(rows, V, generator=g) > 0.99)[::3]     # sparse rows
+    if V >= 1000:
+        probs[::3] *= (torch.rand(rows, V, generator=g) > 0.99)[::3]     # sparse rows
     probs[1] = 0; probs[1, V // 2] = 3.5                             # single-support, un-normalised
     probs = probs.float()
     u = torch.rand(rows, generator=g)

@@ -1,0 +1,104 @@
+"""Kernel micro-benchmarks (B200): HBM GB/s of the norm and verify kernels on synthetic logits.
+
+    python tools/microbench.py [--V 32000] [--rows 576] [--dtype f32] [--sweep]
+
+Inputs rotate over enough distinct buffers to exceed 2x the 126 MB L2, timing is CUDA events on
+the launching stream after warm-up.
+"""
+import argparse
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from llmspeculativesampling_b200 import ops, build  # noqa: E402
+
+
+def time_norm(rows, V, dtype, T, k, p, iters=40, sample=False, write=True):
+    es = torch.tensor([], dtype=dtype).element_size()
+    per_set = rows * V * (es + (4 if write else 0))
+    n_sets = max(2, int(2.2 * 126e6 / per_set) + 1)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ins = [(torch.randn(rows, V, device="cuda", generator=g) * 3.8).to(dtype) for _ in range(n_sets)]
+    outs = [torch.empty(rows, V, device="cuda") for _ in range(n_sets)] if write else [None] * n_sets
+    u = torch.rand(rows, device="cuda")
+    tok = torch.empty(rows, dtype=torch.int64, device="cuda")
+
+    def run(i):
+        if sample:
+            ops.norm_sample(ins[i % n_sets], T, k, p, u, probs_out=outs[i % n_sets], tok_out=tok)
+        else:
+            ops.norm_probs(ins[i % n_sets], T, k, p, out=outs[i % n_sets])
+    for i in range(5):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ops.default_flag("cuda").check()
+    ms = e0.elapsed_time(e1) / iters
+    return ms, per_set / ms / 1e6
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--V", type=int, default=32000)
+    ap.add_argument("--rows", type=int, default=576)
+    ap.add_argument("--dtype", default="f32")
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--mode", default="")
+    ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    a = ap.parse_args()
+    build.build()
+    dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[a.dtype]
+    modes_all = {"topk": ("topk20_p0.9", 0.8, 20, 0.9), "dense": ("dense", 1.0, 0, 0.0), "topp": ("top_p_only", 1.0, 0, 0.9)}
+    if a.mode:
+        ops.set_tuning(a.cluster, a.threads, 0)
+        name, T, k, p = modes_all[a.mode]
+        ms, gbs = time_norm(a.rows, a.V, dt, T, k, p, iters=a.iters)
+        print(json.dumps(dict(kernel="norm", mode=name, rows=a.rows, V=a.V, dtype=a.dtype, ms=round(ms, 4), GBs=round(gbs, 1))))
+        return
+    # reference point: a plain device copy of the same number of bytes
+    n = a.rows * a.V
+    src = [torch.randn(n, device="cuda") for _ in range(4)]
+    dst = [torch.empty(n, device="cuda") for _ in range(4)]
+    for i in range(4):
+        dst[i].copy_(src[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        dst[i % 4].copy_(src[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print(json.dumps(dict(kernel="torch_copy_same_bytes", ms=round(ms, 4), GBs=round(n * 8 / ms / 1e6, 1))), flush=True)
+    del src, dst
+    res = []
+    tunings = [(0, 0)] + ([(1, 512), (1, 1024), (2, 256), (2, 512), (4, 256), (8, 256)] if a.sweep else [])
+    modes = [("topk20_p0.9", 0.8, 20, 0.9), ("dense", 1.0, 0, 0.0), ("top_p_only", 1.0, 0, 0.9), ("dense_T0.8", 0.8, 0, 0.0)]
+    for (c, t) in tunings:
+        ops.set_tuning(c, t, 0)
+        for name, T, k, p in modes:
+            try:
+                ms, gbs = time_norm(a.rows, a.V, dt, T, k, p)
+                res.append(dict(kernel="norm", mode=name, cluster=c, threads=t, rows=a.rows, V=a.V, dtype=a.dtype, ms=round(ms, 4), GBs=round(gbs, 1)))
+            except Exception as e:  # noqa: BLE001
+                res.append(dict(kernel="norm", mode=name, cluster=c, threads=t, error=str(e)[:80]))
+            print(json.dumps(res[-1]), flush=True)
+    ops.set_tuning(0, 0, 0)
+    ms, gbs = time_norm(a.rows, a.V, dt, 0.8, 20, 0.9, sample=True)
+    print(json.dumps(dict(kernel="norm_sample", ms=round(ms, 4), GBs=round(gbs, 1))))
+    ms, gbs = time_norm(a.rows, a.V, dt, 0.8, 20, 0.9, sample=True, write=False)
+    print(json.dumps(dict(kernel="norm_sample_tokens_only", ms=round(ms, 4), GBs_read=round(gbs, 1))))
+
+
+if __name__ == "__main__":
+    main()
