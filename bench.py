@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Headline benchmark of the speculative-decoding draft-and-verify hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): synthetic-logits
+verify microbench, V=32000, gamma=4, batch=64 requests per GPU, T=0.8, top_k=20, top_p=0.9, fp32
+logits.  ONE STEP = one pass of the hot path over one batch:
+    kernel 1b  sd_norm_sample  on the B*gamma draft rows      (filter + softmax + draft token)
+    kernel 1   sd_norm_probs   on the B*(gamma+1) target rows (filter + softmax)
+    kernel 2   sd_verify       accept / first reject / residual / inverse-CDF sample / append
+Metric: accepted tokens/s (whole job, all GPUs); emitted tokens/s and the acceptance are reported too.
+
+value     inputs resident in HBM, the three kernels of a step replayed from a CUDA graph, timed with CUDA
+          events around exactly K steps (barrier + synchronize on both sides, max over ranks).  Inputs
+          rotate over distinct sets whose total exceeds 2x the 126 MB L2.
+e2e       same steps through the public tensor API with HOST buffers: every step copies its logits and
+          uniforms from pinned host memory to the device and reads accept counts and tokens back.
+roofline  dominant kernel (norm, 2 launches per step): algorithmic bytes (rows * V * (4 read + 4 written))
+          / its average launch duration, measured with CUDA events in an instrumented replay of the same
+          K steps; peak = MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference   the oracle port of the reference's CPU path (oracle/ref_ops.py: the same
+          ATen op chain, one row at a time, host syncs included) on a bounded sample of the same workload.
+
+N > 1 (torchrun): requests are independent, every rank runs the same per-GPU batch on its own synthetic
+shard with no data-path collective ("scaling": "weak"); NCCL is used for the barrier and the final
+statistics reduction only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V, GAMMA, BATCH = 32000, 4, 64
+TEMP, TOP_K, TOP_P = 0.8, 20, 0.9
+WORKLOAD = f"synthetic-logits verify microbench V={V} gamma={GAMMA} batch={BATCH}/GPU T={TEMP} top_k={TOP_K} top_p={TOP_P} fp32 logits"
+
+
+def synth_set(seed: int, device, batch: int = BATCH):
+    """shared base z, draft = z + noise, target = z + noise'."""
+    g = torch.Generator(device=device).manual_seed(1234 + seed)
+    z = 3.0 * torch.randn(batch, GAMMA + 1, V, generator=g, device=device)
+    target = z + 0.5 * torch.randn(batch, GAMMA + 1, V, generator=g, device=device)
+    draft = z[:, :GAMMA] + 0.5 * torch.randn(batch, GAMMA, V, generator=g, device=device)
+    u = torch.rand(batch, 2 * GAMMA + 2, generator=g, device=device)
+    return draft.contiguous(), target.contiguous(), u
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0])); mx = int(f[1])
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def oracle_step(draft, target, u, requests):
+    """The reference's CPU path for `requests` of one batch (oracle port; rows one at a time)."""
+    from oracle import ref_ops
+    acc = emitted = 0
+    for b in requests:
+        q_rows = torch.cat([ref_ops.norm_probs(draft[b, i:i + 1], TEMP, TOP_K, TOP_P) for i in range(GAMMA)], 0)
+        toks = torch.tensor([ref_ops.icdf_sample(q_rows[i], float(u[b, i])) for i in range(GAMMA)])
+        p_rows = torch.cat([ref_ops.norm_probs(target[b, i:i + 1], TEMP, TOP_K, TOP_P) for i in range(GAMMA + 1)], 0)
+        _ = ref_ops.icdf_sample(p_rows[GAMMA], float(u[b, GAMMA]))            # the sample the reference discards
+        n_acc, _, _, _ = ref_ops.verify_request(p_rows, q_rows, toks, u[b, GAMMA + 1:2 * GAMMA + 1].numpy(),
+                                                float(u[b, 2 * GAMMA + 1]), residual="normalised")
+        acc += n_acc
+        emitted += n_acc + 1
+    return acc, emitted
+
+
+def time_oracle(steps: int, warmup: int, per_step: int, threads: int):
+    torch.set_num_threads(threads)
+    draft, target, u = synth_set(0, "cpu")
+    acc = emitted = 0
+    for s in range(warmup):
+        oracle_step(draft, target, u, [(s * per_step + j) % BATCH for j in range(per_step)])
+    t0 = time.perf_counter()
+    for s in range(steps):
+        a, e = oracle_step(draft, target, u, [((warmup + s) * per_step + j) % BATCH for j in range(per_step)])
+        acc += a; emitted += e
+    dt = time.perf_counter() - t0
+    return acc, emitted, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = 4
+    cores = os.cpu_count() or 1
+    # the reference is single-stream Python; intra-op threads are the only host parallelism it can use
+    best = None
+    for th in sorted({1, cores}):
+        a, e, dt = time_oracle(max(1, min(args.steps, 3)), 1, per_step, th)
+        if best is None or a / dt > best[0]:
+            best = (a / dt, th)
+    threads = best[1]
+    acc, emitted, dt = time_oracle(args.steps, args.warmup, per_step, threads)
+    val = acc / dt
+    line = {
+        "impl": "reference", "metric": "accepted_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{per_step} of the {BATCH} requests per step"},
+        "emitted_tokens_per_s": emitted / dt, "mean_accepted_per_iteration": acc / (args.steps * per_step),
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {per_step} requests (gamma+gamma+1 rows each), oracle port of the "
+                                   f"reference CPU path, torch threads={threads} of {cores} host cores"},
+        "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from llmspeculativesampling_b200 import build, ops
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    build.build()
+
+    B, g = BATCH, GAMMA
+    n_sets = 4                                              # 4 x (73.7 MB logits + 73.7 MB probs) >> 2 x 126 MB L2
+    sets = [synth_set(rank * 100 + i, dev) for i in range(n_sets)]
+    q_probs = [torch.empty(B, g, V, device=dev) for _ in range(n_sets)]
+    p_probs = [torch.empty(B, g + 1, V, device=dev) for _ in range(n_sets)]
+    draft_tok = torch.zeros(B, g, dtype=torch.int64, device=dev)
+    n_acc = torch.zeros(B, dtype=torch.int32, device=dev)
+    next_tok = torch.zeros(B, dtype=torch.int64, device=dev)
+    acc_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    err = ops.ErrFlag(dev)
+    u_draft = [s[2][:, :g].contiguous().view(-1) for s in sets]
+    u_acc = [s[2][:, g + 1:2 * g + 1].contiguous() for s in sets]
+    u_fin = [s[2][:, 2 * g + 1].contiguous() for s in sets]
+
+    def step(i: int, count: bool = True):
+        d, t, _ = sets[i]
+        ops.norm_sample(d.view(B * g, V), TEMP, TOP_K, TOP_P, u_draft[i], probs_out=q_probs[i].view(B * g, V),
+                        tok_out=draft_tok.view(-1), err=err)
+        ops.norm_probs(t.view(B * (g + 1), V), TEMP, TOP_K, TOP_P, out=p_probs[i].view(B * (g + 1), V), err=err)
+        ops.verify(p_probs[i], q_probs[i], draft_tok, u_acc[i], u_fin[i], n_accepted=n_acc, next_tok=next_tok, err=err)
+        if count:
+            acc_total.add_(n_acc.sum())
+
+    # one CUDA graph per input set (3 kernels + the accept-count accumulation)
+    for i in range(n_sets):
+        step(i)
+    torch.cuda.synchronize()
+    graphs = []
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(n_sets):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                step(i)
+            graphs.append(gr)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        graphs[s % n_sets].replay()
+    barrier()
+    acc_total.zero_()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        graphs[s % n_sets].replay()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop()
+    err.check()
+    accepted = int(acc_total.item())
+
+    # ---- instrumented replay: per-kernel durations (same steps, eager launches bracketed by events)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for s in range(args.steps):
+        i = s % n_sets
+        d, t, _ = sets[i]
+        ev[s][0].record()
+        ops.norm_sample(d.view(B * g, V), TEMP, TOP_K, TOP_P, u_draft[i], probs_out=q_probs[i].view(B * g, V),
+                        tok_out=draft_tok.view(-1), err=err)
+        ev[s][1].record()
+        ops.norm_probs(t.view(B * (g + 1), V), TEMP, TOP_K, TOP_P, out=p_probs[i].view(B * (g + 1), V), err=err)
+        ev[s][2].record()
+        ops.verify(p_probs[i], q_probs[i], draft_tok, u_acc[i], u_fin[i], n_accepted=n_acc, next_tok=next_tok, err=err)
+        ev[s][3].record()
+    torch.cuda.synchronize()
+    t_draft = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    t_target = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    t_verify = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
+    norm_bytes = B * (2 * g + 1) * V * 8                    # logits read once (4 B) + probs written once (4 B)
+    norm_ms = t_draft + t_target
+    achieved = norm_bytes / (norm_ms * 1e-3) / 1e9
+
+    # ---- end to end: host buffers, H2D of the step's inputs and D2H of its results inside the timed region
+    host_sets = []
+    for i in range(n_sets):
+        d, t, u = sets[i]
+        host_sets.append((d.cpu().pin_memory(), t.cpu().pin_memory(), u.cpu().pin_memory()))
+    d_dev, t_dev = torch.empty(B, g, V, device=dev), torch.empty(B, g + 1, V, device=dev)
+    u_dev = torch.empty(B, 2 * g + 2, device=dev)
+    ud_dev, uf_dev = torch.empty(B * g, device=dev), torch.empty(B, device=dev)
+    qd, pd = torch.empty(B, g, V, device=dev), torch.empty(B, g + 1, V, device=dev)
+    h_acc = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_tok = torch.empty(B, dtype=torch.int64).pin_memory()
+
+    def e2e_step(i: int) -> int:
+        hd, ht, hu = host_sets[i]
+        d_dev.copy_(hd, non_blocking=True); t_dev.copy_(ht, non_blocking=True); u_dev.copy_(hu, non_blocking=True)
+        ud_dev.copy_(u_dev[:, :g].reshape(-1)); uf_dev.copy_(u_dev[:, 2 * g + 1])
+        ops.norm_sample(d_dev.view(B * g, V), TEMP, TOP_K, TOP_P, ud_dev, probs_out=qd.view(B * g, V),
+                        tok_out=draft_tok.view(-1), err=err)
+        ops.norm_probs(t_dev.view(B * (g + 1), V), TEMP, TOP_K, TOP_P, out=pd.view(B * (g + 1), V), err=err)
+        ops.verify(pd, qd, draft_tok, u_dev[:, g + 1:2 * g + 1], uf_dev, n_accepted=n_acc, next_tok=next_tok, err=err)
+        h_acc.copy_(n_acc, non_blocking=True); h_tok.copy_(next_tok, non_blocking=True)
+        torch.cuda.synchronize()                            # the caller needs the tokens before the next step
+        return int(h_acc.sum())
+
+    e2e_steps = max(3, min(args.steps, 40))
+    for s in range(3):
+        e2e_step(s % n_sets)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_acc = 0
+    for s in range(e2e_steps):
+        e2e_acc += e2e_step(s % n_sets)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = (B * (2 * g + 1) * V + B * (2 * g + 2)) * 4
+    d2h = B * (4 + 8)
+
+    # ---- reduce over ranks (max time, summed tokens)
+    stats = torch.tensor([ms, e2e_s, float(accepted), float(e2e_acc)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats[:2].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats[2:].clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_s, accepted, e2e_acc = float(mx[0]), float(mx[1]), float(sm[0]), float(sm[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "norm_traffic.json"))).get("dram_bytes_per_launch_pair")
+    except (OSError, ValueError):
+        pass
+    secs = ms * 1e-3
+    iters_total = args.steps * B * world
+    line = {
+        "metric": "accepted_tokens_per_s", "value": accepted / secs, "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2_policy": f"inputs and outputs rotate over {n_sets} sets "
+                   f"({n_sets * norm_bytes / 1e6:.0f} MB > 2 x 126 MB L2)", "cuda_graph": True,
+                   "kernels_per_step": ["sd_norm_sample (B*gamma rows)", "sd_norm_probs (B*(gamma+1) rows)", "sd_verify"]},
+        "emitted_tokens_per_s": (accepted + iters_total) / secs,
+        "mean_accepted_per_iteration": accepted / iters_total,
+        "request_iterations_per_s": iters_total / secs,
+        "clocks": clock_info,
+        "gpu_launches": 3 * args.steps,
+        "e2e": {"value": e2e_acc / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "norm_probs_kernel<float,256,3> (2 launches per step)",
+                     "algorithmic_bytes_per_step": norm_bytes, "ms_per_step": norm_ms,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "kernel_ms": {"norm_draft_rows": t_draft, "norm_target_rows": t_target, "verify": t_verify},
+                     "norm_share_of_step": norm_ms / (norm_ms + t_verify)},
+    }
+    if not args.no_cpu_baseline:
+        per = 4
+        cores = os.cpu_count() or 1
+        a1, e1_, dt1 = time_oracle(4, 1, per, 1)
+        best = (a1 / dt1, 1, a1, dt1)
+        if cores > 1:
+            a2, _, dt2 = time_oracle(2, 1, per, cores)
+            if a2 / dt2 > best[0]:
+                a2, _, dt2 = time_oracle(4, 1, per, cores)
+                best = (a2 / dt2, cores, a2, dt2)
+        line["cpu_baseline"] = {"value": best[0], "unit": "tokens/s", "cores": best[1], "kind": "port",
+                                "sample": f"4 steps x {per} requests of the same workload through oracle/ref_ops.py "
+                                          f"(the reference's ATen op chain, row by row), torch threads={best[1]} "
+                                          f"of {cores} host cores; {best[3]:.1f} s of CPU work"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

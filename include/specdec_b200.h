@@ -53,6 +53,10 @@ const char* sd_last_error(void);
  * 0 = heuristic) of the norm kernel, cluster size of the verify kernel. */
 void sd_set_tuning(int norm_cluster, int norm_threads, int verify_cluster);
 
+/* Debug: when non-NULL, every CTA of the norm kernel writes clock64() phase timestamps into
+ * device_buf[cta * 16 + slot] (tools/microbench.py --prof).  NULL switches it off. */
+void sd_debug_set_prof(int64_t* device_buf);
+
 /* Kernel 1 — fused  logits / T -> top-k -> top-p -> softmax  for `rows` rows of V logits.
  * Replaces sampling/utils.py:152-179 (top_k_top_p_filter) + :182-210 (norm_logits), called once per row
  * from sampling/kvcache_model.py:166-168 and :235-236.

@@ -18,6 +18,7 @@ SIGNATURES = {
     "sd_version": (i32, []),
     "sd_last_error": (C.c_char_p, []),
     "sd_set_tuning": (None, [i32, i32, i32]),
+    "sd_debug_set_prof": (None, [vp]),
     "sd_norm_probs": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp]),
     "sd_norm_sample": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp]),
     "sd_norm_general": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp]),

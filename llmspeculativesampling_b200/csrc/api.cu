@@ -33,6 +33,8 @@ void sd_set_tuning(int norm_cluster, int norm_threads, int verify_cluster) {
   sd::set_verify_tuning(verify_cluster);
 }
 
+void sd_debug_set_prof(int64_t* device_buf) { sd::set_norm_prof(reinterpret_cast<long long*>(device_buf)); }
+
 static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
                        int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
                        int* err_flag, int force_general, void* stream) {

@@ -14,9 +14,11 @@ struct NormParams {
   // filled by the launcher
   int cluster, slice_elems, slice_smem_bytes, use_tma, vec_out;
   int force_general;                       // test knob: skip the fast top-k path
+  long long* prof;                         // debug: per-CTA clock64 timestamps (16 slots per CTA), nullable
 };
 cudaError_t launch_norm(const NormParams& p, int dtype, int rows, cudaStream_t st);
 void set_norm_tuning(int cluster, int threads);
+void set_norm_prof(long long* ptr);
 
 struct VerifyParams {
   const float* p; long long p_req_stride, p_row_stride;     // target probs  (B, gamma+1, V)

@@ -82,7 +82,7 @@ class ModelStepper:
         self.B, self.S = batch, max_len
         layers, kv_heads, head_dim, self.V = _model_geometry(model)
         if cache_dtype is None:
-            cache_dtype = getattr(model, "dtype", torch.float32)
+            cache_dtype = getattr(model, "kv_cache_dtype", None) or getattr(model, "dtype", torch.float32)
         self.cache = StaticKVCache(layers, batch, kv_heads, max_len, head_dim, cache_dtype, device)
         self.device = device
         self._bufs = {}
@@ -113,7 +113,7 @@ class ModelStepper:
 
     def prefill(self, tokens: torch.Tensor, n_positions: int) -> None:
         """Fill the cache for positions 0 .. n_positions-1 of every request (padded prompts)."""
-        chunk = 512
+        chunk = 256
         for s in range(0, n_positions, chunk):
             q = min(chunk, n_positions - s)
             self.forward(tokens, self._zero_len, s, q, None, last_only=True)
@@ -158,6 +158,7 @@ class SpecDecEngine:
         self.ties = torch.zeros(1, dtype=torch.int32, device=dev)
         self.u_rows = torch.zeros(batch, tape_block(g), dtype=torch.float32, device=dev)
         self.u_draft_t = torch.zeros(g, batch, dtype=torch.float32, device=dev)
+        self.u_final = torch.zeros(batch, dtype=torch.float32, device=dev)
         self.max_iterations = max_iterations or max_total_len
         self.acc_hist = torch.full((self.max_iterations, batch), -1, dtype=torch.int32, device=dev)
         self.ratio_hist = torch.zeros(self.max_iterations, batch, g, dtype=torch.float32, device=dev)
@@ -201,6 +202,7 @@ class SpecDecEngine:
     def _iteration(self) -> None:
         g, B, V = self.gamma, self.B, self.V
         self.u_draft_t.copy_(self.u_rows[:, :g].t())
+        self.u_final.copy_(self.u_rows[:, 2 * g + 1])
         for i in range(g):
             if i == 0:
                 logits = self.draft.forward(self.tokens, self.seq_len, -2, 2, None)[:, 1]
@@ -212,7 +214,7 @@ class SpecDecEngine:
         logits = self.target.forward(self.tokens, self.seq_len, -1, g + 1, self.cur_tok)
         ops.norm_probs(logits.reshape(B * (g + 1), V), self.T, self.top_k, self.top_p,
                        out=self.p_probs.view(B * (g + 1), V), err=self.err)
-        ops.verify(self.p_probs, self.q_probs, self.draft_tok, self.u_rows[:, g + 1:2 * g + 1], self.u_rows[:, 2 * g + 1].contiguous(),
+        ops.verify(self.p_probs, self.q_probs, self.draft_tok, self.u_rows[:, g + 1:2 * g + 1], self.u_final,
                    strict=self.strict, n_accepted=self.n_acc, next_tok=self.next_tok, ratios=self.ratios,
                    tie_count=self.ties, tokens=self.tokens, seq_len=self.seq_len, active=self.active, err=self.err)
         # statistics + termination, all on the device
@@ -234,6 +236,8 @@ class SpecDecEngine:
                 for _ in range(2):
                     self.it_dev.zero_()
                     self._iteration()
+                    for t, s_ in zip((self.tokens, self.seq_len, self.active), saved[:3]):
+                        t.copy_(s_)
             torch.cuda.current_stream(self.device).wait_stream(s)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()

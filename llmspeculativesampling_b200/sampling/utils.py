@@ -24,6 +24,7 @@ def norm_logits(logits: torch.Tensor, temperature: float, top_k: float, top_p: f
     """(rows, V) logits -> (rows, V) fp32 probabilities (utils.py:182-210).  Raises
     RuntimeError('norm logits error') where the reference does (one flag read instead of 3 syncs)."""
     assert logits.dim() == 2                                              # utils.py:194
+    ops._require_cuda(logits, "logits")
     flag = ops.default_flag(logits.device)
     probs = ops.norm_probs(logits, temperature, top_k or 0, top_p or 0.0, err=flag)
     flag.check()
@@ -37,6 +38,7 @@ def sample(probs: torch.Tensor, num_samples: int = 1, u: Optional[torch.Tensor] 
     if num_samples != 1:
         raise NotImplementedError("only num_samples=1 is on the speculative hot path")
     p2 = probs if probs.dim() == 2 else probs.reshape(1, -1)
+    ops._require_cuda(p2, "probs")
     if u is None:
         u = torch.rand(p2.shape[0], device=p2.device, dtype=torch.float32, generator=generator)
     flag = ops.default_flag(p2.device)

@@ -43,8 +43,9 @@ class ReplayLM(torch.nn.Module):
         self.register_buffer("table", base.to(dtype).to(device), persistent=False)
         self.vocab_size = vocab_size
         self.config = SimpleNamespace(is_encoder_decoder=False, vocab_size=vocab_size,
-                                      num_hidden_layers=1, num_key_value_heads=1, head_dim=1,
-                                      hidden_size=1, num_attention_heads=1)
+                                      num_hidden_layers=1, num_key_value_heads=1, head_dim=4,
+                                      hidden_size=4, num_attention_heads=1)
+        self.kv_cache_dtype = torch.float32            # hash states must stay exact in the engine's cache
         self._dummy = torch.nn.Parameter(torch.zeros(1), requires_grad=False)
 
     @property
@@ -84,7 +85,7 @@ class ReplayLM(torch.nn.Module):
             prev = past_key_values.peek(0, (pos0 - 1).clamp_min(0))      # (B,) fp32 exact ints
             h_prev = torch.where(pos0 > 0, prev.to(torch.int64), torch.zeros_like(pos0))
             h = self._chain(h_prev, input_ids, pos0)
-            kv = h.to(past_key_values.dtype).view(B, 1, q, 1)
+            kv = h.to(past_key_values.dtype).view(B, 1, q, 1).expand(B, 1, q, 4).contiguous()
             past_key_values.update(kv, kv, 0)
             return _Out(logits=self.logits_of(h), past_key_values=past_key_values)
         if past_key_values is None:

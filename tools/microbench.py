@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--mode", default="")
+    ap.add_argument("--prof", action="store_true")
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
@@ -64,6 +65,30 @@ def main():
         name, T, k, p = modes_all[a.mode]
         ms, gbs = time_norm(a.rows, a.V, dt, T, k, p, iters=a.iters)
         print(json.dumps(dict(kernel="norm", mode=name, rows=a.rows, V=a.V, dtype=a.dtype, ms=round(ms, 4), GBs=round(gbs, 1))))
+        if a.prof:
+            from llmspeculativesampling_b200 import _cabi
+            buf = torch.zeros(a.rows * 8, 16, dtype=torch.int64, device="cuda")
+            x = (torch.randn(a.rows, a.V, device="cuda") * 3.8).to(dt)
+            out = torch.empty(a.rows, a.V, device="cuda")
+            ops.norm_probs(x, T, k, p, out=out)
+            torch.cuda.synchronize()
+            _cabi.load().sd_debug_set_prof(buf.data_ptr())
+            ops.norm_probs(x, T, k, p, out=out)
+            torch.cuda.synchronize()
+            _cabi.load().sd_debug_set_prof(None)
+            b = buf.cpu()
+            b = b[b[:, 0] != 0]
+            names = {1: "setup+issue", 2: "first chunk landed", 3: "pass1 done", 11: "warp sort+sync", 12: "rank+sync", 13: "hot list+sync", 4: "rescan done", 5: "cluster sync", 6: "merge+sort", 7: "select+scatter", 8: "dense sums", 9: "dense write", 10: "exit"}
+            prev = 0
+            print("CTAs", b.shape[0])
+            for s_ in [1, 2, 3, 11, 12, 13, 4, 5, 6, 7, 8, 9, 10]:
+                m = b[:, s_] != 0
+                if m.any():
+                    d = (b[m, s_] - b[m, prev]).float()
+                    print(f"  slot {s_:2d} {names[s_]:20s} +{d.mean():9.0f} cyc (p10 {d.quantile(0.1):7.0f}, p90 {d.quantile(0.9):7.0f})")
+                    prev = s_
+            tot = (b[:, 10] - b[:, 0]).float()
+            print(f"  CTA lifetime mean {tot.mean():.0f} cyc, p90 {tot.quantile(0.9):.0f}")
         return
     # reference point: a plain device copy of the same number of bytes
     n = a.rows * a.V
