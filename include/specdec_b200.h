@@ -68,20 +68,23 @@ void sd_debug_set_prof(int64_t* device_buf);
  *   probs   (rows, V) fp32, row stride ld_out: exp(log_softmax(filtered)) (utils.py:199), 0 outside
  * Sets SD_ERR_NORM_LOGITS where the reference raises 'norm logits error' (utils.py:203-207). */
 int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
-                  float top_p, float* probs, int64_t ld_out, int* err_flag, void* stream);
+                  float top_p, float* probs, int64_t ld_out, int* err_flag, int flags, void* stream);
+
+/* `flags` of the two norm entry points.  By default, for 0 < top_k <= 128 and 16-byte aligned rows the persistent,
+ * warp-specialised pipeline kernel runs (one CTA per SM: a memory warp streams slices in by TMA and zero-fills the
+ * output while compute groups select; rows it cannot serve — massive ties — are re-run on the general path by the same
+ * cluster before the kernel ends); every other case uses the one-cluster-per-row kernel. */
+#define SD_NORM_DEFAULT 0
+#define SD_NORM_NO_PIPELINE 1   /* one-cluster-per-row kernel even where the pipeline applies                 */
+#define SD_NORM_FORCE_GENERAL 2 /* test hook: sort-free threshold-search path (normally top_k = 0, top_k > 128
+                                   or rows with massive ties only); implies SD_NORM_NO_PIPELINE                */
 
 /* Kernel 1b — same, plus one inverse-CDF sample per row from the uniform u[row] (draft step):
  * replaces norm_logits + sample(q) of sampling/kvcache_model.py:280-283 and
  * sampling/autoregressive_sampling.py:41-44.  `probs` may be NULL (token only). */
 int sd_norm_sample(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
                    float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out, int* err_flag,
-                   void* stream);
-
-/* Test hook: as sd_norm_sample (u / tok_out may be NULL) but forces the general sort-free path that
- * normally only serves top_k = 0, top_k > 128 or rows with massive ties. */
-int sd_norm_general(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
-                    int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
-                    int* err_flag, void* stream);
+                   int flags, void* stream);
 
 /* sample — one inverse-CDF draw per row of non-negative weights.  Replaces sampling/utils.py:213-233. */
 int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const float* u, int64_t* tok_out, int* err_flag,

@@ -37,7 +37,7 @@ void sd_debug_set_prof(int64_t* device_buf) { sd::set_norm_prof(reinterpret_cast
 
 static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
                        int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
-                       int* err_flag, int force_general, void* stream) {
+                       int* err_flag, int flags, void* stream) {
   if (rows == 0) return SD_OK;
   if (logits == nullptr || err_flag == nullptr || rows < 0 || V <= 0 || ld_in < V) return fail(SD_EINVAL, "sd_norm: bad logits/shape");
   if (!(temperature > 0.f) || std::isinf(temperature)) return fail(SD_EINVAL, "sd_norm: temperature must be finite and > 0");
@@ -50,30 +50,25 @@ static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, i
   p.temperature = temperature; p.top_k = top_k < 0 ? 0 : top_k; p.top_p = top_p;
   p.probs = probs; p.ld_out = ld_out;
   p.u = u; p.tok_out = reinterpret_cast<long long*>(tok_out);
-  p.err_flag = err_flag; p.force_general = force_general;
+  p.err_flag = err_flag;
+  p.force_general = (flags & SD_NORM_FORCE_GENERAL) ? 1 : 0;
+  p.no_pipeline = (flags & SD_NORM_NO_PIPELINE) ? 1 : 0;
   return done("sd_norm launch", sd::launch_norm(p, dtype, static_cast<int>(rows), static_cast<cudaStream_t>(stream)));
 }
 
 int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
-                  float top_p, float* probs, int64_t ld_out, int* err_flag, void* stream) {
+                  float top_p, float* probs, int64_t ld_out, int* err_flag, int flags, void* stream) {
   if (probs == nullptr) return fail(SD_EINVAL, "sd_norm_probs: probs is null");
   return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, nullptr, nullptr,
-                     err_flag, 0, stream);
+                     err_flag, flags, stream);
 }
 
 int sd_norm_sample(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
                    float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out, int* err_flag,
-                   void* stream) {
+                   int flags, void* stream) {
   if (u == nullptr || tok_out == nullptr) return fail(SD_EINVAL, "sd_norm_sample: u/tok_out is null");
-  return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, err_flag, 0,
-                     stream);
-}
-
-int sd_norm_general(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
-                    int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
-                    int* err_flag, void* stream) {
-  return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, err_flag, 1,
-                     stream);
+  return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, err_flag,
+                     flags, stream);
 }
 
 int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const float* u, int64_t* tok_out, int* err_flag,

@@ -1,0 +1,534 @@
+// Kernel 1, persistent warp-specialised version of the fast top-k path (the headline configuration:
+// 0 < top_k <= 128, any top_p, dense fp32 probabilities out).
+//
+// Why a second kernel: in norm.cu a CTA loads its slice, selects, writes — the HBM pipe idles while the
+// (latency-bound) selection runs, and with only ~2.6 waves of CTAs the phases never de-synchronise.  Here
+// every SM runs ONE persistent CTA made of
+//     1 memory warp      issues the 1-D TMA bulk load of work item i+G (slice of a logits row) into the
+//                        shared-memory buffer that compute group (i+G) % G just released, then writes the
+//                        zeros of that item's output slice (st.global.cs.v4, 512 B per instruction)
+//     G compute groups   of 4 warps; group g owns buffer g and work items g, g+G, ...: thread maxima ->
+//                        exact pivot (k-th largest thread maximum) -> re-scan of the few "hot" threads ->
+//                        candidates pushed to the peer CTAs of the cluster through distributed shared
+//                        memory (st.shared::cluster + remote mbarrier arrive, no cluster-wide barrier) ->
+//                        merge, rank sort, top-k / top-p / softmax on ~2k candidates -> scatter of the
+//                        non-zero probabilities (-> optional inverse-CDF sample)
+// so the selection latency of G items is overlapped with the memory traffic of the next ones.  Buffers are
+// handed back and forth with mbarriers (full / zero-filled / empty).  Rows whose candidate lists overflow
+// (massive ties, adversarial layouts) are remembered in a shared-memory bit mask and re-run by the same cluster on
+// the general path (norm_row) after its pipeline has drained, so results never depend on the fast path's luck.
+//
+// Replaces the same reference code as norm.cu: /root/reference/sampling/utils.py:152-210 (+213-233).
+#include "norm_row.cuh"
+
+namespace sd {
+
+constexpr int kPipeGroupWarps = 4;
+constexpr int kPipeGroupThreads = kPipeGroupWarps * 32;
+constexpr int kPipeMaxGroups = 3;
+constexpr int kPipeCap = 256;          // merged candidates per row
+constexpr int kPipeFastK = 128;
+constexpr uint32_t kPipeTieUlps = 8;
+constexpr int kPipeMaxItems = 4096;    // work items one cluster can walk (bit mask of failed items)
+
+struct alignas(16) PipeGroupShared {
+  float tm[kPipeGroupThreads];                       // per-warp sorted thread maxima
+  unsigned short hot[kPipeGroupThreads];
+  int cand_cnt, hot_cnt, n_keep_k, n_keep_p;
+  float tau;
+  uint2 recv_cnt2[2][kMaxCluster];                   // [item parity][cluster rank].x = candidate count (-1: general path)
+  uint2 r_pair[2][kPipeCap];                         // receive regions (logit/T bits, index), double buffered by item parity
+  float a_val[kPipeCap]; int a_idx[kPipeCap];        // merged list -> final probabilities
+  float s_val[kPipeCap]; int s_idx[kPipeCap];        // sorted list
+};
+
+struct alignas(16) PipeShared {
+  uint64_t full[kPipeMaxGroups];      // TMA bytes landed                     (memory warp -> group)
+  uint64_t zeroed[kPipeMaxGroups];    // output slice zero-filled             (memory warp -> group)
+  uint64_t empty[kPipeMaxGroups];     // slice buffer may be overwritten      (group -> memory warp)
+  uint64_t xbar[kPipeMaxGroups][2];   // peers' candidates landed             (remote groups -> group), by item parity
+  PipeGroupShared g[kPipeMaxGroups];
+  uint32_t fail_bits[kPipeMaxItems / 32];   // work items that need the general path (kept LAST: survives norm_row)
+};
+
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive (release at cluster scope) on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, int rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// 8-byte store into the shared memory of CTA `rank` that completes (complete_tx, 8 bytes) on that CTA's mbarrier:
+// data and signal travel together through the async proxy, so the sender needs NO release fence — a fence or a
+// release-arrive would have to drain this SM's queue of in-flight zero-fill stores first (measured: ~14k cycles)
+__device__ __forceinline__ void st_async_remote_v2(void* local_addr, uint32_t a, uint32_t b, uint64_t* local_bar, int rank) {
+  uint32_t raddr, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_addr)), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+               ::"r"(raddr), "r"(a), "r"(b), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  } while (!ok);
+}
+
+// debug timeline: prof[(cta * 32 + item) * 16 + slot] = clock64()   (items >= 32 are not recorded)
+#define PIPE_PROF(item, slot, cond) do { if (p.prof != nullptr && (cond) && (item) < 32) \
+    p.prof[(static_cast<long long>(blockIdx.x) * 32 + (item)) * 16 + (slot)] = clock64(); } while (0)
+
+template <typename T, int G>
+__global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_kernel(const NormParams p) {
+  constexpr int PV = Elem<T>::kPerVec;
+  constexpr int GT = kPipeGroupThreads;
+  constexpr int GW = kPipeGroupWarps;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PipeShared& sh = *reinterpret_cast<PipeShared*>(smem_raw + static_cast<size_t>(G) * p.slice_smem_bytes);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = p.cluster;
+  const int crank = C > 1 ? static_cast<int>(cluster.block_rank()) : 0;
+  const int cid = blockIdx.x / C, n_clusters = gridDim.x / C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = static_cast<int>(p.V);
+  const long long start = static_cast<long long>(crank) * p.slice_elems;
+  const int n = max(0, min(p.slice_elems, V - static_cast<int>(start)));
+  const int n_vec = (n + PV - 1) / PV;
+  const float temp = p.temperature;
+  const int k_eff = min(p.top_k, V);
+  const bool want_probs = p.probs != nullptr;
+  const int n_items = p.rows > cid ? (p.rows - cid + n_clusters - 1) / n_clusters : 0;   // rows cid, cid+n_clusters, ...
+
+  if (tid == 0) {
+    for (int g = 0; g < G; ++g) {
+      mbar_init(&sh.full[g], 1);
+      mbar_init(&sh.zeroed[g], 1);
+      mbar_init(&sh.empty[g], GW);
+      mbar_init(&sh.xbar[g][0], 1);
+      mbar_init(&sh.xbar[g][1], 1);
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < kPipeMaxItems / 32; i += blockDim.x) sh.fail_bits[i] = 0u;
+  if (C > 1) cluster.sync(); else __syncthreads();     // barriers initialised and every peer CTA is running
+
+  // =============================================================================== memory warp
+  if (warp == G * GW) {
+    for (int it = 0; it < n_items; ++it) {
+      const int g = it % G;
+      const uint32_t use = static_cast<uint32_t>(it / G);
+      const int row = cid + it * n_clusters;
+      PIPE_PROF(it, 0, lane == 0);
+      if (use > 0) mbar_wait(&sh.empty[g], (use - 1) & 1);                  // group g is done with its buffer
+      PIPE_PROF(it, 1, lane == 0);
+      if (lane == 0 && n > 0) {
+        const T* src = reinterpret_cast<const T*>(p.logits) + static_cast<long long>(row) * p.ld_in + start;
+        const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(T);
+        mbar_expect_tx(&sh.full[g], bytes);
+        unsigned char* dst = smem_raw + static_cast<size_t>(g) * p.slice_smem_bytes;
+        for (uint32_t off = 0; off < bytes; off += 32768u)
+          tma_load_1d(dst + off, reinterpret_cast<const unsigned char*>(src) + off, min(32768u, bytes - off), &sh.full[g]);
+      } else if (lane == 0) {
+        mbar_arrive_local(&sh.full[g]);
+      }
+      if (want_probs) {                                                     // zeros of this item's output slice
+        float* o = p.probs + static_cast<long long>(row) * p.ld_out + start;
+        if (p.vec_out) {
+          const int nv4 = n >> 2;
+          for (int v = lane; v < nv4; v += 32) st_cs_v4(o + 4 * v, 0.f, 0.f, 0.f, 0.f);
+          for (int i = (nv4 << 2) + lane; i < n; i += 32) o[i] = 0.f;
+        } else {
+          for (int i = lane; i < n; i += 32) o[i] = 0.f;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&sh.zeroed[g]);
+      PIPE_PROF(it, 2, lane == 0);
+    }
+  } else {
+  // =============================================================================== compute groups
+  const int g = warp / GW;                   // group == buffer
+  const int gt = tid - g * GT;               // thread index inside the group
+  const int gw = warp - g * GW;              // warp index inside the group
+  PipeGroupShared& gs = sh.g[g];
+  const T* slice = reinterpret_cast<const T*>(smem_raw + static_cast<size_t>(g) * p.slice_smem_bytes);
+  const uint4* s4 = reinterpret_cast<const uint4*>(slice);
+  const int bar_id = 1 + g;
+  const int cap = kPipeCap / C;
+  const int vpt = (n_vec + GT - 1) / GT;
+
+  for (int it = g; it < n_items; it += G) {
+    const uint32_t use = static_cast<uint32_t>(it / G);
+    const int par = use & 1;
+    const int row = cid + it * n_clusters;
+    float* orow = want_probs ? p.probs + static_cast<long long>(row) * p.ld_out : nullptr;
+
+    // ---- pass 1: thread maxima (NaN-propagating)
+    PIPE_PROF(it, 3, gt == 0);
+    mbar_wait(&sh.full[g], use & 1);
+    PIPE_PROF(it, 4, gt == 0);
+    float tmax = -INFINITY;
+    for (int v = gt; v < n_vec; v += GT) {
+      float o[PV];
+      Elem<T>::unpack(s4[v], o);
+#pragma unroll
+      for (int j = 0; j < PV; ++j) {
+        float d;
+        asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(tmax), "f"(o[j]));
+        tmax = d;
+      }
+    }
+    if (tmax != tmax || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
+
+    PIPE_PROF(it, 5, gt == 0);
+    // ---- pivot = k-th largest of the GT thread maxima (see norm.cu)
+    const float sv = warp_sort_desc(tmax, lane);
+    gs.tm[gw * 32 + lane] = sv;
+    if (gt == 0) { gs.cand_cnt = 0; gs.hot_cnt = 0; gs.tau = -INFINITY; }
+    named_bar(bar_id, GT);
+    const int kk = min(k_eff, 32);
+    if (gt < GW * kk) {                      // element (list ew, position ej), one per thread, packed into few warps
+      const int ew = gt / kk, ej = gt - ew * kk;
+      const float ev = gs.tm[ew * 32 + ej];
+      int lo[GW], hi[GW];
+#pragma unroll
+      for (int w = 0; w < GW; ++w) { lo[w] = 0; hi[w] = 32; }
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+#pragma unroll
+        for (int w = 0; w < GW; ++w) {
+          const int mid = (lo[w] + hi[w]) >> 1;
+          const float y = gs.tm[w * 32 + min(mid, 31)];
+          const bool before = mid < 32 && ((y > ev) || (y == ev && w < ew));
+          lo[w] = before ? mid + 1 : lo[w];
+          hi[w] = before ? hi[w] : mid;
+        }
+      }
+      int rank = ej;
+#pragma unroll
+      for (int w = 0; w < GW; ++w) rank += (w == ew) ? 0 : lo[w];
+      if (rank == k_eff - 1) gs.tau = ev;
+    }
+    named_bar(bar_id, GT);
+    PIPE_PROF(it, 6, gt == 0);
+    const float tau = float_down(gs.tau, temp == 1.0f ? 0u : kPipeTieUlps);
+
+    // ---- pass 2: re-scan the vectors of the threads whose maximum reaches the pivot
+    uint2* my_pair = gs.r_pair[par] + crank * cap;
+    if (tmax >= tau && n_vec > gt) { const int h = atomicAdd(&gs.hot_cnt, 1); gs.hot[h] = static_cast<unsigned short>(gt); }
+    named_bar(bar_id, GT);
+    {
+      const int H = gs.hot_cnt;
+      for (int hh = gw; hh < H; hh += GW) {                   // one warp per hot thread, lanes over its vectors
+        const int t = gs.hot[hh];
+        for (int i = lane; i < vpt; i += 32) {
+          const int v = t + i * GT;
+          if (v < n_vec) {
+            float o[PV];
+            Elem<T>::unpack(s4[v], o);
+            const int gi = static_cast<int>(start) + v * PV;
+#pragma unroll
+            for (int j = 0; j < PV; ++j) {
+              if (o[j] >= tau && gi + j < V) {
+                const int pos = atomicAdd(&gs.cand_cnt, 1);
+                if (pos < cap) my_pair[pos] = make_uint2(__float_as_uint(__fdiv_rn(o[j], temp)), static_cast<uint32_t>(gi + j));
+              }
+            }
+          }
+        }
+      }
+    }
+    // the zero-fill of this item must be observed before the buffer is handed back (see header), then release it
+    PIPE_PROF(it, 7, gt == 0);
+    mbar_wait(&sh.zeroed[g], use & 1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_local(&sh.empty[g]);
+    named_bar(bar_id, GT);
+
+    PIPE_PROF(it, 8, gt == 0);
+    // ---- publish: push my candidates into every peer's receive region, then signal its mbarrier
+    const int c_mine = gs.cand_cnt;
+    const int mine = (c_mine > cap || c_mine < min(k_eff, n)) ? -1 : c_mine;     // self-check, see norm.cu
+    if (gt == 0) gs.recv_cnt2[par][crank] = make_uint2(static_cast<uint32_t>(mine), 0u);
+    if (C > 1) {
+      // fixed-size records (cap entries + the count) so that the receiver can arm its mbarrier with a known byte count
+      if (gt == 0) mbar_expect_tx(&sh.xbar[g][par], static_cast<uint32_t>(C - 1) * (static_cast<uint32_t>(cap) * 8u + 8u));
+      for (int r = 0; r < C; ++r) {
+        if (r == crank) continue;
+        for (int i = gt; i < cap; i += GT) {
+          const uint2 e = i < mine ? my_pair[i] : make_uint2(0u, 0u);
+          st_async_remote_v2(&gs.r_pair[par][crank * cap + i], e.x, e.y, &sh.xbar[g][par], r);
+        }
+        if (gt == 0) st_async_remote_v2(&gs.recv_cnt2[par][crank], static_cast<uint32_t>(mine), 0u, &sh.xbar[g][par], r);
+      }
+      mbar_wait_cluster(&sh.xbar[g][par], (use >> 1) & 1);    // every peer's candidates have landed here
+    }
+    named_bar(bar_id, GT);
+
+    PIPE_PROF(it, 9, gt == 0);
+    // ---- merge (identical in every CTA of the cluster)
+    int n_tot = 0;
+    bool ok = true;
+    int offs[kMaxCluster + 1];
+#pragma unroll
+    for (int r = 0; r < kMaxCluster; ++r) {
+      offs[r] = n_tot;
+      if (r < C) { const int c = static_cast<int>(gs.recv_cnt2[par][r].x); ok &= c >= 0; n_tot += max(c, 0); }
+    }
+    offs[kMaxCluster] = n_tot;
+    ok &= n_tot >= k_eff;
+    if (!ok) {
+      if (gt == 0) atomicOr(&sh.fail_bits[it >> 5], 1u << (it & 31));   // same decision in every CTA of the cluster
+      named_bar(bar_id, GT);
+      continue;
+    }
+#pragma unroll
+    for (int r = 0; r < kMaxCluster; ++r) {
+      if (r < C) {
+        const int cnt = offs[r + 1] - offs[r];
+        for (int i = gt; i < cnt; i += GT) {
+          const uint2 e = gs.r_pair[par][r * cap + i];
+          gs.a_val[offs[r] + i] = __uint_as_float(e.x);
+          gs.a_idx[offs[r] + i] = static_cast<int>(e.y);
+        }
+      }
+    }
+    named_bar(bar_id, GT);
+
+    // ---- rank sort (value descending, vocabulary index ascending): four threads per candidate
+    for (int base = 0; base < n_tot; base += GT / 4) {
+      const int i = base + (gt >> 2);
+      const bool live = i < n_tot;
+      const float x = live ? gs.a_val[i] : 0.f;
+      const int id = live ? gs.a_idx[i] : 0;
+      int r = 0;
+      if (live)
+#pragma unroll 4
+        for (int j = gt & 3; j < n_tot; j += 4) {
+          const float y = gs.a_val[j];
+          r += (y > x || (y == x && gs.a_idx[j] < id)) ? 1 : 0;
+        }
+      r += __shfl_xor_sync(0xffffffffu, r, 1);
+      r += __shfl_xor_sync(0xffffffffu, r, 2);
+      if (live && (gt & 3) == 0) { gs.s_val[r] = x; gs.s_idx[r] = id; }
+    }
+    named_bar(bar_id, GT);
+    PIPE_PROF(it, 10, gt == 0);
+    const float kth = gs.s_val[k_eff - 1];
+    for (int i = gt; i < n_tot; i += GT)
+      if (gs.s_val[i] >= kth && (i + 1 == n_tot || gs.s_val[i + 1] < kth)) gs.n_keep_k = i + 1;
+    named_bar(bar_id, GT);
+    const int nk = gs.n_keep_k;
+
+    // ---- top-p cut, softmax, optional sample: first warp of the group
+    if (gw == 0 && nk <= 32) {
+      const bool in_k = lane < nk;
+      const float x = in_k ? gs.s_val[lane] : -INFINITY;
+      const int id = in_k ? gs.s_idx[lane] : 0x7fffffff;
+      const float M = __shfl_sync(0xffffffffu, x, 0);
+      const float e = in_k ? expf(x - M) : 0.f;
+      const double zs = warp_sum(static_cast<double>(e));
+      int np = nk;
+      if (p.top_p > 0.f) {
+        const float sp = e * (1.0f / static_cast<float>(zs));
+        const double cum = warp_scan_incl(static_cast<double>(sp), lane);
+        const unsigned ball = __ballot_sync(0xffffffffu, in_k && static_cast<float>(cum) > p.top_p);
+        if (ball) np = min(nk, __ffs(ball));
+      }
+      const bool in_p = lane < np;
+      const double z2 = warp_sum(in_p ? static_cast<double>(e) : 0.0);
+      const float logz = logf(static_cast<float>(z2));
+      const float pr = in_p ? expf((x - M) - logz) : 0.f;
+      if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
+      if (in_p) gs.a_val[lane] = pr;
+      if (lane == 0) gs.n_keep_p = np;
+      if (p.u != nullptr && crank == 0) {
+        const int e2 = frexp_exp(__shfl_sync(0xffffffffu, pr, 0));
+        const unsigned long long wi = weight_of(pr, e2);
+        const unsigned long long tot = warp_sum(wi);
+        if (tot == 0ull) {
+          if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
+        } else {
+          const unsigned long long target = scale_target(tot, u_to_int(p.u[row]));
+          unsigned long long before = 0ull;
+          for (int j = 0; j < np; ++j) {
+            const int idj = __shfl_sync(0xffffffffu, id, j);
+            const unsigned long long wj = __shfl_sync(0xffffffffu, wi, j);
+            before += idj < id ? wj : 0ull;
+          }
+          const int top_id = __shfl_sync(0xffffffffu, id, 0);
+          if (in_p && wi > 0ull && target >= before && target < before + wi)
+            p.tok_out[row] = (pr < kProbGuard) ? top_id : id;
+        }
+      }
+    } else if (gw == 0) {
+      const float M = gs.s_val[0];
+      double zs = 0.0;
+      for (int i = lane; i < nk; i += 32) zs += static_cast<double>(expf(gs.s_val[i] - M));
+      zs = warp_sum(zs);
+      int np = nk;
+      if (p.top_p > 0.f) {
+        const float rz = 1.0f / static_cast<float>(zs);
+        double run = 0.0;
+        for (int base = 0; base < nk; base += 32) {
+          const int i = base + lane;
+          const float sp = i < nk ? expf(gs.s_val[i] - M) * rz : 0.f;
+          const double cum = warp_scan_incl(static_cast<double>(sp), lane) + run;
+          const unsigned ball = __ballot_sync(0xffffffffu, i < nk && static_cast<float>(cum) > p.top_p);
+          if (ball) { np = min(nk, base + __ffs(ball)); break; }
+          run = __shfl_sync(0xffffffffu, cum, 31);
+        }
+      }
+      double z2 = 0.0;
+      for (int i = lane; i < np; i += 32) z2 += static_cast<double>(expf(gs.s_val[i] - M));
+      z2 = warp_sum(z2);
+      const float logz = logf(static_cast<float>(z2));
+      bool badp = false;
+      for (int i = lane; i < np; i += 32) {
+        const float pr = expf((gs.s_val[i] - M) - logz);
+        badp |= !(pr >= 0.f) || isinf(pr);
+        gs.a_val[i] = pr;
+      }
+      if (badp) atomicOr(p.err_flag, kErrNanLogit);
+      if (lane == 0) gs.n_keep_p = np;
+      __syncwarp();
+      if (p.u != nullptr && crank == 0) {
+        const int e = frexp_exp(gs.a_val[0]);
+        unsigned long long tot = 0ull;
+        for (int i = lane; i < np; i += 32) tot += weight_of(gs.a_val[i], e);
+        tot = warp_sum(tot);
+        if (tot == 0ull) {
+          if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
+        } else {
+          const unsigned long long target = scale_target(tot, u_to_int(p.u[row]));
+          for (int i = lane; i < np; i += 32) {
+            const int id = gs.s_idx[i];
+            const unsigned long long wi = weight_of(gs.a_val[i], e);
+            unsigned long long before = 0ull;
+            for (int j = 0; j < np; ++j) before += (gs.s_idx[j] < id) ? weight_of(gs.a_val[j], e) : 0ull;
+            if (wi > 0ull && target >= before && target < before + wi)
+              p.tok_out[row] = (gs.a_val[i] < kProbGuard) ? gs.s_idx[0] : id;
+          }
+        }
+      }
+    }
+    named_bar(bar_id, GT);
+    if (want_probs) {                        // scatter the non-zeros over the zero-filled slice
+      const int np = gs.n_keep_p;
+      for (int i = gt; i < np; i += GT) {
+        const int id = gs.s_idx[i];
+        if (id >= start && id < start + n) orow[id] = gs.a_val[i];
+      }
+    }
+    named_bar(bar_id, GT);                   // group scratch is reused by the next item
+    PIPE_PROF(it, 11, gt == 0);
+  }
+  }  // compute groups
+
+  // =============================================================================== drained: general path for failed items
+  __syncthreads();
+  bool any = false;
+  for (int i = 0; i < (n_items + 31) / 32; ++i) any |= sh.fail_bits[i] != 0u;
+  if (any) {                                  // uniform across the cluster (every CTA recorded the same items)
+    if (C > 1) cluster.sync();                // peers have drained too: their shared memory may be re-purposed
+    NormParams p2 = p;
+    p2.force_general = 1;
+    p2.prof = nullptr;
+    for (int it = 0; it < n_items; ++it) {
+      if ((sh.fail_bits[it >> 5] >> (it & 31)) & 1u) {
+        norm_row<T, 32 + G * kPipeGroupThreads>(p2, cid + it * n_clusters);
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, int G>
+static cudaError_t launch_pipe_g(NormParams p, int rows, cudaStream_t st) {
+  auto kern = norm_topk_pipe_kernel<T, G>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const size_t smem = static_cast<size_t>(p.pipe_groups) * p.slice_smem_bytes + sizeof(PipeShared);
+  const int n_sm = 148;
+  int n_clusters = n_sm / p.cluster;
+  if (n_clusters > rows) n_clusters = rows;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(n_clusters) * p.cluster);
+  cfg.blockDim = dim3(32 + p.pipe_groups * kPipeGroupThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <typename T>
+static cudaError_t launch_pipe_typed(const NormParams& p, int rows, cudaStream_t st) {
+  return p.pipe_groups >= 3 ? launch_pipe_g<T, 3>(p, rows, st) : launch_pipe_g<T, 2>(p, rows, st);
+}
+
+// Decides whether the pipelined kernel applies; fills cluster / slice / groups.  Returns false if not applicable.
+bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
+  const size_t es = dtype == kF32 ? 4 : 2;
+  if (p.top_k <= 0 || p.top_k > kPipeFastK || p.force_general) return false;
+  const long long row_bytes = p.V * static_cast<long long>(es);
+  const bool aligned_in = (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) && ((p.ld_in * es) % 16 == 0) && (row_bytes % 16 == 0);
+  if (!aligned_in) return false;
+  const size_t budget = 227 * 1024 - sizeof(PipeShared);
+  int C = 1;
+  // smallest cluster that leaves room for at least two buffers per CTA
+  while (C < kMaxCluster && ((static_cast<size_t>((p.V + C - 1) / C + 127) & ~127ull) * es + 127) / 128 * 128 * 2 > budget) C <<= 1;
+  if (tune_cluster > 0) C = tune_cluster;
+  long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
+  while (C > 1 && slice * (C - 1) >= p.V) { C >>= 1; slice = ((p.V + C - 1) / C + 127) & ~127LL; }
+  const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
+  int G = static_cast<int>(budget / slice_bytes);
+  if (G > kPipeMaxGroups) G = kPipeMaxGroups;
+  if (G < 2) return false;
+  if (rows < 2) return false;
+  if (p.top_k + 16 > kPipeCap / C) return false;            // per-rank receive region must hold k + slack
+  {
+    // the in-kernel fallback (norm_row) re-uses the front of shared memory; the failed-item mask must survive it
+    const size_t row_need = slice_bytes + (G >= 3 ? sizeof(NormShared<32 + 3 * kPipeGroupThreads>) : sizeof(NormShared<32 + 2 * kPipeGroupThreads>));
+    if (row_need > static_cast<size_t>(G) * slice_bytes + offsetof(PipeShared, fail_bits)) return false;
+    const int n_clusters = 148 / C < rows ? 148 / C : rows;
+    if ((rows + n_clusters - 1) / n_clusters > kPipeMaxItems) return false;
+  }
+  if (slice / kPipeGroupThreads > 65535) return false;
+  p.cluster = C;
+  p.slice_elems = static_cast<int>(slice);
+  p.slice_smem_bytes = static_cast<int>(slice_bytes);
+  p.pipe_groups = G;
+  p.use_tma = 1;
+  p.vec_out = (p.probs != nullptr && reinterpret_cast<uintptr_t>(p.probs) % 16 == 0 && p.ld_out % 4 == 0) ? 1 : 0;
+  p.rows = rows;
+  return true;
+}
+
+cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStream_t st) {
+  switch (dtype) {
+    case kF32: return launch_pipe_typed<float>(p, rows, st);
+    case kBF16: return launch_pipe_typed<__nv_bfloat16>(p, rows, st);
+    case kF16: return launch_pipe_typed<__half>(p, rows, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace sd

@@ -14,11 +14,17 @@ struct NormParams {
   // filled by the launcher
   int cluster, slice_elems, slice_smem_bytes, use_tma, vec_out;
   int force_general;                       // test knob: skip the fast top-k path
+  int no_pipeline;                         // use the one-cluster-per-row kernel even where the persistent one applies
   long long* prof;                         // debug: per-CTA clock64 timestamps (16 slots per CTA), nullable
+  int rows;                                // number of logits rows
+  int pipe_groups;                         // persistent kernel: compute groups (= slice buffers) per CTA
+  const int* row_filter;                   // norm_probs_kernel: process only rows with row_filter[row] != 0
 };
 cudaError_t launch_norm(const NormParams& p, int dtype, int rows, cudaStream_t st);
 void set_norm_tuning(int cluster, int threads);
 void set_norm_prof(long long* ptr);
+bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster);
+cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStream_t st);
 
 struct VerifyParams {
   const float* p; long long p_req_stride, p_row_stride;     // target probs  (B, gamma+1, V)

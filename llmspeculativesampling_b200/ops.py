@@ -63,6 +63,9 @@ def default_flag(device) -> ErrFlag:
     return _flags[key]
 
 
+NORM_NO_PIPELINE, NORM_FORCE_GENERAL = 1, 2
+
+
 def set_tuning(norm_cluster: int = 0, norm_threads: int = 0, verify_cluster: int = 0) -> None:
     _cabi.load().sd_set_tuning(norm_cluster, norm_threads, verify_cluster)
 
@@ -77,7 +80,7 @@ def _rows2d(logits: torch.Tensor) -> torch.Tensor:
 
 def norm_probs(logits: torch.Tensor, temperature: float, top_k: int, top_p: float,
                out: Optional[torch.Tensor] = None, err: Optional[ErrFlag] = None,
-               general: bool = False) -> torch.Tensor:
+               general: bool = False, pipeline: bool = True) -> torch.Tensor:
     """(rows, V) logits (fp32/bf16/fp16) -> (rows, V) fp32 probabilities.  Kernel 1."""
     _require_cuda(logits, "logits")
     x = _rows2d(logits)
@@ -89,19 +92,16 @@ def norm_probs(logits: torch.Tensor, temperature: float, top_k: int, top_p: floa
     lib = _cabi.load()
     k = int(top_k) if top_k else 0
     p = float(top_p) if top_p else 0.0
-    if general:
-        rc = lib.sd_norm_general(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), k, p,
-                                 out.data_ptr(), out.stride(0), None, None, err.ptr(), _stream())
-    else:
-        rc = lib.sd_norm_probs(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), k, p,
-                               out.data_ptr(), out.stride(0), err.ptr(), _stream())
+    flags = (NORM_FORCE_GENERAL if general else 0) | (0 if pipeline else NORM_NO_PIPELINE)
+    rc = lib.sd_norm_probs(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), k, p,
+                           out.data_ptr(), out.stride(0), err.ptr(), flags, _stream())
     _cabi.check(rc, "sd_norm_probs")
     return out
 
 
 def norm_sample(logits: torch.Tensor, temperature: float, top_k: int, top_p: float, u: torch.Tensor,
                 probs_out: Optional[torch.Tensor] = None, tok_out: Optional[torch.Tensor] = None,
-                err: Optional[ErrFlag] = None, general: bool = False) -> torch.Tensor:
+                err: Optional[ErrFlag] = None, general: bool = False, pipeline: bool = True) -> torch.Tensor:
     """Kernel 1b: probabilities (optional, written to probs_out) and one sampled token per row."""
     _require_cuda(logits, "logits")
     x = _rows2d(logits)
@@ -113,10 +113,11 @@ def norm_sample(logits: torch.Tensor, temperature: float, top_k: int, top_p: flo
     if probs_out is not None:
         assert probs_out.dtype == torch.float32 and probs_out.shape == (rows, V) and probs_out.stride(1) == 1
     err = err or default_flag(x.device)
-    fn = _cabi.load().sd_norm_general if general else _cabi.load().sd_norm_sample
-    rc = fn(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), int(top_k or 0), float(top_p or 0.0),
-            _ptr(probs_out), probs_out.stride(0) if probs_out is not None else V, u.data_ptr(), tok_out.data_ptr(),
-            err.ptr(), _stream())
+    flags = (NORM_FORCE_GENERAL if general else 0) | (0 if pipeline else NORM_NO_PIPELINE)
+    rc = _cabi.load().sd_norm_sample(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature),
+                                     int(top_k or 0), float(top_p or 0.0), _ptr(probs_out),
+                                     probs_out.stride(0) if probs_out is not None else V, u.data_ptr(),
+                                     tok_out.data_ptr(), err.ptr(), flags, _stream())
     _cabi.check(rc, "sd_norm_sample")
     return tok_out
 

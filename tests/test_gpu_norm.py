@@ -35,14 +35,16 @@ CASES = [  # V, rows, T, k, p, scale, dtype
 
 
 @pytest.mark.parametrize("V,rows,T,k,p,scale,dtype", CASES)
-@pytest.mark.parametrize("general", [False, True])
-def test_norm_probs_matches_oracle(cuda_lib, V, rows, T, k, p, scale, dtype, general):
+@pytest.mark.parametrize("path", ["pipeline", "classic", "general"])
+def test_norm_probs_matches_oracle(cuda_lib, V, rows, T, k, p, scale, dtype, path):
+    """pipeline: persistent warp-specialised kernel where it applies (0 < top_k <= 128, aligned rows), else the
+    one-cluster-per-row kernel; classic: one-cluster-per-row kernel; general: its sort-free threshold search."""
     from llmspeculativesampling_b200 import ops
     x = make_logits(rows, V, scale, seed=V + rows + k, dtype=dtype)
     want = oracle_probs(x, T, k, p)
-    got = ops.norm_probs(x.cuda(), T, k, p, general=general)
+    got = ops.norm_probs(x.cuda(), T, k, p, general=(path == "general"), pipeline=(path == "pipeline"))
     ops.default_flag("cuda").check()
-    boundary = compare_probs(got, want, f"V={V} k={k} p={p} general={general}")
+    boundary = compare_probs(got, want, f"V={V} k={k} p={p} path={path}")
     assert boundary == 0, f"{boundary} rows with a different support (boundary ties) — none expected on these seeds"
     assert torch.allclose(got.sum(-1).cpu(), torch.ones(rows), atol=1e-5)
 
@@ -88,9 +90,10 @@ def test_massive_ties_fall_back_to_general_path(cuda_lib):
     x[3] = make_logits(1, V, 3.0, 3).bfloat16().float().round()   # coarse grid
     for (T, k, p) in [(1.0, 20, 0.9), (0.8, 20, 0.0), (1.0, 5, 0.5)]:
         want = oracle_probs(x, T, k, p)
-        got = ops.norm_probs(x.cuda(), T, k, p)
-        ops.default_flag("cuda").check()
-        assert compare_probs(got, want, f"ties k={k} p={p}") == 0
+        for pipeline in (True, False):
+            got = ops.norm_probs(x.cuda(), T, k, p, pipeline=pipeline)
+            ops.default_flag("cuda").check()
+            assert compare_probs(got, want, f"ties k={k} p={p} pipeline={pipeline}") == 0
 
 
 def test_minus_inf_and_strided_rows(cuda_lib):
@@ -137,6 +140,8 @@ def test_norm_sample_tokens_bit_exact(cuda_lib, V, T, k, p, dtype):
     # and the token-only variant (no dense write) gives the same ids
     tok2 = ops.norm_sample(x.cuda(), T, k, p, u.cuda(), probs_out=None)
     assert torch.equal(tok, tok2)
+    tok3 = ops.norm_sample(x.cuda(), T, k, p, u.cuda(), probs_out=None, pipeline=False)
+    assert torch.equal(tok, tok3)
     # against the oracle's own probabilities the only permitted divergence is a boundary tie
     wp = oracle_probs(x, T, k, p)
     diff = 0
@@ -147,3 +152,22 @@ def test_norm_sample_tokens_bit_exact(cuda_lib, V, T, k, p, dtype):
             assert margin < 1e-5, f"row {i}: token differs with margin {margin}"
             diff += 1
     assert diff <= 1
+
+
+@pytest.mark.parametrize("V,dtype,rows", [(32000, torch.float32, 576), (50272, torch.bfloat16, 300), (32000, torch.bfloat16, 149),
+                                          (128256, torch.bfloat16, 40), (262144, torch.float32, 9)])
+def test_pipeline_kernel_many_rows_with_sampling(cuda_lib, V, dtype, rows):
+    """More rows than SMs: every persistent CTA walks several work items through all buffers / parities."""
+    from llmspeculativesampling_b200 import ops
+    x = make_logits(rows, V, 3.8, seed=rows, dtype=dtype).cuda()
+    x[3] = 1.0                                               # an all-ties row must be flagged and served by the general path
+    u = torch.rand(rows, generator=torch.Generator().manual_seed(1)).cuda()
+    pa = torch.empty(rows, V, device="cuda"); pb = torch.empty(rows, V, device="cuda")
+    ta = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pa, pipeline=True)
+    tb = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pb, pipeline=False)
+    ops.default_flag("cuda").check()
+    assert torch.equal(pa, pb), "pipelined and classic kernels must agree bit for bit"
+    assert torch.equal(ta, tb)
+    sel = [0, 3, rows // 2, rows - 1]
+    want = oracle_probs(x[sel].cpu(), 0.8, 20, 0.9)
+    assert compare_probs(pa[sel], want, "pipeline vs oracle") == 0

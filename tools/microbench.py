@@ -16,6 +16,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from llmspeculativesampling_b200 import ops, build  # noqa: E402
 
 
+PIPELINE = True
+
+
 def time_norm(rows, V, dtype, T, k, p, iters=40, sample=False, write=True):
     es = torch.tensor([], dtype=dtype).element_size()
     per_set = rows * V * (es + (4 if write else 0))
@@ -28,9 +31,9 @@ def time_norm(rows, V, dtype, T, k, p, iters=40, sample=False, write=True):
 
     def run(i):
         if sample:
-            ops.norm_sample(ins[i % n_sets], T, k, p, u, probs_out=outs[i % n_sets], tok_out=tok)
+            ops.norm_sample(ins[i % n_sets], T, k, p, u, probs_out=outs[i % n_sets], tok_out=tok, pipeline=PIPELINE)
         else:
-            ops.norm_probs(ins[i % n_sets], T, k, p, out=outs[i % n_sets])
+            ops.norm_probs(ins[i % n_sets], T, k, p, out=outs[i % n_sets], pipeline=PIPELINE)
     for i in range(5):
         run(i)
     torch.cuda.synchronize()
@@ -53,10 +56,13 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--mode", default="")
     ap.add_argument("--prof", action="store_true")
+    ap.add_argument("--classic", action="store_true")
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     a = ap.parse_args()
+    global PIPELINE
+    PIPELINE = not a.classic
     build.build()
     dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[a.dtype]
     modes_all = {"topk": ("topk20_p0.9", 0.8, 20, 0.9), "dense": ("dense", 1.0, 0, 0.0), "topp": ("top_p_only", 1.0, 0, 0.9)}
@@ -67,7 +73,7 @@ def main():
         print(json.dumps(dict(kernel="norm", mode=name, rows=a.rows, V=a.V, dtype=a.dtype, ms=round(ms, 4), GBs=round(gbs, 1))))
         if a.prof:
             from llmspeculativesampling_b200 import _cabi
-            buf = torch.zeros(a.rows * 8, 16, dtype=torch.int64, device="cuda")
+            buf = torch.zeros(a.rows * 8 + 8192, 16, dtype=torch.int64, device="cuda")
             x = (torch.randn(a.rows, a.V, device="cuda") * 3.8).to(dt)
             out = torch.empty(a.rows, a.V, device="cuda")
             ops.norm_probs(x, T, k, p, out=out)
@@ -77,6 +83,23 @@ def main():
             torch.cuda.synchronize()
             _cabi.load().sd_debug_set_prof(None)
             b = buf.cpu()
+            if PIPELINE and a.mode == "topk":
+                t = b[: (b.shape[0] // 32) * 32].view(-1, 32, 16)
+                t = t[t[:, 0, 0] != 0]
+                print("persistent CTAs", t.shape[0])
+                t0 = t[:, 0, 0].clone()
+                names = ["mem: item start", "mem: buffer free", "mem: load issued + zero-filled", "grp: wait for data", "grp: data landed",
+                         "grp: pass1 done", "grp: pivot done", "grp: rescan done", "grp: buffer released", "grp: peers landed",
+                         "grp: sorted", "grp: item done"]
+                for it in range(0, 9):
+                    row = []
+                    for s_ in range(12):
+                        v = t[:, it, s_]
+                        m = v != 0
+                        row.append(f"{((v - t0)[m]).double().mean() / 1000:6.2f}" if m.any() else "   -  ")
+                    print(f"  item {it}: " + " ".join(row))
+                print("  columns (kcycles since kernel start, mean over CTAs): " + " | ".join(names))
+                return
             b = b[b[:, 0] != 0]
             names = {1: "setup+issue", 2: "first chunk landed", 3: "pass1 done", 11: "warp sort+sync", 12: "rank+sync", 13: "hot list+sync", 4: "rescan done", 5: "cluster sync", 6: "merge+sort", 7: "select+scatter", 8: "dense sums", 9: "dense write", 10: "exit"}
             prev = 0
