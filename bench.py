@@ -6,9 +6,10 @@
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): synthetic-logits
 verify microbench, V=32000, gamma=4, batch=64 requests per GPU, T=0.8, top_k=20, top_p=0.9, fp32
 logits.  ONE STEP = one pass of the hot path over one batch:
-    kernel 1b  sd_norm_sample  on the B*gamma draft rows      (filter + softmax + draft token)
-    kernel 1   sd_norm_probs   on the B*(gamma+1) target rows (filter + softmax)
-    kernel 2   sd_verify       accept / first reject / residual / inverse-CDF sample / append
+    kernel 1/1b  sd_norm_sample  ONE launch over the B*(2*gamma+1) rows of the batch (per request: gamma draft rows
+                                 that also draw the drafted token from their uniform, then gamma+1 target rows whose
+                                 uniform is -1 = "no sample"): filter + softmax (+ draft token)
+    kernel 2     sd_verify       accept / first reject / residual / inverse-CDF sample / append
 Metric: accepted tokens/s (whole job, all GPUs); emitted tokens/s and the acceptance are reported too.
 
 value     inputs resident in HBM, the three kernels of a step replayed from a CUDA graph, timed with CUDA
@@ -16,7 +17,7 @@ value     inputs resident in HBM, the three kernels of a step replayed from a CU
           rotate over distinct sets whose total exceeds 2x the 126 MB L2.
 e2e       same steps through the public tensor API with HOST buffers: every step copies its logits and
           uniforms from pinned host memory to the device and reads accept counts and tokens back.
-roofline  dominant kernel (norm, 2 launches per step): algorithmic bytes (rows * V * (4 read + 4 written))
+roofline  dominant kernel (norm, 1 launch per step): algorithmic bytes (rows * V * (4 read + 4 written))
           / its average launch duration, measured with CUDA events in an instrumented replay of the same
           K steps; peak = MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline / --impl reference   the oracle port of the reference's CPU path (oracle/ref_ops.py: the same
@@ -67,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -161,7 +162,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -185,25 +186,30 @@ def main():
     build.build()
 
     B, g = BATCH, GAMMA
+    R = 2 * g + 1                                           # rows per request: gamma draft + gamma+1 target
     n_sets = 4                                              # 4 x (73.7 MB logits + 73.7 MB probs) >> 2 x 126 MB L2
-    sets = [synth_set(rank * 100 + i, dev) for i in range(n_sets)]
-    q_probs = [torch.empty(B, g, V, device=dev) for _ in range(n_sets)]
-    p_probs = [torch.empty(B, g + 1, V, device=dev) for _ in range(n_sets)]
-    draft_tok = torch.zeros(B, g, dtype=torch.int64, device=dev)
+    logits, probs, u_rows, u_acc, u_fin = [], [], [], [], []
+    for i in range(n_sets):
+        d, t, u = synth_set(rank * 100 + i, dev)
+        logits.append(torch.cat([d, t], dim=1).contiguous())            # (B, 2g+1, V)
+        probs.append(torch.empty(B, R, V, device=dev))
+        ur = torch.full((B, R), -1.0, device=dev)
+        ur[:, :g] = u[:, :g]                                            # draft rows sample, target rows do not
+        u_rows.append(ur.view(-1).contiguous())
+        u_acc.append(u[:, g + 1:2 * g + 1].contiguous())
+        u_fin.append(u[:, 2 * g + 1].contiguous())
+        del d, t
+    tok_rows = torch.zeros(B, R, dtype=torch.int64, device=dev)
     n_acc = torch.zeros(B, dtype=torch.int32, device=dev)
     next_tok = torch.zeros(B, dtype=torch.int64, device=dev)
     acc_total = torch.zeros(1, dtype=torch.int64, device=dev)
     err = ops.ErrFlag(dev)
-    u_draft = [s[2][:, :g].contiguous().view(-1) for s in sets]
-    u_acc = [s[2][:, g + 1:2 * g + 1].contiguous() for s in sets]
-    u_fin = [s[2][:, 2 * g + 1].contiguous() for s in sets]
 
     def step(i: int, count: bool = True):
-        d, t, _ = sets[i]
-        ops.norm_sample(d.view(B * g, V), TEMP, TOP_K, TOP_P, u_draft[i], probs_out=q_probs[i].view(B * g, V),
-                        tok_out=draft_tok.view(-1), err=err)
-        ops.norm_probs(t.view(B * (g + 1), V), TEMP, TOP_K, TOP_P, out=p_probs[i].view(B * (g + 1), V), err=err)
-        ops.verify(p_probs[i], q_probs[i], draft_tok, u_acc[i], u_fin[i], n_accepted=n_acc, next_tok=next_tok, err=err)
+        ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
+                        tok_out=tok_rows.view(-1), err=err)
+        ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
+                   next_tok=next_tok, err=err)
         if count:
             acc_total.add_(n_acc.sum())
 
@@ -247,46 +253,39 @@ def main():
     accepted = int(acc_total.item())
 
     # ---- instrumented replay: per-kernel durations (same steps, eager launches bracketed by events)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     for s in range(args.steps):
         i = s % n_sets
-        d, t, _ = sets[i]
         ev[s][0].record()
-        ops.norm_sample(d.view(B * g, V), TEMP, TOP_K, TOP_P, u_draft[i], probs_out=q_probs[i].view(B * g, V),
-                        tok_out=draft_tok.view(-1), err=err)
+        ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
+                        tok_out=tok_rows.view(-1), err=err)
         ev[s][1].record()
-        ops.norm_probs(t.view(B * (g + 1), V), TEMP, TOP_K, TOP_P, out=p_probs[i].view(B * (g + 1), V), err=err)
+        ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
+                   next_tok=next_tok, err=err)
         ev[s][2].record()
-        ops.verify(p_probs[i], q_probs[i], draft_tok, u_acc[i], u_fin[i], n_accepted=n_acc, next_tok=next_tok, err=err)
-        ev[s][3].record()
     torch.cuda.synchronize()
-    t_draft = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    t_target = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    t_verify = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
-    norm_bytes = B * (2 * g + 1) * V * 8                    # logits read once (4 B) + probs written once (4 B)
-    norm_ms = t_draft + t_target
+    t_norm = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    t_verify = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    norm_bytes = B * R * V * 8                              # logits read once (4 B) + probs written once (4 B)
+    norm_ms = t_norm
     achieved = norm_bytes / (norm_ms * 1e-3) / 1e9
 
     # ---- end to end: host buffers, H2D of the step's inputs and D2H of its results inside the timed region
-    host_sets = []
-    for i in range(n_sets):
-        d, t, u = sets[i]
-        host_sets.append((d.cpu().pin_memory(), t.cpu().pin_memory(), u.cpu().pin_memory()))
-    d_dev, t_dev = torch.empty(B, g, V, device=dev), torch.empty(B, g + 1, V, device=dev)
-    u_dev = torch.empty(B, 2 * g + 2, device=dev)
-    ud_dev, uf_dev = torch.empty(B * g, device=dev), torch.empty(B, device=dev)
-    qd, pd = torch.empty(B, g, V, device=dev), torch.empty(B, g + 1, V, device=dev)
+    host_sets = [(logits[i].cpu().pin_memory(), torch.cat([u_rows[i].view(B, R), u_acc[i], u_fin[i].view(B, 1)], 1).cpu().pin_memory())
+                 for i in range(n_sets)]
+    l_dev, pr_dev = torch.empty(B, R, V, device=dev), torch.empty(B, R, V, device=dev)
+    u_dev = torch.empty(B, R + g + 1, device=dev)
+    ur_dev, ua_dev, uf_dev = torch.empty(B * R, device=dev), torch.empty(B, g, device=dev), torch.empty(B, device=dev)
     h_acc = torch.empty(B, dtype=torch.int32).pin_memory()
     h_tok = torch.empty(B, dtype=torch.int64).pin_memory()
 
     def e2e_step(i: int) -> int:
-        hd, ht, hu = host_sets[i]
-        d_dev.copy_(hd, non_blocking=True); t_dev.copy_(ht, non_blocking=True); u_dev.copy_(hu, non_blocking=True)
-        ud_dev.copy_(u_dev[:, :g].reshape(-1)); uf_dev.copy_(u_dev[:, 2 * g + 1])
-        ops.norm_sample(d_dev.view(B * g, V), TEMP, TOP_K, TOP_P, ud_dev, probs_out=qd.view(B * g, V),
-                        tok_out=draft_tok.view(-1), err=err)
-        ops.norm_probs(t_dev.view(B * (g + 1), V), TEMP, TOP_K, TOP_P, out=pd.view(B * (g + 1), V), err=err)
-        ops.verify(pd, qd, draft_tok, u_dev[:, g + 1:2 * g + 1], uf_dev, n_accepted=n_acc, next_tok=next_tok, err=err)
+        hl, hu = host_sets[i]
+        l_dev.copy_(hl, non_blocking=True); u_dev.copy_(hu, non_blocking=True)
+        ur_dev.copy_(u_dev[:, :R].reshape(-1)); ua_dev.copy_(u_dev[:, R:R + g]); uf_dev.copy_(u_dev[:, R + g])
+        ops.norm_sample(l_dev.view(B * R, V), TEMP, TOP_K, TOP_P, ur_dev, probs_out=pr_dev.view(B * R, V),
+                        tok_out=tok_rows.view(-1), err=err)
+        ops.verify(pr_dev[:, g:], pr_dev[:, :g], tok_rows[:, :g], ua_dev, uf_dev, n_accepted=n_acc, next_tok=next_tok, err=err)
         h_acc.copy_(n_acc, non_blocking=True); h_tok.copy_(next_tok, non_blocking=True)
         torch.cuda.synchronize()                            # the caller needs the tokens before the next step
         return int(h_acc.sum())
@@ -301,7 +300,7 @@ def main():
         e2e_acc += e2e_step(s % n_sets)
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = (B * (2 * g + 1) * V + B * (2 * g + 2)) * 4
+    h2d = (B * R * V + B * (R + g + 1)) * 4
     d2h = B * (4 + 8)
 
     # ---- reduce over ranks (max time, summed tokens)
@@ -334,20 +333,20 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2_policy": f"inputs and outputs rotate over {n_sets} sets "
                    f"({n_sets * norm_bytes / 1e6:.0f} MB > 2 x 126 MB L2)", "cuda_graph": True,
-                   "kernels_per_step": ["sd_norm_sample (B*gamma rows)", "sd_norm_probs (B*(gamma+1) rows)", "sd_verify"]},
+                   "kernels_per_step": ["sd_norm_sample (B*(2*gamma+1) rows, one launch)", "sd_verify"]},
         "emitted_tokens_per_s": (accepted + iters_total) / secs,
         "mean_accepted_per_iteration": accepted / iters_total,
         "request_iterations_per_s": iters_total / secs,
         "clocks": clock_info,
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 2 * args.steps,
         "e2e": {"value": e2e_acc / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "norm_probs_kernel<float,256,3> (2 launches per step)",
+                     "traffic": traffic, "kernel": "norm_topk_pipe_kernel<float,3> (1 launch per step, 576 rows)",
                      "algorithmic_bytes_per_step": norm_bytes, "ms_per_step": norm_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                      "frac_of_nominal_8TBs": achieved / 8000.0,
-                     "kernel_ms": {"norm_draft_rows": t_draft, "norm_target_rows": t_target, "verify": t_verify},
+                     "kernel_ms": {"norm": t_norm, "verify": t_verify},
                      "norm_share_of_step": norm_ms / (norm_ms + t_verify)},
     }
     if not args.no_cpu_baseline:

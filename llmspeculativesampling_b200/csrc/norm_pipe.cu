@@ -29,16 +29,19 @@ constexpr int kPipeMaxGroups = 3;
 constexpr int kPipeCap = 256;          // merged candidates per row
 constexpr int kPipeFastK = 128;
 constexpr uint32_t kPipeTieUlps = 8;
+constexpr int kPipeWarpCap = 48;       // candidates one warp may collect per work item
 constexpr int kPipeMaxItems = 4096;    // work items one cluster can walk (bit mask of failed items)
 
 struct alignas(16) PipeGroupShared {
   float tm[kPipeGroupThreads];                       // per-warp sorted thread maxima
-  unsigned short hot[kPipeGroupThreads];
-  int cand_cnt, hot_cnt, n_keep_k, n_keep_p;
+  uint2 w_pair[kPipeGroupWarps][kPipeWarpCap];       // candidates found by each warp (logit/T bits, index)
+  int w_cnt[kPipeGroupWarps];
+  int n_keep_p;
   float tau;
   uint2 recv_cnt2[2][kMaxCluster];                   // [item parity][cluster rank].x = candidate count (-1: general path)
   uint2 r_pair[2][kPipeCap];                         // receive regions (logit/T bits, index), double buffered by item parity
-  float a_val[kPipeCap]; int a_idx[kPipeCap];        // merged list -> final probabilities
+  unsigned long long a_key[kPipeCap];                // merged list as sort keys (value key << 32 | ~index)
+  float a_val[kPipeCap];                             // final probabilities (sorted order)
   float s_val[kPipeCap]; int s_idx[kPipeCap];        // sorted list
 };
 
@@ -120,7 +123,11 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     fence_barrier_init();
   }
   for (int i = tid; i < kPipeMaxItems / 32; i += blockDim.x) sh.fail_bits[i] = 0u;
-  if (C > 1) cluster.sync(); else __syncthreads();     // barriers initialised and every peer CTA is running
+  __syncthreads();
+  // "my mbarriers are initialised": peers may only push candidates to me (st.async) after they waited on this; the
+  // wait is deferred to the first push so that the loads start immediately
+  if (C > 1) cluster.barrier_arrive();
+  bool shook = (C == 1);
 
   // =============================================================================== memory warp
   if (warp == G * GW) {
@@ -154,6 +161,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
       __syncwarp();
       if (lane == 0) mbar_arrive_local(&sh.zeroed[g]);
       PIPE_PROF(it, 2, lane == 0);
+      if (!shook && (it + 1 == n_items || it + 1 >= G)) { cluster.barrier_wait(); shook = true; }
     }
   } else {
   // =============================================================================== compute groups
@@ -178,7 +186,11 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     mbar_wait(&sh.full[g], use & 1);
     PIPE_PROF(it, 4, gt == 0);
     float tmax = -INFINITY;
-    for (int v = gt; v < n_vec; v += GT) {
+    // ownership: in round i thread t owns vector i*GT + ((t + i) mod GT): consecutive lanes read consecutive vectors
+    // here, and a warp that later re-reads ONE thread's vectors (lane = round) also walks consecutive banks
+    for (int i = 0; i < vpt; ++i) {
+      const int v = i * GT + ((gt + i) & (GT - 1));
+      if (v >= n_vec) continue;
       float o[PV];
       Elem<T>::unpack(s4[v], o);
 #pragma unroll
@@ -194,7 +206,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     // ---- pivot = k-th largest of the GT thread maxima (see norm.cu)
     const float sv = warp_sort_desc(tmax, lane);
     gs.tm[gw * 32 + lane] = sv;
-    if (gt == 0) { gs.cand_cnt = 0; gs.hot_cnt = 0; gs.tau = -INFINITY; }
+    if (gt == 0) gs.tau = -INFINITY;
     named_bar(bar_id, GT);
     const int kk = min(k_eff, 32);
     if (gt < GW * kk) {                      // element (list ew, position ej), one per thread, packed into few warps
@@ -223,31 +235,40 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     PIPE_PROF(it, 6, gt == 0);
     const float tau = float_down(gs.tau, temp == 1.0f ? 0u : kPipeTieUlps);
 
-    // ---- pass 2: re-scan the vectors of the threads whose maximum reaches the pivot
+    // ---- pass 2: every warp re-scans the vectors of ITS OWN threads whose maximum reaches the pivot (lane = round
+    //      index: bank-conflict free thanks to the swizzled ownership) and appends to a private candidate region:
+    //      no shared-memory atomics, no hot list, no barrier
     uint2* my_pair = gs.r_pair[par] + crank * cap;
-    if (tmax >= tau && n_vec > gt) { const int h = atomicAdd(&gs.hot_cnt, 1); gs.hot[h] = static_cast<unsigned short>(gt); }
-    named_bar(bar_id, GT);
+    int wc = 0;                                               // candidates found by this warp (warp-uniform)
     {
-      const int H = gs.hot_cnt;
-      for (int hh = gw; hh < H; hh += GW) {                   // one warp per hot thread, lanes over its vectors
-        const int t = gs.hot[hh];
-        for (int i = lane; i < vpt; i += 32) {
-          const int v = t + i * GT;
-          if (v < n_vec) {
-            float o[PV];
-            Elem<T>::unpack(s4[v], o);
-            const int gi = static_cast<int>(start) + v * PV;
+      unsigned hm = __ballot_sync(0xffffffffu, tmax >= tau);
+      while (hm) {
+        const int t = gw * 32 + (__ffs(hm) - 1);
+        hm &= hm - 1;
+        for (int i0 = 0; i0 < vpt; i0 += 32) {
+          const int v = (i0 + lane) * GT + ((t + i0 + lane) & (GT - 1));
+          const bool inb = i0 + lane < vpt && v < n_vec;
+          float o[PV];
 #pragma unroll
-            for (int j = 0; j < PV; ++j) {
-              if (o[j] >= tau && gi + j < V) {
-                const int pos = atomicAdd(&gs.cand_cnt, 1);
-                if (pos < cap) my_pair[pos] = make_uint2(__float_as_uint(__fdiv_rn(o[j], temp)), static_cast<uint32_t>(gi + j));
-              }
+          for (int j = 0; j < PV; ++j) o[j] = -INFINITY;
+          if (inb) Elem<T>::unpack(s4[v], o);
+          const int gi = static_cast<int>(start) + v * PV;
+#pragma unroll
+          for (int j = 0; j < PV; ++j) {
+            const bool hit = inb && o[j] >= tau && gi + j < V;
+            const unsigned cm = __ballot_sync(0xffffffffu, hit);
+            if (cm) {                                          // warp-uniform
+              const int pos = wc + __popc(cm & ((1u << lane) - 1u));
+              if (hit && pos < kPipeWarpCap)
+                gs.w_pair[gw][pos] = make_uint2(__float_as_uint(__fdiv_rn(o[j], temp)), static_cast<uint32_t>(gi + j));
+              wc += __popc(cm);
             }
           }
         }
       }
+      if (lane == 0) gs.w_cnt[gw] = wc;
     }
+    PIPE_PROF(it, 14, gt == 0);
     // the zero-fill of this item must be observed before the buffer is handed back (see header), then release it
     PIPE_PROF(it, 7, gt == 0);
     mbar_wait(&sh.zeroed[g], use & 1);
@@ -257,18 +278,30 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
 
     PIPE_PROF(it, 8, gt == 0);
     // ---- publish: push my candidates into every peer's receive region, then signal its mbarrier
-    const int c_mine = gs.cand_cnt;
-    const int mine = (c_mine > cap || c_mine < min(k_eff, n)) ? -1 : c_mine;     // self-check, see norm.cu
+    int wofs[GW + 1];
+    bool w_over = false;
+    wofs[0] = 0;
+#pragma unroll
+    for (int w = 0; w < GW; ++w) { const int c = gs.w_cnt[w]; w_over |= c > kPipeWarpCap; wofs[w + 1] = wofs[w] + c; }
+    const int c_mine = wofs[GW];
+    const int mine = (w_over || c_mine > cap || c_mine < min(k_eff, n)) ? -1 : c_mine;     // self-check, see norm.cu
     if (gt == 0) gs.recv_cnt2[par][crank] = make_uint2(static_cast<uint32_t>(mine), 0u);
+    uint2 my_e = make_uint2(0u, 0u);                          // entry gt of my (concatenated) candidate list
+    for (int i = gt; i < mine; i += GT) {
+      int w = 0;
+#pragma unroll
+      for (int q = 1; q < GW; ++q) w += i >= wofs[q] ? 1 : 0;
+      const uint2 e = gs.w_pair[w][i - wofs[w]];
+      my_pair[i] = e;
+      if (i == gt) my_e = e;
+    }
     if (C > 1) {
+      if (!shook) { cluster.barrier_wait(); shook = true; }   // every peer's mbarriers are initialised
       // fixed-size records (cap entries + the count) so that the receiver can arm its mbarrier with a known byte count
       if (gt == 0) mbar_expect_tx(&sh.xbar[g][par], static_cast<uint32_t>(C - 1) * (static_cast<uint32_t>(cap) * 8u + 8u));
       for (int r = 0; r < C; ++r) {
         if (r == crank) continue;
-        for (int i = gt; i < cap; i += GT) {
-          const uint2 e = i < mine ? my_pair[i] : make_uint2(0u, 0u);
-          st_async_remote_v2(&gs.r_pair[par][crank * cap + i], e.x, e.y, &sh.xbar[g][par], r);
-        }
+        if (gt < cap) st_async_remote_v2(&gs.r_pair[par][crank * cap + gt], my_e.x, my_e.y, &sh.xbar[g][par], r);
         if (gt == 0) st_async_remote_v2(&gs.recv_cnt2[par][crank], static_cast<uint32_t>(mine), 0u, &sh.xbar[g][par], r);
       }
       mbar_wait_cluster(&sh.xbar[g][par], (use >> 1) & 1);    // every peer's candidates have landed here
@@ -298,37 +331,45 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
         const int cnt = offs[r + 1] - offs[r];
         for (int i = gt; i < cnt; i += GT) {
           const uint2 e = gs.r_pair[par][r * cap + i];
-          gs.a_val[offs[r] + i] = __uint_as_float(e.x);
-          gs.a_idx[offs[r] + i] = static_cast<int>(e.y);
+          const float xv = __uint_as_float(e.x) + 0.0f;                     // -0 -> +0: equal values must tie on the index
+          gs.a_key[offs[r] + i] = (static_cast<unsigned long long>(f2key(xv)) << 32) | (0xffffffffu - e.y);
         }
       }
     }
     named_bar(bar_id, GT);
+    PIPE_PROF(it, 12, gt == 0);
 
-    // ---- rank sort (value descending, vocabulary index ascending): four threads per candidate
+    // ---- rank sort on 64-bit keys (value descending, then vocabulary index ascending): four threads per candidate,
+    //      branch-free inner loop
     for (int base = 0; base < n_tot; base += GT / 4) {
       const int i = base + (gt >> 2);
       const bool live = i < n_tot;
-      const float x = live ? gs.a_val[i] : 0.f;
-      const int id = live ? gs.a_idx[i] : 0;
+      const unsigned long long ki = live ? gs.a_key[i] : 0ull;
       int r = 0;
-      if (live)
+      if (live) {
 #pragma unroll 4
-        for (int j = gt & 3; j < n_tot; j += 4) {
-          const float y = gs.a_val[j];
-          r += (y > x || (y == x && gs.a_idx[j] < id)) ? 1 : 0;
-        }
+        for (int j = gt & 3; j < n_tot; j += 4) r += gs.a_key[j] > ki ? 1 : 0;
+      }
       r += __shfl_xor_sync(0xffffffffu, r, 1);
       r += __shfl_xor_sync(0xffffffffu, r, 2);
-      if (live && (gt & 3) == 0) { gs.s_val[r] = x; gs.s_idx[r] = id; }
+      if (live && (gt & 3) == 0) {
+        gs.s_val[r] = key2f(static_cast<uint32_t>(ki >> 32));
+        gs.s_idx[r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(ki & 0xffffffffull));
+      }
     }
+    PIPE_PROF(it, 13, gt == 0);
     named_bar(bar_id, GT);
     PIPE_PROF(it, 10, gt == 0);
-    const float kth = gs.s_val[k_eff - 1];
-    for (int i = gt; i < n_tot; i += GT)
-      if (gs.s_val[i] >= kth && (i + 1 == n_tot || gs.s_val[i + 1] < kth)) gs.n_keep_k = i + 1;
-    named_bar(bar_id, GT);
-    const int nk = gs.n_keep_k;
+    int nk = 0;
+    if (gw == 0) {                           // entries >= the k-th value form a prefix of the sorted list (ties kept)
+      const float kth = gs.s_val[k_eff - 1];
+      for (int base = 0; base < n_tot; base += 32) {
+        const int i = base + lane;
+        const unsigned ge = __ballot_sync(0xffffffffu, i < n_tot && gs.s_val[i] >= kth);
+        nk += __popc(ge);
+        if (ge != 0xffffffffu) break;
+      }
+    }
 
     // ---- top-p cut, softmax, optional sample: first warp of the group
     if (gw == 0 && nk <= 32) {
@@ -352,7 +393,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
       if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
       if (in_p) gs.a_val[lane] = pr;
       if (lane == 0) gs.n_keep_p = np;
-      if (p.u != nullptr && crank == 0) {
+      if (p.u != nullptr && crank == 0 && p.u[row] >= 0.f) {
         const int e2 = frexp_exp(__shfl_sync(0xffffffffu, pr, 0));
         const unsigned long long wi = weight_of(pr, e2);
         const unsigned long long tot = warp_sum(wi);
@@ -402,7 +443,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
       if (badp) atomicOr(p.err_flag, kErrNanLogit);
       if (lane == 0) gs.n_keep_p = np;
       __syncwarp();
-      if (p.u != nullptr && crank == 0) {
+      if (p.u != nullptr && crank == 0 && p.u[row] >= 0.f) {
         const int e = frexp_exp(gs.a_val[0]);
         unsigned long long tot = 0ull;
         for (int i = lane; i < np; i += 32) tot += weight_of(gs.a_val[i], e);
@@ -436,6 +477,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
   }  // compute groups
 
   // =============================================================================== drained: general path for failed items
+  if (!shook) cluster.barrier_wait();
   __syncthreads();
   bool any = false;
   for (int i = 0; i < (n_items + 31) / 32; ++i) any |= sh.fail_bits[i] != 0u;

@@ -296,7 +296,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
         if (in_p) sh.a_val[lane] = pr;
         if (lane == 0) sh.n_keep_p = np;
-        if (p.u != nullptr && cx.crank == 0) {   // inverse-CDF sample in vocabulary order over the kept list
+        if (p.u != nullptr && cx.crank == 0 && p.u[row] >= 0.f) {   // inverse-CDF sample in vocabulary order over the kept list
           const int e2 = frexp_exp(__shfl_sync(0xffffffffu, pr, 0));
           const unsigned long long wi = weight_of(pr, e2);
           const unsigned long long tot = warp_sum(wi);
@@ -347,7 +347,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         if (badp) atomicOr(p.err_flag, kErrNanLogit);
         if (lane == 0) sh.n_keep_p = np;
         __syncwarp();
-        if (p.u != nullptr && cx.crank == 0) {
+        if (p.u != nullptr && cx.crank == 0 && p.u[row] >= 0.f) {
           const int e = frexp_exp(sh.a_val[0]);
           unsigned long long tot = 0ull;
           for (int i = lane; i < np; i += 32) tot += weight_of(sh.a_val[i], e);
@@ -443,7 +443,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         for (int j = 0; j < PV; ++j) if (v * PV + j < n) o[v * PV + j] = pr[j];
       }
     }
-    if (p.u != nullptr) {
+    if (p.u != nullptr && p.u[row] >= 0.f) {
       int amin = 0x7fffffff;
       for_each_elem<T, THREADS>(slice, n_vec, start, tid, [&](float l, int g) { if (l == Ml && g < V) amin = min(amin, g); });
       const int argmax = cx.allreduce_min(amin);
@@ -562,7 +562,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         for (int j = 0; j < PV; ++j) if (v * PV + j < n) o[v * PV + j] = pr[j];
       }
     }
-    if (p.u != nullptr) {
+    if (p.u != nullptr && p.u[row] >= 0.f) {
       // argmax index for the < 1e-9 guard (first index holding the row maximum)
       int amin = 0x7fffffff;
       for_each_elem<T, THREADS>(slice, n_vec, start, tid, [&](float l, int g) { if (l == Ml && g < V) amin = min(amin, g); });

@@ -168,6 +168,13 @@ def test_pipeline_kernel_many_rows_with_sampling(cuda_lib, V, dtype, rows):
     ops.default_flag("cuda").check()
     assert torch.equal(pa, pb), "pipelined and classic kernels must agree bit for bit"
     assert torch.equal(ta, tb)
+    # u < 0 switches sampling off for that row (its tok_out entry is left untouched)
+    u2 = u.clone(); u2[1::2] = -1.0
+    for pipeline in (True, False):
+        tc = torch.full((rows,), -5, dtype=torch.int64, device="cuda")
+        ops.norm_sample(x, 0.8, 20, 0.9, u2, probs_out=pb, tok_out=tc, pipeline=pipeline)
+        assert torch.equal(tc[0::2], ta[0::2]) and bool((tc[1::2] == -5).all())
+        assert torch.equal(pa, pb)
     sel = [0, 3, rows // 2, rows - 1]
     want = oracle_probs(x[sel].cpu(), 0.8, 20, 0.9)
     assert compare_probs(pa[sel], want, "pipeline vs oracle") == 0

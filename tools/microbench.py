@@ -90,15 +90,16 @@ def main():
                 t0 = t[:, 0, 0].clone()
                 names = ["mem: item start", "mem: buffer free", "mem: load issued + zero-filled", "grp: wait for data", "grp: data landed",
                          "grp: pass1 done", "grp: pivot done", "grp: rescan done", "grp: buffer released", "grp: peers landed",
-                         "grp: sorted", "grp: item done"]
+                         "grp: sorted", "grp: item done", "grp: compacted", "grp: ranks done", "grp: hot list"]
                 for it in range(0, 9):
                     row = []
-                    for s_ in range(12):
+                    for s_ in [0, 1, 2, 3, 4, 5, 6, 14, 7, 8, 9, 12, 13, 10, 11]:
                         v = t[:, it, s_]
                         m = v != 0
                         row.append(f"{((v - t0)[m]).double().mean() / 1000:6.2f}" if m.any() else "   -  ")
                     print(f"  item {it}: " + " ".join(row))
-                print("  columns (kcycles since kernel start, mean over CTAs): " + " | ".join(names))
+                order = [0, 1, 2, 3, 4, 5, 6, 14, 7, 8, 9, 12, 13, 10, 11]
+                print("  columns (kcycles since kernel start, mean over CTAs): " + " | ".join(names[o] if o < 12 else names[o] for o in [0,1,2,3,4,5,6] ) + " | hot list | rescan done | released | peers landed | compacted | ranks done | sorted | item done")
                 return
             b = b[b[:, 0] != 0]
             names = {1: "setup+issue", 2: "first chunk landed", 3: "pass1 done", 11: "warp sort+sync", 12: "rank+sync", 13: "hot list+sync", 4: "rescan done", 5: "cluster sync", 6: "merge+sort", 7: "select+scatter", 8: "dense sums", 9: "dense write", 10: "exit"}
