@@ -252,9 +252,29 @@ def main():
     err.check()
     accepted = int(acc_total.item())
 
-    # ---- instrumented replay: per-kernel durations (same steps, eager launches bracketed by events)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    for s in range(args.steps):
+    # ---- per-kernel durations, same steps: (a) the norm kernel alone, replayed back to back from a CUDA graph that
+    #      holds one launch per input set (no host or event overhead between launches), (b) eager launches bracketed
+    #      by events to split a step into norm / verify shares
+    with torch.cuda.stream(side):
+        g_norm = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_norm, stream=side):
+            for i in range(n_sets):
+                ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
+                                tok_out=tok_rows.view(-1), err=err)
+    torch.cuda.current_stream().wait_stream(side)
+    reps = max(1, args.steps // n_sets)
+    for _ in range(3):
+        g_norm.replay()
+    torch.cuda.synchronize()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for _ in range(reps):
+        g_norm.replay()
+    n1.record()
+    torch.cuda.synchronize()
+    norm_ms = n0.elapsed_time(n1) / (reps * n_sets)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(min(args.steps, 200))]
+    for s in range(len(ev)):
         i = s % n_sets
         ev[s][0].record()
         ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
@@ -264,10 +284,9 @@ def main():
                    next_tok=next_tok, err=err)
         ev[s][2].record()
     torch.cuda.synchronize()
-    t_norm = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    t_verify = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    t_norm = sum(e[0].elapsed_time(e[1]) for e in ev) / len(ev)
+    t_verify = sum(e[1].elapsed_time(e[2]) for e in ev) / len(ev)
     norm_bytes = B * R * V * 8                              # logits read once (4 B) + probs written once (4 B)
-    norm_ms = t_norm
     achieved = norm_bytes / (norm_ms * 1e-3) / 1e9
 
     # ---- end to end: host buffers, H2D of the step's inputs and D2H of its results inside the timed region
@@ -346,23 +365,25 @@ def main():
                      "algorithmic_bytes_per_step": norm_bytes, "ms_per_step": norm_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                      "frac_of_nominal_8TBs": achieved / 8000.0,
-                     "kernel_ms": {"norm": t_norm, "verify": t_verify},
-                     "norm_share_of_step": norm_ms / (norm_ms + t_verify)},
+                     "timing": "CUDA events around back-to-back graph replays of the norm launch (4 rotating input sets)",
+                     "kernel_ms_eager_with_events": {"norm": t_norm, "verify": t_verify},
+                     "norm_share_of_step": t_norm / (t_norm + t_verify)},
     }
     if not args.no_cpu_baseline:
-        per = 4
+        per = 16
         cores = os.cpu_count() or 1
-        a1, e1_, dt1 = time_oracle(4, 1, per, 1)
-        best = (a1 / dt1, 1, a1, dt1)
+        a1, _, dt1 = time_oracle(1, 1, per, 1)
+        best_threads, best_rate = 1, a1 / dt1
         if cores > 1:
-            a2, _, dt2 = time_oracle(2, 1, per, cores)
-            if a2 / dt2 > best[0]:
-                a2, _, dt2 = time_oracle(4, 1, per, cores)
-                best = (a2 / dt2, cores, a2, dt2)
-        line["cpu_baseline"] = {"value": best[0], "unit": "tokens/s", "cores": best[1], "kind": "port",
-                                "sample": f"4 steps x {per} requests of the same workload through oracle/ref_ops.py "
-                                          f"(the reference's ATen op chain, row by row), torch threads={best[1]} "
-                                          f"of {cores} host cores; {best[3]:.1f} s of CPU work"}
+            a2, _, dt2 = time_oracle(1, 1, per, cores)
+            if a2 / dt2 > best_rate:
+                best_threads, best_rate = cores, a2 / dt2
+        n_steps = 12
+        acc_c, _, dt_c = time_oracle(n_steps, 0, per, best_threads)
+        line["cpu_baseline"] = {"value": acc_c / dt_c, "unit": "tokens/s", "cores": best_threads, "kind": "port",
+                                "sample": f"{n_steps} steps x {per} requests of the same workload ({n_steps * per * (2 * GAMMA + 1)} rows "
+                                          f"+ verify) through oracle/ref_ops.py (the reference's ATen op chain, row by row), "
+                                          f"torch threads={best_threads} of {cores} host cores; {dt_c:.1f} s of CPU work"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
