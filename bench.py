@@ -200,18 +200,19 @@ def main():
         u_fin.append(u[:, 2 * g + 1].contiguous())
         del d, t
     tok_rows = torch.zeros(B, R, dtype=torch.int64, device=dev)
+    cmp_rows = ops.CompactRows(B * R, dev)                  # compact top-k lists written by kernel 1, read by kernel 2
+    c_all, c_q, c_p = cmp_rows.view(), cmp_rows.view(0, 1), cmp_rows.view(g, 1)
     n_acc = torch.zeros(B, dtype=torch.int32, device=dev)
     next_tok = torch.zeros(B, dtype=torch.int64, device=dev)
-    acc_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    acc_total = torch.zeros(2, dtype=torch.int64, device=dev)     # [accepted tokens, requests verified], updated by kernel 2
     err = ops.ErrFlag(dev)
 
     def step(i: int, count: bool = True):
         ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
-                        tok_out=tok_rows.view(-1), err=err)
+                        tok_out=tok_rows.view(-1), err=err, compact=c_all)
         ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
-                   next_tok=next_tok, err=err)
-        if count:
-            acc_total.add_(n_acc.sum())
+                   next_tok=next_tok, err=err, p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R,
+                   stats=acc_total if count else None)
 
     # one CUDA graph per input set (3 kernels + the accept-count accumulation)
     for i in range(n_sets):
@@ -250,7 +251,8 @@ def main():
     ms = e0.elapsed_time(e1)
     clock_info = clocks.stop()
     err.check()
-    accepted = int(acc_total.item())
+    accepted = int(acc_total[0].item())
+    assert int(acc_total[1].item()) == args.steps * B, "kernel 2 must have verified every request of every step"
 
     # ---- per-kernel durations, same steps: (a) the norm kernel alone, replayed back to back from a CUDA graph that
     #      holds one launch per input set (no host or event overhead between launches), (b) eager launches bracketed
@@ -260,7 +262,7 @@ def main():
         with torch.cuda.graph(g_norm, stream=side):
             for i in range(n_sets):
                 ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
-                                tok_out=tok_rows.view(-1), err=err)
+                                tok_out=tok_rows.view(-1), err=err, compact=c_all)
     torch.cuda.current_stream().wait_stream(side)
     reps = max(1, args.steps // n_sets)
     for _ in range(3):
@@ -278,10 +280,10 @@ def main():
         i = s % n_sets
         ev[s][0].record()
         ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
-                        tok_out=tok_rows.view(-1), err=err)
+                        tok_out=tok_rows.view(-1), err=err, compact=c_all)
         ev[s][1].record()
         ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
-                   next_tok=next_tok, err=err)
+                   next_tok=next_tok, err=err, p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
         ev[s][2].record()
     torch.cuda.synchronize()
     t_norm = sum(e[0].elapsed_time(e[1]) for e in ev) / len(ev)
@@ -303,8 +305,9 @@ def main():
         l_dev.copy_(hl, non_blocking=True); u_dev.copy_(hu, non_blocking=True)
         ur_dev.copy_(u_dev[:, :R].reshape(-1)); ua_dev.copy_(u_dev[:, R:R + g]); uf_dev.copy_(u_dev[:, R + g])
         ops.norm_sample(l_dev.view(B * R, V), TEMP, TOP_K, TOP_P, ur_dev, probs_out=pr_dev.view(B * R, V),
-                        tok_out=tok_rows.view(-1), err=err)
-        ops.verify(pr_dev[:, g:], pr_dev[:, :g], tok_rows[:, :g], ua_dev, uf_dev, n_accepted=n_acc, next_tok=next_tok, err=err)
+                        tok_out=tok_rows.view(-1), err=err, compact=c_all)
+        ops.verify(pr_dev[:, g:], pr_dev[:, :g], tok_rows[:, :g], ua_dev, uf_dev, n_accepted=n_acc, next_tok=next_tok, err=err,
+                   p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
         h_acc.copy_(n_acc, non_blocking=True); h_tok.copy_(next_tok, non_blocking=True)
         torch.cuda.synchronize()                            # the caller needs the tokens before the next step
         return int(h_acc.sum())
@@ -352,7 +355,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2_policy": f"inputs and outputs rotate over {n_sets} sets "
                    f"({n_sets * norm_bytes / 1e6:.0f} MB > 2 x 126 MB L2)", "cuda_graph": True,
-                   "kernels_per_step": ["sd_norm_sample (B*(2*gamma+1) rows, one launch)", "sd_verify"]},
+                   "kernels_per_step": ["sd_norm_sample (B*(2*gamma+1) rows, one launch; dense probs + compact lists)",
+                                        "sd_verify (sparse path on the compact lists)"]},
         "emitted_tokens_per_s": (accepted + iters_total) / secs,
         "mean_accepted_per_iteration": accepted / iters_total,
         "request_iterations_per_s": iters_total / secs,

@@ -46,6 +46,21 @@ extern "C" {
 #define SD_ERR_ZERO_Q 4      /* q[drafted token] == 0 (ZeroDivisionError)     -> 's'                 */
 #define SD_ERR_BAD_TOKEN 8   /* drafted token id outside [0, V)                                       */
 
+/* Optional compact form of top-k filtered probability rows (all pointers device memory, caller-owned).
+ * Logical row r owns compact row cr = r * row_stride:  cnt[cr] = number of kept (non-zero) entries, or -1 when the
+ * row has no compact form (it was served by the dense / general path or has more than `cap` entries);
+ * idx[cr * cap + j], val[cr * cap + j], j < cnt[cr], are the vocabulary indices and probabilities (any order).
+ * Kernel 1 writes it next to the dense row; kernel 2 can then verify from a few hundred bytes per request instead of
+ * two dense vocabulary rows.  The reference has no counterpart: it always materialises dense rows
+ * (sampling/kvcache_model.py:246). */
+typedef struct sd_compact {
+  int32_t* cnt;
+  int32_t* idx;
+  float* val;
+  int32_t cap;
+  int64_t row_stride;
+} sd_compact_t;
+
 int sd_version(void);
 const char* sd_last_error(void);
 
@@ -68,7 +83,8 @@ void sd_debug_set_prof(int64_t* device_buf);
  *   probs   (rows, V) fp32, row stride ld_out: exp(log_softmax(filtered)) (utils.py:199), 0 outside
  * Sets SD_ERR_NORM_LOGITS where the reference raises 'norm logits error' (utils.py:203-207). */
 int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
-                  float top_p, float* probs, int64_t ld_out, int* err_flag, int flags, void* stream);
+                  float top_p, float* probs, int64_t ld_out, const sd_compact_t* compact, int* err_flag, int flags,
+                  void* stream);
 
 /* `flags` of the two norm entry points.  By default, for 0 < top_k <= 128 and 16-byte aligned rows the persistent,
  * warp-specialised pipeline kernel runs (one CTA per SM: a memory warp streams slices in by TMA and zero-fills the
@@ -83,8 +99,8 @@ int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_
  * replaces norm_logits + sample(q) of sampling/kvcache_model.py:280-283 and
  * sampling/autoregressive_sampling.py:41-44.  `probs` may be NULL (token only). */
 int sd_norm_sample(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
-                   float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out, int* err_flag,
-                   int flags, void* stream);
+                   float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                   const sd_compact_t* compact, int* err_flag, int flags, void* stream);
 
 /* sample — one inverse-CDF draw per row of non-negative weights.  Replaces sampling/utils.py:213-233. */
 int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const float* u, int64_t* tok_out, int* err_flag,
@@ -104,12 +120,19 @@ int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const flo
  *   tokens / seq_len  optional fused append: tokens[b, seq_len[b] + n_acc] = next_tok;
  *            seq_len[b] += n_acc + 1  — with static caches this counter write IS the rollback of
  *            sampling/kvcache_model.py:360-431 (approx rollback(n+1) :2000, target :2015/:2023)
- *   active   optional (B,) int32; requests with active[b] == 0 are skipped entirely. */
+ *   active   optional (B,) int32; requests with active[b] == 0 are skipped entirely.
+ *   p_compact / q_compact  optional compact lists of the same rows (request b, row i -> logical row
+ *            b * p_cmp_req_stride + i, scaled by the struct's row_stride); when both are given one warp per request
+ *            works from the lists (sparse path) and only requests whose lists are unavailable read dense rows.
+ *   stats    optional device uint64[2]: [0] += accepted tokens, [1] += requests verified (acc_len / call counters of
+ *            sampling/speculative_sampling.py:1991, 2062-2073 without a host round trip). */
 int sd_verify(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const float* q_probs,
               int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
               const float* u_acc, int64_t u_acc_stride, const float* u_final, int B, int gamma, int64_t V, int strict,
               int32_t* n_accepted, int64_t* next_tok, float* ratios, int32_t* tie_count, int64_t* tokens,
-              int64_t tokens_stride, int32_t* seq_len, const int32_t* active, int* err_flag, void* stream);
+              int64_t tokens_stride, int32_t* seq_len, const int32_t* active, const sd_compact_t* p_compact,
+              int64_t p_cmp_req_stride, const sd_compact_t* q_compact, int64_t q_cmp_req_stride, uint64_t* stats,
+              int* err_flag, void* stream);
 
 /* max_fn — out = max(x,0) / (sum(max(x,0)) + 1e-6) per row.  Replaces sampling/utils.py:236-245. */
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream);

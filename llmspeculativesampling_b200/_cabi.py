@@ -19,15 +19,20 @@ SIGNATURES = {
     "sd_last_error": (C.c_char_p, []),
     "sd_set_tuning": (None, [i32, i32, i32]),
     "sd_debug_set_prof": (None, [vp]),
-    "sd_norm_probs": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, i32, vp]),
-    "sd_norm_sample": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, i32, vp]),
+    "sd_norm_probs": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, i32, vp]),
+    "sd_norm_sample": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp, i32, vp]),
     "sd_sample": (i32, [vp, i64, i64, i64, vp, vp, vp, vp]),
     "sd_verify": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, vp, i32, i32, i64, i32,
-                        vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]),
+                        vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
     "sd_max_fn": (i32, [vp, i64, i64, i64, vp, i64, vp]),
     "sd_kv_append": (i32, [vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sd_build_step": (i32, [vp, i64, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]),
 }
+
+class Compact(C.Structure):
+    """struct sd_compact (include/specdec_b200.h)"""
+    _fields_ = [("cnt", vp), ("idx", vp), ("val", vp), ("cap", C.c_int32), ("row_stride", i64)]
+
 
 _lib = None
 

@@ -35,9 +35,17 @@ void sd_set_tuning(int norm_cluster, int norm_threads, int verify_cluster) {
 
 void sd_debug_set_prof(int64_t* device_buf) { sd::set_norm_prof(reinterpret_cast<long long*>(device_buf)); }
 
+static sd::Compact to_compact(const sd_compact_t* c) {
+  sd::Compact o = {};
+  if (c != nullptr && c->cnt != nullptr && c->idx != nullptr && c->val != nullptr && c->cap > 0) {
+    o.cnt = c->cnt; o.idx = c->idx; o.val = c->val; o.cap = c->cap; o.row_stride = c->row_stride;
+  }
+  return o;
+}
+
 static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
                        int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
-                       int* err_flag, int flags, void* stream) {
+                       const sd_compact_t* compact, int* err_flag, int flags, void* stream) {
   if (rows == 0) return SD_OK;
   if (logits == nullptr || err_flag == nullptr || rows < 0 || V <= 0 || ld_in < V) return fail(SD_EINVAL, "sd_norm: bad logits/shape");
   if (!(temperature > 0.f) || std::isinf(temperature)) return fail(SD_EINVAL, "sd_norm: temperature must be finite and > 0");
@@ -51,24 +59,26 @@ static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, i
   p.probs = probs; p.ld_out = ld_out;
   p.u = u; p.tok_out = reinterpret_cast<long long*>(tok_out);
   p.err_flag = err_flag;
+  p.cmp = to_compact(compact);
   p.force_general = (flags & SD_NORM_FORCE_GENERAL) ? 1 : 0;
   p.no_pipeline = (flags & SD_NORM_NO_PIPELINE) ? 1 : 0;
   return done("sd_norm launch", sd::launch_norm(p, dtype, static_cast<int>(rows), static_cast<cudaStream_t>(stream)));
 }
 
 int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
-                  float top_p, float* probs, int64_t ld_out, int* err_flag, int flags, void* stream) {
+                  float top_p, float* probs, int64_t ld_out, const sd_compact_t* compact, int* err_flag, int flags,
+                  void* stream) {
   if (probs == nullptr) return fail(SD_EINVAL, "sd_norm_probs: probs is null");
   return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, nullptr, nullptr,
-                     err_flag, flags, stream);
+                     compact, err_flag, flags, stream);
 }
 
 int sd_norm_sample(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
-                   float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out, int* err_flag,
-                   int flags, void* stream) {
+                   float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                   const sd_compact_t* compact, int* err_flag, int flags, void* stream) {
   if (u == nullptr || tok_out == nullptr) return fail(SD_EINVAL, "sd_norm_sample: u/tok_out is null");
-  return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, err_flag,
-                     flags, stream);
+  return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, compact,
+                     err_flag, flags, stream);
 }
 
 int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const float* u, int64_t* tok_out, int* err_flag,
@@ -87,7 +97,9 @@ int sd_verify(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, 
               int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
               const float* u_acc, int64_t u_acc_stride, const float* u_final, int B, int gamma, int64_t V, int strict,
               int32_t* n_accepted, int64_t* next_tok, float* ratios, int32_t* tie_count, int64_t* tokens,
-              int64_t tokens_stride, int32_t* seq_len, const int32_t* active, int* err_flag, void* stream) {
+              int64_t tokens_stride, int32_t* seq_len, const int32_t* active, const sd_compact_t* p_compact,
+              int64_t p_cmp_req_stride, const sd_compact_t* q_compact, int64_t q_cmp_req_stride, uint64_t* stats,
+              int* err_flag, void* stream) {
   if (B == 0) return SD_OK;
   if (!p_probs || !q_probs || !draft_tok || !u_acc || !u_final || !n_accepted || !next_tok || !err_flag)
     return fail(SD_EINVAL, "sd_verify: null argument");
@@ -102,6 +114,9 @@ int sd_verify(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, 
   p.n_accepted = n_accepted; p.next_tok = reinterpret_cast<long long*>(next_tok); p.ratios = ratios;
   p.tie_count = tie_count; p.err_flag = err_flag;
   p.tokens = reinterpret_cast<long long*>(tokens); p.tokens_stride = tokens_stride; p.seq_len = seq_len; p.active = active;
+  p.stats = reinterpret_cast<unsigned long long*>(stats);
+  p.pc = to_compact(p_compact); p.qc = to_compact(q_compact);
+  p.pc_req_stride = p_cmp_req_stride * p.pc.row_stride; p.qc_req_stride = q_cmp_req_stride * p.qc.row_stride;
   return done("sd_verify launch", sd::launch_verify(p, static_cast<cudaStream_t>(stream)));
 }
 

@@ -393,6 +393,13 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
       if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
       if (in_p) gs.a_val[lane] = pr;
       if (lane == 0) gs.n_keep_p = np;
+      if (p.cmp.cnt != nullptr && crank == 0) {                   // compact form of the row for the sparse verify path
+        const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
+        if (np <= p.cmp.cap) {
+          if (in_p) { p.cmp.idx[cr * p.cmp.cap + lane] = id; p.cmp.val[cr * p.cmp.cap + lane] = pr; }
+          if (lane == 0) p.cmp.cnt[cr] = np;
+        } else if (lane == 0) p.cmp.cnt[cr] = -1;
+      }
       if (p.u != nullptr && crank == 0 && p.u[row] >= 0.f) {
         const int e2 = frexp_exp(__shfl_sync(0xffffffffu, pr, 0));
         const unsigned long long wi = weight_of(pr, e2);
@@ -443,6 +450,13 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
       if (badp) atomicOr(p.err_flag, kErrNanLogit);
       if (lane == 0) gs.n_keep_p = np;
       __syncwarp();
+      if (p.cmp.cnt != nullptr && crank == 0) {
+        const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
+        if (np <= p.cmp.cap) {
+          for (int i = lane; i < np; i += 32) { p.cmp.idx[cr * p.cmp.cap + i] = gs.s_idx[i]; p.cmp.val[cr * p.cmp.cap + i] = gs.a_val[i]; }
+          if (lane == 0) p.cmp.cnt[cr] = np;
+        } else if (lane == 0) p.cmp.cnt[cr] = -1;
+      }
       if (p.u != nullptr && crank == 0 && p.u[row] >= 0.f) {
         const int e = frexp_exp(gs.a_val[0]);
         unsigned long long tot = 0ull;

@@ -296,6 +296,13 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
         if (in_p) sh.a_val[lane] = pr;
         if (lane == 0) sh.n_keep_p = np;
+        if (p.cmp.cnt != nullptr && cx.crank == 0) {              // compact form of the row for the sparse verify path
+          const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
+          if (np <= p.cmp.cap) {
+            if (in_p) { p.cmp.idx[cr * p.cmp.cap + lane] = id; p.cmp.val[cr * p.cmp.cap + lane] = pr; }
+            if (lane == 0) p.cmp.cnt[cr] = np;
+          } else if (lane == 0) p.cmp.cnt[cr] = -1;
+        }
         if (p.u != nullptr && cx.crank == 0 && p.u[row] >= 0.f) {   // inverse-CDF sample in vocabulary order over the kept list
           const int e2 = frexp_exp(__shfl_sync(0xffffffffu, pr, 0));
           const unsigned long long wi = weight_of(pr, e2);
@@ -347,6 +354,13 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         if (badp) atomicOr(p.err_flag, kErrNanLogit);
         if (lane == 0) sh.n_keep_p = np;
         __syncwarp();
+        if (p.cmp.cnt != nullptr && cx.crank == 0) {
+          const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
+          if (np <= p.cmp.cap) {
+            for (int i = lane; i < np; i += 32) { p.cmp.idx[cr * p.cmp.cap + i] = sh.r_idx[i]; p.cmp.val[cr * p.cmp.cap + i] = sh.a_val[i]; }
+            if (lane == 0) p.cmp.cnt[cr] = np;
+          } else if (lane == 0) p.cmp.cnt[cr] = -1;
+        }
         if (p.u != nullptr && cx.crank == 0 && p.u[row] >= 0.f) {
           const int e = frexp_exp(sh.a_val[0]);
           unsigned long long tot = 0ull;
@@ -380,6 +394,9 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
     SD_PROF(7);
     if (!done) __syncthreads();
   }
+
+  if (!done && p.cmp.cnt != nullptr && cx.crank == 0 && tid == 0)
+    p.cmp.cnt[static_cast<long long>(row) * p.cmp.row_stride] = -1;        // dense / general path: no compact list
 
   // ================================================================== dense path (no filter): max / sum / exp
   if (!done && k_eff == 0 && !(p.top_p > 0.f) && !p.force_general) {

@@ -5,12 +5,20 @@
 
 namespace sd {
 
+// Optional compact form of top-k filtered rows: row r of a norm call owns compact row r * row_stride:
+//   cnt[cr] = number of kept entries (or -1: not available, use the dense row), idx/val[cr * cap + j] its entries.
+struct Compact {
+  int* cnt; int* idx; float* val;
+  int cap; long long row_stride;
+};
+
 struct NormParams {
   const void* logits; long long ld_in; long long V;
   float temperature; int top_k; float top_p;
   float* probs; long long ld_out;          // nullable: no dense write (sample only)
   const float* u; long long* tok_out;      // nullable pair: per-row uniform -> sampled token
   int* err_flag;
+  Compact cmp;                             // cmp.cnt == nullptr: disabled
   // filled by the launcher
   int cluster, slice_elems, slice_smem_bytes, use_tma, vec_out;
   int force_general;                       // test knob: skip the fast top-k path
@@ -35,8 +43,11 @@ struct VerifyParams {
   int B, gamma; long long V; int strict;
   int* n_accepted; long long* next_tok; float* ratios;      // outputs (ratios nullable, (B, gamma))
   int* tie_count; int* err_flag;
+  unsigned long long* stats;                                // optional: [0] += accepted tokens, [1] += requests verified
   // optional fused token append / length update ("rollback" of the static caches is this counter write)
   long long* tokens; long long tokens_stride; int* seq_len; const int* active;
+  // optional compact lists of the p and q rows (request b, row i -> compact row b * req_stride + i * row_stride)
+  Compact pc, qc; long long pc_req_stride, qc_req_stride;
   // filled by the launcher
   int cluster, slice_elems, use_tma;
 };

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParam
       const long long out = guard_val < kProbGuard ? argmax : tok;
       p.next_tok[b] = out;
       if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc;
+      if (p.stats != nullptr) { atomicAdd(&p.stats[0], static_cast<unsigned long long>(n_acc)); atomicAdd(&p.stats[1], 1ull); }
       if (p.tokens != nullptr) {                               // append + "rollback": one counter write
         const int L = p.seq_len[b];
         p.tokens[b * p.tokens_stride + L + n_acc] = out;
@@ -163,6 +164,214 @@ __global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParam
   if (C > 1) cx.cluster.sync();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sparse verify: when kernel 1 also emitted the compact (index, probability) lists of its top-k filtered rows, the
+// residual max(0, p_n - q_n) lives on the <= ~2k entries of p_n's support, so one warp per request does the whole
+// verify step from a few hundred bytes instead of two dense vocabulary rows.  Arithmetic (fp32 subtraction, 64-bit
+// fixed-point weights, integer prefix sums in vocabulary order) is the dense kernel's, so tokens are identical.
+// Requests whose lists are unavailable (count -1: the row was served by the dense / general path) fall back, inside
+// this kernel, to a single-CTA dense scan straight from HBM/L2.
+constexpr int kSparseThreads = 128;
+constexpr int kSparseCap = 64;
+
+__device__ __forceinline__ void verify_commit(const VerifyParams& p, int b, int n_acc, long long out) {
+  p.next_tok[b] = out;
+  if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc;
+  if (p.stats != nullptr) { atomicAdd(&p.stats[0], static_cast<unsigned long long>(n_acc)); atomicAdd(&p.stats[1], 1ull); }
+  if (p.tokens != nullptr) {
+    const int L = p.seq_len[b];
+    p.tokens[b * p.tokens_stride + L + n_acc] = out;
+    p.seq_len[b] = L + n_acc + 1;
+  }
+}
+
+__global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const VerifyParams p) {
+  __shared__ RowScratch<kSparseThreads> rs;
+  __shared__ int s_n_acc, s_dense;
+  constexpr int kPre = 9;                                     // rows per tensor prefetched into shared memory
+  __shared__ uint2 p_pre[kPre][kSparseCap], q_pre[kPre][kSparseCap];
+  __shared__ int p_cnt_pre[kPre], q_cnt_pre[kPre];
+  __shared__ int q_idx[kSparseCap];
+  __shared__ float q_val[kSparseCap];
+  __shared__ int e_idx[kSparseCap];
+  __shared__ unsigned long long e_w[kSparseCap];
+  const int b = blockIdx.x;
+  if (p.active != nullptr && p.active[b] == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = static_cast<int>(p.V), gamma = p.gamma;
+  const int n_pre_p = min(gamma + 1, kPre), n_pre_q = min(gamma, kPre);
+
+  if (warp > 0) {
+    // warps 1..3: while warp 0 chases token -> p[token], q[token], pull the (tiny) compact lists of every row that
+    // could become the residual row into shared memory — the dependent chain of global loads shrinks to two
+    for (int i = tid - 32; i < (n_pre_p + n_pre_q) * kSparseCap; i += kSparseThreads - 32) {
+      const int rr = i / kSparseCap, j = i - rr * kSparseCap;
+      if (rr < n_pre_p) {
+        const long long cr = b * p.pc_req_stride + rr * p.pc.row_stride;
+        if (j < p.pc.cap) p_pre[rr][j] = make_uint2(static_cast<uint32_t>(p.pc.idx[cr * p.pc.cap + j]), __float_as_uint(p.pc.val[cr * p.pc.cap + j]));
+        if (j == 0) p_cnt_pre[rr] = p.pc.cnt[cr];
+      } else {
+        const int r2 = rr - n_pre_p;
+        const long long cr = b * p.qc_req_stride + r2 * p.qc.row_stride;
+        if (j < p.qc.cap) q_pre[r2][j] = make_uint2(static_cast<uint32_t>(p.qc.idx[cr * p.qc.cap + j]), __float_as_uint(p.qc.val[cr * p.qc.cap + j]));
+        if (j == 0) q_cnt_pre[r2] = p.qc.cnt[cr];
+      }
+    }
+  }
+  int n_acc_w0 = 0;
+  bool tie_w0 = false;
+  if (warp == 0) {
+    // ---- accept scan (dense gathers of single elements, as in verify_kernel)
+    bool acc = true, tie = false;
+    float ratio = 0.f;
+    if (lane < gamma) {
+      long long tok = p.draft[b * p.draft_stride + lane];
+      if (tok < 0 || tok >= V) { atomicOr(p.err_flag, kErrBadToken); tok = 0; }
+      const float pv = p.p[b * p.p_req_stride + lane * p.p_row_stride + tok];
+      const float qv = p.q[b * p.q_req_stride + lane * p.q_row_stride + tok];
+      if (qv == 0.f) atomicOr(p.err_flag, kErrZeroQ);
+      ratio = __fdiv_rn(pv, qv);
+      const float u = p.u_acc[b * p.u_acc_stride + lane];
+      const float thr = p.strict ? fminf(1.0f, ratio) : ratio;
+      acc = p.strict ? (u < thr) : !(u > thr);
+      tie = (u == thr);
+      if (p.ratios != nullptr) p.ratios[b * gamma + lane] = ratio;
+    }
+    const unsigned rej = __ballot_sync(0xffffffffu, !acc);
+    n_acc_w0 = rej ? (__ffs(rej) - 1) : gamma;
+    tie_w0 = tie && lane < gamma && lane <= n_acc_w0;
+    if (p.tie_count != nullptr && tie_w0) atomicAdd(p.tie_count, 1);
+  }
+  __syncthreads();                                            // lists are in shared memory
+  if (warp == 0) {
+    const int n_acc = n_acc_w0;
+    bool use_q = n_acc < gamma;
+    // ---- compact lists of the two rows that matter
+    const long long pcr = b * p.pc_req_stride + n_acc * p.pc.row_stride;
+    const long long qcr = b * p.qc_req_stride + n_acc * p.qc.row_stride;
+    const bool pre = n_acc < kPre;
+    const int cp = pre ? p_cnt_pre[n_acc] : p.pc.cnt[pcr];
+    const int cq = use_q ? (pre ? q_cnt_pre[n_acc] : p.qc.cnt[qcr]) : 0;
+    const bool sparse_ok = cp >= 0 && cp <= kSparseCap && cp <= p.pc.cap && cq >= 0 && cq <= kSparseCap && cq <= p.qc.cap;
+    if (lane == 0) { s_n_acc = n_acc; s_dense = sparse_ok ? 0 : 1; }
+    if (sparse_ok) {
+      for (int t = lane; t < cq; t += 32) {
+        if (pre) { q_idx[t] = static_cast<int>(q_pre[n_acc][t].x); q_val[t] = __uint_as_float(q_pre[n_acc][t].y); }
+        else { q_idx[t] = p.qc.idx[qcr * p.qc.cap + t]; q_val[t] = p.qc.val[qcr * p.qc.cap + t]; }
+      }
+      int id[2]; float pv[2], r[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        if (j < cp) {
+          id[h] = pre ? static_cast<int>(p_pre[n_acc][j].x) : p.pc.idx[pcr * p.pc.cap + j];
+          pv[h] = pre ? __uint_as_float(p_pre[n_acc][j].y) : p.pc.val[pcr * p.pc.cap + j];
+        } else { id[h] = 0x7fffffff; pv[h] = 0.f; }
+      }
+      __syncwarp();
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float qv = 0.f;
+          if (use_q) for (int t = 0; t < cq; ++t) qv = (q_idx[t] == id[h]) ? q_val[t] : qv;
+          r[h] = use_q ? fmaxf(pv[h] - qv, 0.f) : pv[h];
+          if (r[h] > 0.f) {
+            const unsigned long long pk = (static_cast<unsigned long long>(f2key(r[h])) << 32) | (0xffffffffu - static_cast<uint32_t>(id[h]));
+            best = pk > best ? pk : best;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
+        if (best == 0ull) {
+          if (use_q && !p.strict && attempt == 0) { use_q = false; continue; }     // empty residual: resample from p_n
+          if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.next_tok[b] = 0; if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc; }
+          break;
+        }
+        const float rmax = key2f(static_cast<uint32_t>(best >> 32));
+        const int argmax = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffu));
+        const int e = frexp_exp(rmax);
+        unsigned long long w[2], tot = 0ull;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          w[h] = weight_of(r[h], e);
+          tot += w[h];
+          const int j = lane + 32 * h;
+          if (j < kSparseCap) { e_idx[j] = id[h]; e_w[j] = w[h]; }
+        }
+        tot = warp_sum(tot);
+        __syncwarp();
+        const unsigned long long target = scale_target(tot, u_to_int(p.u_final[b]));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          unsigned long long before = 0ull;
+          for (int t = 0; t < cp; ++t) before += e_idx[t] < id[h] ? e_w[t] : 0ull;
+          if (w[h] > 0ull && target >= before && target < before + w[h]) {
+            float guard_val = r[h];
+            if (use_q) guard_val = __fdiv_rn(r[h], ldexpf(__ull2float_rn(tot), e - kScaleBits) + 1e-6f);
+            verify_commit(p, b, n_acc, guard_val < kProbGuard ? argmax : id[h]);
+          }
+        }
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_dense == 0) return;
+
+  // ---- dense fallback for this request: one CTA scans p_n (and q_n) straight from global memory
+  RowCtx<kSparseThreads> cx(&rs, 1);
+  const int n_acc = s_n_acc;
+  bool use_q = n_acc < gamma;
+  const float* prow = p.p + b * p.p_req_stride + n_acc * p.p_row_stride;
+  const float* qrow = p.q + b * p.q_req_stride + n_acc * p.q_row_stride;
+  const int n_vec = (V + 3) / 4;
+  auto vecw = [&](int v, float (&w)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = v * 4 + j;
+      float a = i < V ? prow[i] : 0.f;
+      if (use_q && i < V) a = fmaxf(a - qrow[i], 0.f);
+      w[j] = a;
+    }
+  };
+  unsigned long long best = 0ull;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    unsigned long long mine = 0ull;
+    bool bad = false;
+    for (int v = tid; v < n_vec; v += kSparseThreads) {
+      float w[4];
+      vecw(v, w);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bad |= !(w[j] >= 0.f) || isinf(w[j]);
+        if (w[j] > 0.f) {
+          const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(v * 4 + j));
+          mine = pk > mine ? pk : mine;
+        }
+      }
+    }
+    if (bad) atomicOr(p.err_flag, kErrEmptyRow);
+    best = cx.allreduce_max(mine);
+    if (best != 0ull || !use_q || p.strict) break;
+    use_q = false;
+  }
+  if (best == 0ull) {
+    if (tid == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.next_tok[b] = 0; if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc; }
+    return;
+  }
+  const float rmax = key2f(static_cast<uint32_t>(best >> 32));
+  const int argmax = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffu));
+  unsigned long long total = 0ull;
+  float psel = 1.f;
+  const int tok = cluster_icdf<4, kSparseThreads>(cx, n_vec, 0, rmax, p.u_final[b], vecw, &total, &psel);
+  if (tok >= 0) {
+    float guard_val = psel;
+    if (use_q) guard_val = __fdiv_rn(psel, ldexpf(__ull2float_rn(total), frexp_exp(rmax) - kScaleBits) + 1e-6f);
+    verify_commit(p, b, n_acc, guard_val < kProbGuard ? argmax : tok);
+  }
+}
+
 static int g_verify_cluster = 0;
 void set_verify_tuning(int cluster) { g_verify_cluster = cluster; }
 
@@ -170,6 +379,10 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
   VerifyParams p = pin;
   constexpr int THREADS = 256;
   if (p.gamma > 32 || (p.q != nullptr && p.gamma < 1)) return cudaErrorInvalidValue;
+  if (p.q != nullptr && p.pc.cnt != nullptr && p.qc.cnt != nullptr) {      // compact lists available: sparse path
+    verify_sparse_kernel<<<static_cast<unsigned>(p.B), kSparseThreads, 0, st>>>(p);
+    return cudaGetLastError();
+  }
   const long long row_bytes = p.V * 4;
   int C = 1;
   while (C < kMaxCluster && (row_bytes + C - 1) / C > 48 * 1024) C <<= 1;

@@ -166,6 +166,10 @@ class SpecDecEngine:
         self.eos = torch.full((1,), -1, dtype=torch.int64, device=dev)
         self._cols = torch.arange(self.S, device=dev, dtype=torch.int32).unsqueeze(0)
         self.err = ops.ErrFlag(dev)
+        # compact (index, prob) lists of the filtered rows: kernel 2 then verifies from a few hundred bytes per request
+        self.use_compact = 0 < self.top_k <= 128
+        self.q_cmp = ops.CompactRows(batch * g, dev) if self.use_compact else None
+        self.p_cmp = ops.CompactRows(batch * (g + 1), dev) if self.use_compact else None
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self.graph_captured = False
@@ -209,14 +213,18 @@ class SpecDecEngine:
             else:
                 logits = self.draft.forward(self.tokens, self.seq_len, i - 1, 1, self.cur_tok)[:, 0]
             ops.norm_sample(logits, self.T, self.top_k, self.top_p, self.u_draft_t[i], probs_out=self.q_probs[:, i],
-                            tok_out=self.cur_tok, err=self.err)
+                            tok_out=self.cur_tok, err=self.err,
+                            compact=self.q_cmp.view(i, g) if self.use_compact else None)
             self.draft_tok[:, i].copy_(self.cur_tok)
         logits = self.target.forward(self.tokens, self.seq_len, -1, g + 1, self.cur_tok)
         ops.norm_probs(logits.reshape(B * (g + 1), V), self.T, self.top_k, self.top_p,
-                       out=self.p_probs.view(B * (g + 1), V), err=self.err)
+                       out=self.p_probs.view(B * (g + 1), V), err=self.err,
+                       compact=self.p_cmp.view() if self.use_compact else None)
         ops.verify(self.p_probs, self.q_probs, self.draft_tok, self.u_rows[:, g + 1:2 * g + 1], self.u_final,
                    strict=self.strict, n_accepted=self.n_acc, next_tok=self.next_tok, ratios=self.ratios,
-                   tie_count=self.ties, tokens=self.tokens, seq_len=self.seq_len, active=self.active, err=self.err)
+                   tie_count=self.ties, tokens=self.tokens, seq_len=self.seq_len, active=self.active, err=self.err,
+                   p_compact=self.p_cmp.view() if self.use_compact else None, p_cmp_req_stride=g + 1,
+                   q_compact=self.q_cmp.view() if self.use_compact else None, q_cmp_req_stride=g)
         # statistics + termination, all on the device
         it = self.it_dev
         self.acc_hist.index_copy_(0, it, torch.where(self.active > 0, self.n_acc, torch.full_like(self.n_acc, -1)).unsqueeze(0))

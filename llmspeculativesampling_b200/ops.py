@@ -66,6 +66,37 @@ def default_flag(device) -> ErrFlag:
 NORM_NO_PIPELINE, NORM_FORCE_GENERAL = 1, 2
 
 
+class CompactRows:
+    """Compact (index, probability) lists of top-k filtered rows: `cnt` (n_rows,), `idx` / `val` (n_rows, cap).
+    `view(first_row, row_stride)` addresses logical row r of a kernel call at compact row first_row + r * row_stride."""
+
+    def __init__(self, n_rows: int, device, cap: int = 64):
+        self.cnt = torch.full((n_rows,), -1, dtype=torch.int32, device=device)
+        self.idx = torch.zeros(n_rows, cap, dtype=torch.int32, device=device)
+        self.val = torch.zeros(n_rows, cap, dtype=torch.float32, device=device)
+        self.cap = cap
+
+    def view(self, first_row: int = 0, row_stride: int = 1) -> "_cabi.Compact":
+        return _cabi.Compact(self.cnt.data_ptr() + 4 * first_row, self.idx.data_ptr() + 4 * first_row * self.cap,
+                             self.val.data_ptr() + 4 * first_row * self.cap, self.cap, row_stride)
+
+    def to_dense(self, V: int) -> torch.Tensor:
+        """(n_rows, V) dense rows rebuilt from the lists (rows with cnt < 0 are NaN) — test helper."""
+        out = torch.zeros(self.cnt.numel(), V, dtype=torch.float32, device=self.cnt.device)
+        for r in range(self.cnt.numel()):
+            c = int(self.cnt[r])
+            if c < 0:
+                out[r] = float("nan")
+            else:
+                out[r, self.idx[r, :c].long()] = self.val[r, :c]
+        return out
+
+
+def _cref(c):
+    import ctypes
+    return None if c is None else ctypes.byref(c)
+
+
 def set_tuning(norm_cluster: int = 0, norm_threads: int = 0, verify_cluster: int = 0) -> None:
     _cabi.load().sd_set_tuning(norm_cluster, norm_threads, verify_cluster)
 
@@ -80,7 +111,7 @@ def _rows2d(logits: torch.Tensor) -> torch.Tensor:
 
 def norm_probs(logits: torch.Tensor, temperature: float, top_k: int, top_p: float,
                out: Optional[torch.Tensor] = None, err: Optional[ErrFlag] = None,
-               general: bool = False, pipeline: bool = True) -> torch.Tensor:
+               general: bool = False, pipeline: bool = True, compact=None) -> torch.Tensor:
     """(rows, V) logits (fp32/bf16/fp16) -> (rows, V) fp32 probabilities.  Kernel 1."""
     _require_cuda(logits, "logits")
     x = _rows2d(logits)
@@ -94,14 +125,15 @@ def norm_probs(logits: torch.Tensor, temperature: float, top_k: int, top_p: floa
     p = float(top_p) if top_p else 0.0
     flags = (NORM_FORCE_GENERAL if general else 0) | (0 if pipeline else NORM_NO_PIPELINE)
     rc = lib.sd_norm_probs(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), k, p,
-                           out.data_ptr(), out.stride(0), err.ptr(), flags, _stream())
+                           out.data_ptr(), out.stride(0), _cref(compact), err.ptr(), flags, _stream())
     _cabi.check(rc, "sd_norm_probs")
     return out
 
 
 def norm_sample(logits: torch.Tensor, temperature: float, top_k: int, top_p: float, u: torch.Tensor,
                 probs_out: Optional[torch.Tensor] = None, tok_out: Optional[torch.Tensor] = None,
-                err: Optional[ErrFlag] = None, general: bool = False, pipeline: bool = True) -> torch.Tensor:
+                err: Optional[ErrFlag] = None, general: bool = False, pipeline: bool = True,
+                compact=None) -> torch.Tensor:
     """Kernel 1b: probabilities (optional, written to probs_out) and one sampled token per row."""
     _require_cuda(logits, "logits")
     x = _rows2d(logits)
@@ -117,7 +149,7 @@ def norm_sample(logits: torch.Tensor, temperature: float, top_k: int, top_p: flo
     rc = _cabi.load().sd_norm_sample(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature),
                                      int(top_k or 0), float(top_p or 0.0), _ptr(probs_out),
                                      probs_out.stride(0) if probs_out is not None else V, u.data_ptr(),
-                                     tok_out.data_ptr(), err.ptr(), flags, _stream())
+                                     tok_out.data_ptr(), _cref(compact), err.ptr(), flags, _stream())
     _cabi.check(rc, "sd_norm_sample")
     return tok_out
 
@@ -155,7 +187,8 @@ def verify(p_probs: torch.Tensor, q_probs: torch.Tensor, draft_tok: torch.Tensor
            next_tok: Optional[torch.Tensor] = None, ratios: Optional[torch.Tensor] = None,
            tie_count: Optional[torch.Tensor] = None, tokens: Optional[torch.Tensor] = None,
            seq_len: Optional[torch.Tensor] = None, active: Optional[torch.Tensor] = None,
-           err: Optional[ErrFlag] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+           err: Optional[ErrFlag] = None, p_compact=None, p_cmp_req_stride: int = 0, q_compact=None,
+           q_cmp_req_stride: int = 0, stats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Kernel 2.  p_probs (B, gamma+1, V), q_probs (B, gamma, V) fp32 (last dim contiguous),
     draft_tok (B, gamma) int64, u_acc (B, gamma), u_final (B,).  Returns (n_accepted, next_tok)."""
     _require_cuda(p_probs, "p_probs")
@@ -176,7 +209,8 @@ def verify(p_probs: torch.Tensor, q_probs: torch.Tensor, draft_tok: torch.Tensor
         p_probs.data_ptr(), p_probs.stride(0), p_probs.stride(1), q_probs.data_ptr(), q_probs.stride(0), q_probs.stride(1),
         draft_tok.data_ptr(), draft_tok.stride(0), u_acc.data_ptr(), u_acc.stride(0), u_final.data_ptr(),
         B, gamma, V, 1 if strict else 0, n_accepted.data_ptr(), next_tok.data_ptr(), _ptr(ratios), _ptr(tie_count),
-        _ptr(tokens), tokens.stride(0) if tokens is not None else 0, _ptr(seq_len), _ptr(active), err.ptr(), _stream())
+        _ptr(tokens), tokens.stride(0) if tokens is not None else 0, _ptr(seq_len), _ptr(active),
+        _cref(p_compact), p_cmp_req_stride, _cref(q_compact), q_cmp_req_stride, _ptr(stats), err.ptr(), _stream())
     _cabi.check(rc, "sd_verify")
     return n_accepted, next_tok
 

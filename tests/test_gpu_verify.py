@@ -152,3 +152,47 @@ def test_kv_append_and_build_step(cuda_lib, dtype):
         v_ref[b, :, start[b]:start[b] + q] = vn[b]
     ops.kv_append(kn, vn, kc, vc, wp)
     assert torch.equal(kc, k_ref) and torch.equal(vc, v_ref)
+
+
+@pytest.mark.parametrize("V,dtype", [(32000, torch.float32), (50272, torch.bfloat16)])
+@pytest.mark.parametrize("pipeline", [True, False])
+def test_compact_lists_and_sparse_verify_equal_dense(cuda_lib, V, dtype, pipeline):
+    """Kernel 1 emits the compact (index, prob) lists next to the dense rows; kernel 2 fed with them (sparse path)
+    must return exactly what the dense path returns, including for requests whose lists are unavailable."""
+    from llmspeculativesampling_b200 import ops
+    B, gamma, T, k, p = 24, 4, 0.8, 20, 0.9
+    R = 2 * gamma + 1
+    g = torch.Generator().manual_seed(V)
+    z = torch.randn(B, gamma + 1, V, generator=g) * 3.0
+    tl = (z + 0.5 * torch.randn(B, gamma + 1, V, generator=g)).to(dtype)
+    dl = (z[:, :gamma] + 0.5 * torch.randn(B, gamma, V, generator=g)).to(dtype)
+    tl[5, 2] = 1.0                                            # all-ties target row: no compact list (-1) -> dense fallback
+    dl[7, 0] = dl[7, 0].round()                               # heavy ties in a draft row
+    logits = torch.cat([dl, tl], 1).contiguous().cuda()
+    u = torch.rand(B, 2 * gamma + 2, generator=g)
+    ur = torch.full((B, R), -1.0); ur[:, :gamma] = u[:, :gamma]
+    probs = torch.empty(B, R, V, device="cuda")
+    tok = torch.zeros(B, R, dtype=torch.int64, device="cuda")
+    cmp_rows = ops.CompactRows(B * R, "cuda")
+    ops.norm_sample(logits.view(B * R, V), T, k, p, ur.view(-1).cuda(), probs_out=probs.view(B * R, V), tok_out=tok.view(-1),
+                    pipeline=pipeline, compact=cmp_rows.view())
+    ops.default_flag("cuda").check()
+    dense_from_lists = cmp_rows.to_dense(V).view(B, R, V)
+    have = ~torch.isnan(dense_from_lists[:, :, 0])
+    assert bool(have.float().mean() > 0.9) and not bool(have[5, gamma + 2])
+    assert torch.equal(dense_from_lists[have], probs[have])
+    u_acc = u[:, gamma + 1:2 * gamma + 1].contiguous().cuda(); u_fin = u[:, 2 * gamma + 1].contiguous().cuda()
+    u_acc[5, :] = 0.0                                         # request 5 accepts up to the tie row ...
+    u_acc[5, 2] = 1.0 - 2 ** -24                              # ... and rejects there: its residual needs the dense fallback
+    a_d, t_d = ops.verify(probs[:, gamma:], probs[:, :gamma], tok[:, :gamma], u_acc, u_fin)
+    ratios = torch.zeros(B, gamma, device="cuda")
+    a_s, t_s = ops.verify(probs[:, gamma:], probs[:, :gamma], tok[:, :gamma], u_acc, u_fin, ratios=ratios,
+                          p_compact=cmp_rows.view(gamma, 1), p_cmp_req_stride=R, q_compact=cmp_rows.view(0, 1), q_cmp_req_stride=R)
+    ops.default_flag("cuda").check()
+    assert torch.equal(a_d, a_s) and torch.equal(t_d, t_s)
+    assert int(a_s[5]) == 2
+    pc, qc = probs.cpu(), None
+    for b in range(0, B, 5):
+        wn, wt, wr, _ = ref_ops.verify_request(pc[b, gamma:], pc[b, :gamma], tok[b, :gamma].cpu(), u_acc[b].cpu().numpy(), float(u_fin[b]))
+        assert (int(a_s[b]), int(t_s[b])) == (wn, wt)
+        assert np.array_equal(ratios[b].cpu().numpy(), wr)
