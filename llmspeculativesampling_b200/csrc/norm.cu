@@ -80,8 +80,8 @@ static cudaError_t launch_typed(NormParams p, int rows, cudaStream_t st) {
   const size_t es = sizeof(T);
   const long long row_bytes = p.V * static_cast<long long>(es);
   int C = 1;
-  while (C < kMaxCluster && (row_bytes + C - 1) / C > 64 * 1024) C <<= 1;
-  while (C < kMaxCluster && static_cast<long long>(rows) * C < 148 && row_bytes / (2 * C) >= 8192) C <<= 1;
+  while (C < kMaxPortableCluster && (row_bytes + C - 1) / C > 64 * 1024) C <<= 1;
+  while (C < kMaxPortableCluster && static_cast<long long>(rows) * C < 148 && row_bytes / (2 * C) >= 8192) C <<= 1;
   if (g_tune_cluster > 0) C = g_tune_cluster;
   // slice: multiple of 128 elements so that every slice start is 16-byte aligned in both dtypes
   long long slice = ((p.V + C - 1) / C + 127) & ~127LL;

@@ -21,17 +21,22 @@
 // Replaces the same reference code as norm.cu: /root/reference/sampling/utils.py:152-210 (+213-233).
 #include "norm_row.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace sd {
 
 constexpr int kPipeGroupWarps = 4;
 constexpr int kPipeGroupThreads = kPipeGroupWarps * 32;
 constexpr int kPipeMaxGroups = 3;
-constexpr int kPipeCap = 256;          // merged candidates per row
+constexpr int kPipeCapSmall = 256;     // merged candidates per row, clusters of <= 8 CTAs
+constexpr int kPipeCapLarge = 512;     // ... clusters of 9..16 CTAs
 constexpr int kPipeFastK = 128;
 constexpr uint32_t kPipeTieUlps = 8;
 constexpr int kPipeWarpCap = 48;       // candidates one warp may collect per work item
 constexpr int kPipeMaxItems = 4096;    // work items one cluster can walk (bit mask of failed items)
 
+template <int CAP>
 struct alignas(16) PipeGroupShared {
   float tm[kPipeGroupThreads];                       // per-warp sorted thread maxima
   uint2 w_pair[kPipeGroupWarps][kPipeWarpCap];       // candidates found by each warp (logit/T bits, index)
@@ -39,18 +44,19 @@ struct alignas(16) PipeGroupShared {
   int n_keep_p;
   float tau;
   uint2 recv_cnt2[2][kMaxCluster];                   // [item parity][cluster rank].x = candidate count (-1: general path)
-  uint2 r_pair[2][kPipeCap];                         // receive regions (logit/T bits, index), double buffered by item parity
-  unsigned long long a_key[kPipeCap];                // merged list as sort keys (value key << 32 | ~index)
-  float a_val[kPipeCap];                             // final probabilities (sorted order)
-  float s_val[kPipeCap]; int s_idx[kPipeCap];        // sorted list
+  uint2 r_pair[2][CAP];                         // receive regions (logit/T bits, index), double buffered by item parity
+  unsigned long long a_key[CAP];                // merged list as sort keys (value key << 32 | ~index)
+  float a_val[CAP];                             // final probabilities (sorted order)
+  float s_val[CAP]; int s_idx[CAP];        // sorted list
 };
 
+template <int G, int CAP>
 struct alignas(16) PipeShared {
-  uint64_t full[kPipeMaxGroups];      // TMA bytes landed                     (memory warp -> group)
-  uint64_t zeroed[kPipeMaxGroups];    // output slice zero-filled             (memory warp -> group)
-  uint64_t empty[kPipeMaxGroups];     // slice buffer may be overwritten      (group -> memory warp)
-  uint64_t xbar[kPipeMaxGroups][2];   // peers' candidates landed             (remote groups -> group), by item parity
-  PipeGroupShared g[kPipeMaxGroups];
+  uint64_t full[G];                   // TMA bytes landed                     (memory warp -> group)
+  uint64_t zeroed[G];                 // output slice zero-filled             (memory warp -> group)
+  uint64_t empty[G];                  // slice buffer may be overwritten      (group -> memory warp)
+  uint64_t xbar[G][2];                // peers' candidates landed             (remote groups -> group), by item parity
+  PipeGroupShared<CAP> g[G];
   uint32_t fail_bits[kPipeMaxItems / 32];   // work items that need the general path (kept LAST: survives norm_row)
 };
 
@@ -91,13 +97,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t phase)
 #define PIPE_PROF(item, slot, cond) do { if (p.prof != nullptr && (cond) && (item) < 32) \
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + (item)) * 16 + (slot)] = clock64(); } while (0)
 
-template <typename T, int G>
+template <typename T, int G, int CAP>
 __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_kernel(const NormParams p) {
   constexpr int PV = Elem<T>::kPerVec;
   constexpr int GT = kPipeGroupThreads;
   constexpr int GW = kPipeGroupWarps;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PipeShared& sh = *reinterpret_cast<PipeShared*>(smem_raw + static_cast<size_t>(G) * p.slice_smem_bytes);
+  PipeShared<G, CAP>& sh = *reinterpret_cast<PipeShared<G, CAP>*>(smem_raw + static_cast<size_t>(G) * p.slice_smem_bytes);
   cg::cluster_group cluster = cg::this_cluster();
   const int C = p.cluster;
   const int crank = C > 1 ? static_cast<int>(cluster.block_rank()) : 0;
@@ -111,6 +117,12 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
   const int k_eff = min(p.top_k, V);
   const bool want_probs = p.probs != nullptr;
   const int n_items = p.rows > cid ? (p.rows - cid + n_clusters - 1) / n_clusters : 0;   // rows cid, cid+n_clusters, ...
+  if (p.prof != nullptr && tid == 0) {
+    unsigned long long gt0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+    p.prof[(static_cast<long long>(blockIdx.x) * 32 + 0) * 16 + 15] = clock64();
+    p.prof[(static_cast<long long>(blockIdx.x) * 32 + 2) * 16 + 15] = static_cast<long long>(gt0);
+  }
 
   if (tid == 0) {
     for (int g = 0; g < G; ++g) {
@@ -131,13 +143,9 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
 
   // =============================================================================== memory warp
   if (warp == G * GW) {
-    for (int it = 0; it < n_items; ++it) {
+    auto issue_load = [&](int it) {
       const int g = it % G;
-      const uint32_t use = static_cast<uint32_t>(it / G);
       const int row = cid + it * n_clusters;
-      PIPE_PROF(it, 0, lane == 0);
-      if (use > 0) mbar_wait(&sh.empty[g], (use - 1) & 1);                  // group g is done with its buffer
-      PIPE_PROF(it, 1, lane == 0);
       if (lane == 0 && n > 0) {
         const T* src = reinterpret_cast<const T*>(p.logits) + static_cast<long long>(row) * p.ld_in + start;
         const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(T);
@@ -148,6 +156,10 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
       } else if (lane == 0) {
         mbar_arrive_local(&sh.full[g]);
       }
+    };
+    auto zero_fill = [&](int it) {
+      const int g = it % G;
+      const int row = cid + it * n_clusters;
       if (want_probs) {                                                     // zeros of this item's output slice
         float* o = p.probs + static_cast<long long>(row) * p.ld_out + start;
         if (p.vec_out) {
@@ -160,19 +172,37 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_local(&sh.zeroed[g]);
+    };
+    // start-up: all G buffers are free.  (Issuing the G loads before the first zero-fill was measured slower: the
+    // three store bursts then collide with the first item's pass 1 instead of hiding behind its load.)
+    const int n_first = min(G, n_items);
+    for (int it = 0; it < n_first; ++it) {
+      PIPE_PROF(it, 0, lane == 0); PIPE_PROF(it, 1, lane == 0);
+      issue_load(it);
+      zero_fill(it);
       PIPE_PROF(it, 2, lane == 0);
-      if (!shook && (it + 1 == n_items || it + 1 >= G)) { cluster.barrier_wait(); shook = true; }
+    }
+    if (!shook) { cluster.barrier_wait(); shook = true; }
+    for (int it = n_first; it < n_items; ++it) {
+      const int g = it % G;
+      const uint32_t use = static_cast<uint32_t>(it / G);
+      PIPE_PROF(it, 0, lane == 0);
+      mbar_wait(&sh.empty[g], (use - 1) & 1);                               // group g is done with its buffer
+      PIPE_PROF(it, 1, lane == 0);
+      issue_load(it);
+      zero_fill(it);
+      PIPE_PROF(it, 2, lane == 0);
     }
   } else {
   // =============================================================================== compute groups
   const int g = warp / GW;                   // group == buffer
   const int gt = tid - g * GT;               // thread index inside the group
   const int gw = warp - g * GW;              // warp index inside the group
-  PipeGroupShared& gs = sh.g[g];
+  PipeGroupShared<CAP>& gs = sh.g[g];
   const T* slice = reinterpret_cast<const T*>(smem_raw + static_cast<size_t>(g) * p.slice_smem_bytes);
   const uint4* s4 = reinterpret_cast<const uint4*>(slice);
   const int bar_id = 1 + g;
-  const int cap = kPipeCap / C;
+  const int cap = CAP / C;
   const int vpt = (n_vec + GT - 1) / GT;
 
   for (int it = g; it < n_items; it += G) {
@@ -252,16 +282,22 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
 #pragma unroll
           for (int j = 0; j < PV; ++j) o[j] = -INFINITY;
           if (inb) Elem<T>::unpack(s4[v], o);
-          const int gi = static_cast<int>(start) + v * PV;
+          float vmax = o[0];
 #pragma unroll
-          for (int j = 0; j < PV; ++j) {
-            const bool hit = inb && o[j] >= tau && gi + j < V;
-            const unsigned cm = __ballot_sync(0xffffffffu, hit);
-            if (cm) {                                          // warp-uniform
-              const int pos = wc + __popc(cm & ((1u << lane) - 1u));
-              if (hit && pos < kPipeWarpCap)
-                gs.w_pair[gw][pos] = make_uint2(__float_as_uint(__fdiv_rn(o[j], temp)), static_cast<uint32_t>(gi + j));
-              wc += __popc(cm);
+          for (int j = 1; j < PV; ++j) vmax = fmaxf(vmax, o[j]);
+          unsigned vm = __ballot_sync(0xffffffffu, vmax >= tau);      // vectors holding at least one candidate (1-2 per hot thread)
+          const int gi = static_cast<int>(start) + v * PV;
+          while (vm) {
+            const int src = __ffs(vm) - 1;
+            vm &= vm - 1;
+#pragma unroll
+            for (int j = 0; j < PV; ++j) {
+              const float val = __shfl_sync(0xffffffffu, o[j], src);
+              const int idx = __shfl_sync(0xffffffffu, gi, src) + j;
+              if (val >= tau && idx < V) {                             // warp-uniform
+                if (lane == 0 && wc < kPipeWarpCap) gs.w_pair[gw][wc] = make_uint2(__float_as_uint(val), static_cast<uint32_t>(idx));
+                ++wc;
+              }
             }
           }
         }
@@ -331,7 +367,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
         const int cnt = offs[r + 1] - offs[r];
         for (int i = gt; i < cnt; i += GT) {
           const uint2 e = gs.r_pair[par][r * cap + i];
-          const float xv = __uint_as_float(e.x) + 0.0f;                     // -0 -> +0: equal values must tie on the index
+          const float xv = __fdiv_rn(__uint_as_float(e.x), temp) + 0.0f;    // logit / T;  -0 -> +0: equal values tie on the index
           gs.a_key[offs[r] + i] = (static_cast<unsigned long long>(f2key(xv)) << 32) | (0xffffffffu - e.y);
         }
       }
@@ -493,6 +529,12 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
   // =============================================================================== drained: general path for failed items
   if (!shook) cluster.barrier_wait();
   __syncthreads();
+  if (p.prof != nullptr && tid == 0) {
+    unsigned long long gt1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+    p.prof[(static_cast<long long>(blockIdx.x) * 32 + 1) * 16 + 15] = clock64();
+    p.prof[(static_cast<long long>(blockIdx.x) * 32 + 3) * 16 + 15] = static_cast<long long>(gt1);
+  }
   bool any = false;
   for (int i = 0; i < (n_items + 31) / 32; ++i) any |= sh.fail_bits[i] != 0u;
   if (any) {                                  // uniform across the cluster (every CTA recorded the same items)
@@ -510,68 +552,121 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
 }
 
 // ------------------------------------------------------------------------------------------------
-template <typename T, int G>
-static cudaError_t launch_pipe_g(NormParams p, int rows, cudaStream_t st) {
-  auto kern = norm_topk_pipe_kernel<T, G>;
+using PipeShared3S = PipeShared<3, kPipeCapSmall>;
+using PipeShared2S = PipeShared<2, kPipeCapSmall>;
+
+// static shared-memory need besides the G slice buffers, and whether the in-kernel fallback (norm_row) fits in front
+// of the failed-item mask
+static bool pipe_fits(int G, int CAP, size_t slice_bytes, size_t* fixed_out) {
+  size_t fixed, mask_off, row_need;
+  if (G >= 3 && CAP == kPipeCapSmall) { fixed = sizeof(PipeShared3S); mask_off = offsetof(PipeShared3S, fail_bits); row_need = sizeof(NormShared<32 + 3 * kPipeGroupThreads>); }
+  else if (G == 2 && CAP == kPipeCapSmall) { fixed = sizeof(PipeShared2S); mask_off = offsetof(PipeShared2S, fail_bits); row_need = sizeof(NormShared<32 + 2 * kPipeGroupThreads>); }
+  else return false;
+  *fixed_out = fixed;
+  if (static_cast<size_t>(G) * slice_bytes + fixed > 227 * 1024) return false;
+  return slice_bytes + row_need <= static_cast<size_t>(G) * slice_bytes + mask_off;
+}
+
+template <typename T, int G, int CAP>
+static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStream_t st, int* query_max_clusters) {
+  auto kern = norm_topk_pipe_kernel<T, G, CAP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const size_t smem = static_cast<size_t>(p.pipe_groups) * p.slice_smem_bytes + sizeof(PipeShared);
-  const int n_sm = 148;
-  int n_clusters = n_sm / p.cluster;
-  if (n_clusters > rows) n_clusters = rows;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(n_clusters) * p.cluster);
-  cfg.blockDim = dim3(32 + p.pipe_groups * kPipeGroupThreads);
-  cfg.dynamicSmemBytes = smem;
+  cfg.blockDim = dim3(32 + G * kPipeGroupThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(G) * p.slice_smem_bytes + sizeof(PipeShared<G, CAP>);
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (query_max_clusters != nullptr) {
+    // a persistent grid must be co-resident: clusters cannot use every SM (GPC boundaries), ask the driver
+    cfg.gridDim = dim3(static_cast<unsigned>(p.cluster) * 148);
+    return cudaOccupancyMaxActiveClusters(query_max_clusters, kern, &cfg);
+  }
+  cfg.gridDim = dim3(static_cast<unsigned>(p.pipe_clusters) * p.cluster);
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 template <typename T>
-static cudaError_t launch_pipe_typed(const NormParams& p, int rows, cudaStream_t st) {
-  return p.pipe_groups >= 3 ? launch_pipe_g<T, 3>(p, rows, st) : launch_pipe_g<T, 2>(p, rows, st);
+static cudaError_t pipe_dispatch(const NormParams& p, int rows, cudaStream_t st, int* q) {
+  if (p.pipe_groups >= 3) return pipe_launch_or_query<T, 3, kPipeCapSmall>(p, rows, st, q);
+  return pipe_launch_or_query<T, 2, kPipeCapSmall>(p, rows, st, q);
 }
 
-// Decides whether the pipelined kernel applies; fills cluster / slice / groups.  Returns false if not applicable.
+static cudaError_t pipe_dispatch_dtype(const NormParams& p, int dtype, int rows, cudaStream_t st, int* q) {
+  switch (dtype) {
+    case kF32: return pipe_dispatch<float>(p, rows, st, q);
+    case kBF16: return pipe_dispatch<__nv_bfloat16>(p, rows, st, q);
+    case kF16: return pipe_dispatch<__half>(p, rows, st, q);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Decides whether the pipelined kernel applies and with which geometry: among the cluster sizes whose slices leave
+// room for >= 2 buffers, take the one that keeps the most SMs busy (clusters of 3..16 CTAs cannot use every SM).
+// The choice is cached per (dtype, V, top_k bucket).  Returns false if the kernel is not applicable.
+struct PipePlan { long long V; int dtype, kcap, cluster, groups, cap, max_clusters; };
+static PipePlan g_plans[32];
+static int g_n_plans = 0;
+
 bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
   const size_t es = dtype == kF32 ? 4 : 2;
-  if (p.top_k <= 0 || p.top_k > kPipeFastK || p.force_general) return false;
+  if (p.top_k <= 0 || p.top_k > kPipeFastK || p.force_general || rows < 2) return false;
   const long long row_bytes = p.V * static_cast<long long>(es);
   const bool aligned_in = (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) && ((p.ld_in * es) % 16 == 0) && (row_bytes % 16 == 0);
   if (!aligned_in) return false;
-  const size_t budget = 227 * 1024 - sizeof(PipeShared);
-  int C = 1;
-  // smallest cluster that leaves room for at least two buffers per CTA
-  while (C < kMaxCluster && ((static_cast<size_t>((p.V + C - 1) / C + 127) & ~127ull) * es + 127) / 128 * 128 * 2 > budget) C <<= 1;
-  if (tune_cluster > 0) C = tune_cluster;
-  long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
-  while (C > 1 && slice * (C - 1) >= p.V) { C >>= 1; slice = ((p.V + C - 1) / C + 127) & ~127LL; }
-  const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
-  int G = static_cast<int>(budget / slice_bytes);
-  if (G > kPipeMaxGroups) G = kPipeMaxGroups;
-  if (G < 2) return false;
-  if (rows < 2) return false;
-  if (p.top_k + 16 > kPipeCap / C) return false;            // per-rank receive region must hold k + slack
-  {
-    // the in-kernel fallback (norm_row) re-uses the front of shared memory; the failed-item mask must survive it
-    const size_t row_need = slice_bytes + (G >= 3 ? sizeof(NormShared<32 + 3 * kPipeGroupThreads>) : sizeof(NormShared<32 + 2 * kPipeGroupThreads>));
-    if (row_need > static_cast<size_t>(G) * slice_bytes + offsetof(PipeShared, fail_bits)) return false;
-    const int n_clusters = 148 / C < rows ? 148 / C : rows;
-    if ((rows + n_clusters - 1) / n_clusters > kPipeMaxItems) return false;
+  const int kcap = p.top_k + 8;                              // per-rank receive region must hold k + slack
+  const PipePlan* plan = nullptr;
+  for (int i = 0; i < g_n_plans; ++i)
+    if (g_plans[i].V == p.V && g_plans[i].dtype == dtype && g_plans[i].kcap == kcap && tune_cluster == 0) plan = &g_plans[i];
+  PipePlan fresh = {p.V, dtype, kcap, 0, 0, 0, 0};
+  if (plan == nullptr) {
+    double best_score = 0.0;
+    for (int C = 1; C <= kMaxPortableCluster; ++C) {
+      if (tune_cluster > 0 && C != tune_cluster) continue;
+      const long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
+      if (C > 1 && slice * (C - 1) >= p.V) continue;         // last rank would be empty
+      if (slice / kPipeGroupThreads > 60000) continue;
+      const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
+      const int CAP = C <= 8 ? kPipeCapSmall : kPipeCapLarge;
+      if (kcap > CAP / C) continue;
+      size_t fixed = 0;
+      int G = 0;
+      if (CAP == kPipeCapSmall && pipe_fits(3, CAP, slice_bytes, &fixed)) G = 3;
+      else if (pipe_fits(2, CAP, slice_bytes, &fixed)) G = 2;
+      if (G == 0) continue;
+      NormParams q = p;
+      q.cluster = C; q.slice_elems = static_cast<int>(slice); q.slice_smem_bytes = static_cast<int>(slice_bytes);
+      q.pipe_groups = G; q.pipe_cap = CAP;
+      int n = 0;
+      if (pipe_dispatch_dtype(q, dtype, rows, nullptr, &n) != cudaSuccess || n < 1) { (void)cudaGetLastError(); continue; }
+      // busy SMs, mildly preferring three buffers (better latency hiding) and small clusters (less exchange)
+      const double score = static_cast<double>(n) * C * (G == 3 ? 1.0 : 0.93) * (1.0 - 0.01 * C);
+      if (getenv("SD_DEBUG") != nullptr)
+        fprintf(stderr, "[specdec] pipe plan V=%lld es=%zu C=%d G=%d CAP=%d slice=%zuB: %d clusters, score %.1f\n", p.V, es, C, G, CAP, slice_bytes, n, score);
+      if (score > best_score) { best_score = score; fresh.cluster = C; fresh.groups = G; fresh.cap = CAP; fresh.max_clusters = n; }
+      if (tune_cluster == 0 && n * C >= 148 && G == 3) break;          // cannot do better than all SMs with three buffers
+    }
+    if (tune_cluster == 0 && g_n_plans < 32) { g_plans[g_n_plans] = fresh; plan = &g_plans[g_n_plans++]; }
+    else plan = &fresh;
   }
-  if (slice / kPipeGroupThreads > 65535) return false;
+  if (plan->cluster == 0) return false;
+  const int C = plan->cluster;
+  const long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
+  const int n_clusters = plan->max_clusters < rows ? plan->max_clusters : rows;
+  if ((rows + n_clusters - 1) / n_clusters > kPipeMaxItems) return false;
   p.cluster = C;
   p.slice_elems = static_cast<int>(slice);
-  p.slice_smem_bytes = static_cast<int>(slice_bytes);
-  p.pipe_groups = G;
+  p.slice_smem_bytes = static_cast<int>((static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127));
+  p.pipe_groups = plan->groups;
+  p.pipe_cap = plan->cap;
+  p.pipe_clusters = n_clusters;
   p.use_tma = 1;
   p.vec_out = (p.probs != nullptr && reinterpret_cast<uintptr_t>(p.probs) % 16 == 0 && p.ld_out % 4 == 0) ? 1 : 0;
   p.rows = rows;
@@ -579,12 +674,7 @@ bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
 }
 
 cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStream_t st) {
-  switch (dtype) {
-    case kF32: return launch_pipe_typed<float>(p, rows, st);
-    case kBF16: return launch_pipe_typed<__nv_bfloat16>(p, rows, st);
-    case kF16: return launch_pipe_typed<__half>(p, rows, st);
-    default: return cudaErrorInvalidValue;
-  }
+  return pipe_dispatch_dtype(p, dtype, rows, st, nullptr);
 }
 
 }  // namespace sd

@@ -10,7 +10,8 @@
 
 namespace sd {
 
-constexpr int kMaxCluster = 8;
+constexpr int kMaxPortableCluster = 8;
+constexpr int kMaxCluster = 16;    // 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed (pipelined kernel only)
 
 // Scratch every CTA of a cluster keeps at the same shared-memory offset, so that peers can read it
 // through distributed shared memory (cluster.map_shared_rank).

@@ -385,8 +385,8 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
   }
   const long long row_bytes = p.V * 4;
   int C = 1;
-  while (C < kMaxCluster && (row_bytes + C - 1) / C > 48 * 1024) C <<= 1;
-  while (C < kMaxCluster && static_cast<long long>(p.B) * C < 148 && row_bytes / (2 * C) >= 4096) C <<= 1;
+  while (C < kMaxPortableCluster && (row_bytes + C - 1) / C > 48 * 1024) C <<= 1;
+  while (C < kMaxPortableCluster && static_cast<long long>(p.B) * C < 148 && row_bytes / (2 * C) >= 4096) C <<= 1;
   if (g_verify_cluster > 0) C = g_verify_cluster;
   long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
   while (C > 1 && slice * (C - 1) >= p.V) { C >>= 1; slice = ((p.V + C - 1) / C + 127) & ~127LL; }

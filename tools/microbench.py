@@ -87,6 +87,11 @@ def main():
                 t = b[: (b.shape[0] // 32) * 32].view(-1, 32, 16)
                 t = t[t[:, 0, 0] != 0]
                 print("persistent CTAs", t.shape[0])
+                ent, ext, g0, g1 = t[:, 0, 15], t[:, 1, 15], t[:, 2, 15], t[:, 3, 15]
+                print(f"  kernel entry -> first item start: {(t[:, 0, 0] - ent).double().mean() / 1000:.2f} kcyc; "
+                      f"CTA lifetime (clock64): {(ext - ent).double().mean() / 1000:.2f} kcyc; "
+                      f"globaltimer: first entry -> last exit {(g1.max() - g0.min()).item() / 1000:.2f} us, "
+                      f"entry spread {(g0.max() - g0.min()).item() / 1000:.2f} us, exit spread {(g1.max() - g1.min()).item() / 1000:.2f} us")
                 t0 = t[:, 0, 0].clone()
                 names = ["mem: item start", "mem: buffer free", "mem: load issued + zero-filled", "grp: wait for data", "grp: data landed",
                          "grp: pass1 done", "grp: pivot done", "grp: rescan done", "grp: buffer released", "grp: peers landed",
