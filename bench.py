@@ -344,7 +344,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "norm_traffic.json"))).get("dram_bytes_per_launch_pair")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "norm_traffic.json"))).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     secs = ms * 1e-3
@@ -382,7 +382,7 @@ def main():
             a2, _, dt2 = time_oracle(1, 1, per, cores)
             if a2 / dt2 > best_rate:
                 best_threads, best_rate = cores, a2 / dt2
-        n_steps = 12
+        n_steps = 60 if best_threads > 1 else 24          # ~10 s of CPU work
         acc_c, _, dt_c = time_oracle(n_steps, 0, per, best_threads)
         line["cpu_baseline"] = {"value": acc_c / dt_c, "unit": "tokens/s", "cores": best_threads, "kind": "port",
                                 "sample": f"{n_steps} steps x {per} requests of the same workload ({n_steps * per * (2 * GAMMA + 1)} rows "
