@@ -89,6 +89,39 @@ template <> struct Elem<__half> {
   __device__ static __forceinline__ __half neg_inf() { return __float2half(-INFINITY); }
 };
 
+// NaN-propagating maximum of (m, all elements of one 16-byte vector).  16-bit types are reduced with packed
+// two-lane instructions before a single conversion to fp32 (the conversion is monotone, so the result is exact).
+template <typename T> __device__ __forceinline__ float vec_max_nan(float m, const uint4& v);
+template <> __device__ __forceinline__ float vec_max_nan<float>(float m, const uint4& v) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)));
+  asm("max.NaN.f32 %0, %0, %1;" : "+f"(d) : "f"(__uint_as_float(v.z)));
+  asm("max.NaN.f32 %0, %0, %1;" : "+f"(d) : "f"(__uint_as_float(v.w)));
+  asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(d));
+  return m;
+}
+template <> __device__ __forceinline__ float vec_max_nan<__nv_bfloat16>(float m, const uint4& v) {
+  uint32_t a, b;
+  asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(a) : "r"(v.x), "r"(v.y));
+  asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(b) : "r"(v.z), "r"(v.w));
+  asm("max.NaN.bf16x2 %0, %0, %1;" : "+r"(a) : "r"(b));
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(__uint_as_float(a << 16)), "f"(__uint_as_float(a & 0xffff0000u)));
+  asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(d));
+  return m;
+}
+template <> __device__ __forceinline__ float vec_max_nan<__half>(float m, const uint4& v) {
+  uint32_t a, b;
+  asm("max.NaN.f16x2 %0, %1, %2;" : "=r"(a) : "r"(v.x), "r"(v.y));
+  asm("max.NaN.f16x2 %0, %1, %2;" : "=r"(b) : "r"(v.z), "r"(v.w));
+  asm("max.NaN.f16x2 %0, %0, %1;" : "+r"(a) : "r"(b));
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&a));
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(f.x), "f"(f.y));
+  asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(d));
+  return m;
+}
+
 // ----------------------------------------------------------------------------------------------
 // warp / block reductions
 __device__ __forceinline__ float warp_max(float v) {

@@ -221,14 +221,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     for (int i = 0; i < vpt; ++i) {
       const int v = i * GT + ((gt + i) & (GT - 1));
       if (v >= n_vec) continue;
-      float o[PV];
-      Elem<T>::unpack(s4[v], o);
-#pragma unroll
-      for (int j = 0; j < PV; ++j) {
-        float d;
-        asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(tmax), "f"(o[j]));
-        tmax = d;
-      }
+      tmax = vec_max_nan<T>(tmax, s4[v]);
     }
     if (tmax != tmax || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
 
@@ -278,14 +271,12 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
         for (int i0 = 0; i0 < vpt; i0 += 32) {
           const int v = (i0 + lane) * GT + ((t + i0 + lane) & (GT - 1));
           const bool inb = i0 + lane < vpt && v < n_vec;
-          float o[PV];
-#pragma unroll
-          for (int j = 0; j < PV; ++j) o[j] = -INFINITY;
-          if (inb) Elem<T>::unpack(s4[v], o);
-          float vmax = o[0];
-#pragma unroll
-          for (int j = 1; j < PV; ++j) vmax = fmaxf(vmax, o[j]);
+          uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+          if (inb) raw = s4[v];
+          const float vmax = inb ? vec_max_nan<T>(-INFINITY, raw) : -INFINITY;
           unsigned vm = __ballot_sync(0xffffffffu, vmax >= tau);      // vectors holding at least one candidate (1-2 per hot thread)
+          float o[PV];
+          if (vm) Elem<T>::unpack(raw, o);                            // warp-uniform, rare
           const int gi = static_cast<int>(start) + v * PV;
           while (vm) {
             const int src = __ffs(vm) - 1;

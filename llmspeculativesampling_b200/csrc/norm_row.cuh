@@ -129,12 +129,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
       if (v1 <= v0) break;
       if (p.use_tma) mbar_wait(&sh.bar[c], 0);
       if (c == 0) SD_PROF(2);
-      for (int v = v0 + tid; v < v1; v += THREADS) {
-        float o[PV];
-        Elem<T>::unpack(s4[v], o);
-#pragma unroll
-        for (int j = 0; j < PV; ++j) tmax = max_nan(tmax, o[j]);
-      }
+      for (int v = v0 + tid; v < v1; v += THREADS) tmax = vec_max_nan<T>(tmax, s4[v]);
     }
   }
   if (tmax != tmax || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
