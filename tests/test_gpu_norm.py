@@ -178,3 +178,39 @@ def test_pipeline_kernel_many_rows_with_sampling(cuda_lib, V, dtype, rows):
     sel = [0, 3, rows // 2, rows - 1]
     want = oracle_probs(x[sel].cpu(), 0.8, 20, 0.9)
     assert compare_probs(pa[sel], want, "pipeline vs oracle") == 0
+
+
+def test_fuzz_shapes_parameters_and_ties_against_oracle(cuda_lib):
+    """Randomised sweep (fixed seed) over V, rows, dtype, T, top_k, top_p, tie density, -inf masks and row strides, on
+    every kernel path; probabilities must match the oracle and the support must be identical."""
+    from llmspeculativesampling_b200 import ops
+    rng = np.random.default_rng(1234)
+    n_cases, boundary_rows, total_rows = 60, 0, 0
+    for case in range(n_cases):
+        V = int(rng.choice([17, 64, 257, 1000, 1024, 4099, 8192, 12345, 32000]))
+        rows = int(rng.integers(1, 7))
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.integers(0, 3))]
+        T = float(rng.choice([1.0, 0.7, 0.8, 1.3, 2.0]))
+        k = int(rng.choice([0, 1, 2, 5, 20, 50, 128, 129, 400]))
+        p = float(rng.choice([0.0, 0.3, 0.9, 0.95, 1.0]))
+        scale = float(rng.choice([0.3, 1.0, 3.8, 8.0]))
+        g = torch.Generator().manual_seed(case)
+        x = torch.randn(rows, V, generator=g) * scale
+        mode = int(rng.integers(0, 4))
+        if mode == 1:
+            x = (x * 2).round() / 2                               # dense ties
+        elif mode == 2:
+            x[:, rng.integers(0, V, size=max(1, V // 3))] = float("-inf")
+        x = x.to(dtype)
+        pad = int(rng.choice([0, 0, 8, 24]))
+        big = torch.zeros(rows, V + pad, dtype=dtype)
+        big[:, :V] = x
+        xd = big.cuda()[:, :V]                                    # row stride V + pad
+        want = oracle_probs(x, T, k, p)
+        for path in ("pipeline", "classic", "general"):
+            got = ops.norm_probs(xd, T, k, p, general=(path == "general"), pipeline=(path == "pipeline"))
+            ops.default_flag("cuda").check()
+            boundary_rows += compare_probs(got, want, f"case {case} V={V} rows={rows} {dtype} T={T} k={k} p={p} mode={mode} path={path}")
+            total_rows += rows
+    # a different support is only legitimate when the top-p cumulative sum lands within fp32 rounding of top_p
+    assert boundary_rows <= max(2, total_rows // 100), f"{boundary_rows} boundary rows out of {total_rows}"
