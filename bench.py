@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("SD_PDL", "1")), help="programmatic dependent launch on/off")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -184,6 +185,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     build.build()
+    ops.set_pdl(bool(args.pdl))
 
     B, g = BATCH, GAMMA
     R = 2 * g + 1                                           # rows per request: gamma draft + gamma+1 target

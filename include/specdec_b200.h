@@ -68,6 +68,12 @@ const char* sd_last_error(void);
  * 0 = heuristic) of the norm kernel, cluster size of the verify kernel. */
 void sd_set_tuning(int norm_cluster, int norm_threads, int verify_cluster);
 
+/* Programmatic dependent launch (on by default): when enabled, the pipelined norm kernel and the sparse verify
+ * kernel are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so their CTA scheduling and
+ * shared-memory / mbarrier set-up overlap the tail of the previous kernel in the stream; both execute
+ * griddepcontrol.wait before their first global-memory access, so results are unchanged. */
+void sd_set_pdl(int enable);
+
 /* Debug: when non-NULL, every CTA of the norm kernel writes clock64() phase timestamps into
  * device_buf[cta * 16 + slot] (tools/microbench.py --prof).  NULL switches it off. */
 void sd_debug_set_prof(int64_t* device_buf);

@@ -19,6 +19,7 @@ SIGNATURES = {
     "sd_last_error": (C.c_char_p, []),
     "sd_set_tuning": (None, [i32, i32, i32]),
     "sd_debug_set_prof": (None, [vp]),
+    "sd_set_pdl": (None, [i32]),
     "sd_norm_probs": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, i32, vp]),
     "sd_norm_sample": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp, i32, vp]),
     "sd_sample": (i32, [vp, i64, i64, i64, vp, vp, vp, vp]),

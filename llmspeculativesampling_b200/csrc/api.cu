@@ -28,6 +28,8 @@ extern "C" {
 int sd_version(void) { return SD_VERSION; }
 const char* sd_last_error(void) { return g_err; }
 
+void sd_set_pdl(int enable) { sd::set_pdl(enable); }
+
 void sd_set_tuning(int norm_cluster, int norm_threads, int verify_cluster) {
   sd::set_norm_tuning(norm_cluster, norm_threads);
   sd::set_verify_tuning(verify_cluster);

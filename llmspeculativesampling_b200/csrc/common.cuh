@@ -251,6 +251,13 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// (CTA scheduling, shared-memory carve-up, barrier initialisation) before its predecessor in the stream has finished;
+// it must execute pdl_wait() before its first global-memory access.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // fixed-point sampling weights (oracle/ref_ops.py: sampling_weights / icdf_sample)
 //   w = floor(p * 2^(40 - e)),  e = frexp exponent of the row maximum
 __device__ __forceinline__ int frexp_exp(float mx) {

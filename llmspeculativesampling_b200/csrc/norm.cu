@@ -44,6 +44,9 @@ __global__ void __launch_bounds__(THREADS, MINB) norm_probs_kernel(const NormPar
 // host side
 static int g_tune_cluster = 0, g_tune_threads = 0;
 static long long* g_prof = nullptr;
+static int g_pdl = 1;
+void set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
+int pdl_enabled() { return g_pdl; }
 
 void set_norm_prof(long long* ptr) { g_prof = ptr; }
 

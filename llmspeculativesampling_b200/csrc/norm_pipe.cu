@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
   }
   for (int i = tid; i < kPipeMaxItems / 32; i += blockDim.x) sh.fail_bits[i] = 0u;
   __syncthreads();
+  pdl_wait();                                          // everything above overlapped the previous kernel's tail
   // "my mbarriers are initialised": peers may only push candidates to me (st.async) after they waited on this; the
   // wait is deferred to the first push so that the loads start immediately
   if (C > 1) cluster.barrier_arrive();
@@ -518,6 +519,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
   }  // compute groups
 
   // =============================================================================== drained: general path for failed items
+  pdl_launch_dependents();                             // the next kernel may start occupying freed SMs
   if (!shook) cluster.barrier_wait();
   __syncthreads();
   if (p.prof != nullptr && tid == 0) {
@@ -571,10 +573,12 @@ static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStrea
   cfg.blockDim = dim3(32 + G * kPipeGroupThreads);
   cfg.dynamicSmemBytes = static_cast<size_t>(G) * p.slice_smem_bytes + sizeof(PipeShared<G, CAP>);
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (pdl_enabled() && query_max_clusters == nullptr) ? 2 : 1;
   if (query_max_clusters != nullptr) {
     // a persistent grid must be co-resident: clusters cannot use every SM (GPC boundaries), ask the driver
     cfg.gridDim = dim3(static_cast<unsigned>(p.cluster) * 148);

@@ -32,6 +32,8 @@ struct NormParams {
 cudaError_t launch_norm(const NormParams& p, int dtype, int rows, cudaStream_t st);
 void set_norm_tuning(int cluster, int threads);
 void set_norm_prof(long long* ptr);
+void set_pdl(int enable);
+int pdl_enabled();
 bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster);
 cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStream_t st);
 

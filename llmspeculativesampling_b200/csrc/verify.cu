@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
   __shared__ int e_idx[kSparseCap];
   __shared__ unsigned long long e_w[kSparseCap];
   const int b = blockIdx.x;
+  pdl_wait();
   if (p.active != nullptr && p.active[b] == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = static_cast<int>(p.V), gamma = p.gamma;
@@ -380,8 +381,15 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
   constexpr int THREADS = 256;
   if (p.gamma > 32 || (p.q != nullptr && p.gamma < 1)) return cudaErrorInvalidValue;
   if (p.q != nullptr && p.pc.cnt != nullptr && p.qc.cnt != nullptr) {      // compact lists available: sparse path
-    verify_sparse_kernel<<<static_cast<unsigned>(p.B), kSparseThreads, 0, st>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t scfg = {};
+    scfg.gridDim = dim3(static_cast<unsigned>(p.B));
+    scfg.blockDim = dim3(kSparseThreads);
+    scfg.stream = st;
+    cudaLaunchAttribute sat[1];
+    sat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    sat[0].val.programmaticStreamSerializationAllowed = 1;
+    scfg.attrs = sat; scfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&scfg, verify_sparse_kernel, p);
   }
   const long long row_bytes = p.V * 4;
   int C = 1;

@@ -101,6 +101,11 @@ def set_tuning(norm_cluster: int = 0, norm_threads: int = 0, verify_cluster: int
     _cabi.load().sd_set_tuning(norm_cluster, norm_threads, verify_cluster)
 
 
+def set_pdl(enable: bool) -> None:
+    """Programmatic dependent launch for the pipelined norm kernel and the sparse verify kernel (see the header)."""
+    _cabi.load().sd_set_pdl(1 if enable else 0)
+
+
 def _rows2d(logits: torch.Tensor) -> torch.Tensor:
     if logits.dim() != 2:
         raise AssertionError("logits must be 2-D (rows, vocab)")      # reference utils.py:194
