@@ -337,32 +337,24 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     named_bar(bar_id, GT);
 
     PIPE_PROF(it, 9, gt == 0);
-    // ---- merge (identical in every CTA of the cluster)
+    // ---- merge (identical in every CTA of the cluster): concatenate the C receive regions as 64-bit sort keys
     int n_tot = 0;
     bool ok = true;
-    int offs[kMaxCluster + 1];
-#pragma unroll
-    for (int r = 0; r < kMaxCluster; ++r) {
-      offs[r] = n_tot;
-      if (r < C) { const int c = static_cast<int>(gs.recv_cnt2[par][r].x); ok &= c >= 0; n_tot += max(c, 0); }
+    for (int r = 0; r < C; ++r) {
+      const int c = static_cast<int>(gs.recv_cnt2[par][r].x);
+      ok &= c >= 0;
+      for (int i = gt; i < c; i += GT) {
+        const uint2 e = gs.r_pair[par][r * cap + i];
+        const float xv = __fdiv_rn(__uint_as_float(e.x), temp) + 0.0f;    // logit / T;  -0 -> +0: equal values tie on the index
+        gs.a_key[n_tot + i] = (static_cast<unsigned long long>(f2key(xv)) << 32) | (0xffffffffu - e.y);
+      }
+      n_tot += max(c, 0);
     }
-    offs[kMaxCluster] = n_tot;
     ok &= n_tot >= k_eff;
-    if (!ok) {
+    if (!ok) {                               // (keys written above are simply discarded)
       if (gt == 0) atomicOr(&sh.fail_bits[it >> 5], 1u << (it & 31));   // same decision in every CTA of the cluster
       named_bar(bar_id, GT);
       continue;
-    }
-#pragma unroll
-    for (int r = 0; r < kMaxCluster; ++r) {
-      if (r < C) {
-        const int cnt = offs[r + 1] - offs[r];
-        for (int i = gt; i < cnt; i += GT) {
-          const uint2 e = gs.r_pair[par][r * cap + i];
-          const float xv = __fdiv_rn(__uint_as_float(e.x), temp) + 0.0f;    // logit / T;  -0 -> +0: equal values tie on the index
-          gs.a_key[offs[r] + i] = (static_cast<unsigned long long>(f2key(xv)) << 32) | (0xffffffffu - e.y);
-        }
-      }
     }
     named_bar(bar_id, GT);
     PIPE_PROF(it, 12, gt == 0);
