@@ -158,6 +158,49 @@ def run_reference(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------- config 1 (side report)
+def run_config1(args):
+    """BASELINE.json configs[0]: llama-68m-shape draft + target (random init), gamma=4, batch=1, 128 new tokens, fp32.
+    The reference's own CPU-runnable case: the oracle port of its KV-cached loop is timed on the host cores and the
+    drop-in speculative_sampling on cuda:0, same weights, same prompt, same uniform tape.  Reported for T=1 with
+    (top_k=20, top_p=0.9) and (0, 0), and for identical / independent weights (acceptance 1.0 / ~0)."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from llmspeculativesampling_b200 import build, uniform_tape
+    from llmspeculativesampling_b200.sampling import speculative_sampling
+    from oracle import spec_loop
+    build.build()
+    cfg = LlamaConfig(vocab_size=32000, hidden_size=768, intermediate_size=3072, num_hidden_layers=2,
+                      num_attention_heads=12, num_key_value_heads=12, max_position_embeddings=2048)
+    prompt = torch.randint(3, 32000, (1, 16), generator=torch.Generator().manual_seed(7))
+    out = []
+    for pair in ("identical", "independent"):
+        torch.manual_seed(0); draft = LlamaForCausalLM(cfg).eval()
+        torch.manual_seed(0 if pair == "identical" else 1); target = LlamaForCausalLM(cfg).eval()
+        for (k, p) in ((20, 0.9), (0, 0.0)):
+            tape = uniform_tape.batch_tape(3, [0], 129, GAMMA)
+            torch.set_num_threads(1)
+            t0 = time.perf_counter()
+            ref_tok, ref_d = spec_loop.speculative_sampling(prompt, draft, target, 128, GAMMA, 1.0, k, p, tape=tape[:, 0])
+            cpu_s = time.perf_counter() - t0
+            dg, tg = draft.cuda(), target.cuda()
+            speculative_sampling(prompt.cuda(), dg, tg, None, None, 128, GAMMA, 1.0, k, p, uniforms=tape)   # warm-up + graph
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            tok, d = speculative_sampling(prompt.cuda(), dg, tg, None, None, 128, GAMMA, 1.0, k, p, uniforms=tape, details=True)
+            torch.cuda.synchronize(); gpu_s = time.perf_counter() - t0
+            n_ref, n_gpu = ref_tok.shape[1] - 16, tok.shape[1] - 16
+            same = min(n_ref, n_gpu)
+            agree = int((ref_tok[0, 16:16 + same] == tok[0, 16:16 + same].cpu()).long().cumprod(0).sum())
+            out.append({"weights": pair, "top_k": k, "top_p": p,
+                        "cpu_oracle": {"seconds": cpu_s, "emitted_tokens_per_s": n_ref / cpu_s, "accepted_tokens_per_s": sum(ref_d["acc_len"]) / cpu_s,
+                                       "iterations": ref_d["iterations"], "mean_accepted": sum(ref_d["acc_len"]) / max(1, len(ref_d["acc_len"])), "threads": 1},
+                        "b200": {"seconds": gpu_s, "emitted_tokens_per_s": n_gpu / gpu_s, "accepted_tokens_per_s": sum(d["acc_len"]) / gpu_s,
+                                 "iterations": d["iterations"], "mean_accepted": sum(d["acc_len"]) / max(1, len(d["acc_len"])), "cuda_graph": d["cuda_graph"]},
+                        "leading_tokens_identical_to_cpu_run": agree, "of": same})
+            draft.cpu(); target.cpu()
+    print(json.dumps({"workload": "config 1: llama-68m-shape draft + target, gamma=4, batch=1, 128 new tokens, fp32", "results": out}))
+    return 0
+
+
 # ------------------------------------------------------------------------------------------- B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -166,11 +209,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config1"],
+                    help="config2 = headline synthetic verify microbench; config1 = side report on the reference's CPU-runnable case")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("SD_PDL", "1")), help="programmatic dependent launch on/off")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "config1":
+        return run_config1(args)
 
     import torch.distributed as dist
     from llmspeculativesampling_b200 import build, ops
