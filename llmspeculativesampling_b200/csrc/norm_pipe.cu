@@ -29,8 +29,6 @@ namespace sd {
 constexpr int kPipeGroupWarps = 4;
 constexpr int kPipeGroupThreads = kPipeGroupWarps * 32;
 constexpr int kPipeMaxGroups = 3;
-constexpr int kPipeCapSmall = 256;     // merged candidates per row, clusters of <= 8 CTAs
-constexpr int kPipeCapLarge = 512;     // ... clusters of 9..16 CTAs
 constexpr int kPipeFastK = 128;
 constexpr uint32_t kPipeTieUlps = 8;
 constexpr int kPipeWarpCap = 48;       // candidates one warp may collect per work item
@@ -50,13 +48,17 @@ struct alignas(16) PipeGroupShared {
   float s_val[CAP]; int s_idx[CAP];        // sorted list
 };
 
-template <int G, int CAP>
+template <int NG, int NB, int CAP>
 struct alignas(16) PipeShared {
-  uint64_t full[G];                   // TMA bytes landed                     (memory warp -> group)
-  uint64_t zeroed[G];                 // output slice zero-filled             (memory warp -> group)
-  uint64_t empty[G];                  // slice buffer may be overwritten      (group -> memory warp)
-  uint64_t xbar[G][2];                // peers' candidates landed             (remote groups -> group), by item parity
-  PipeGroupShared<CAP> g[G];
+  // per slice buffer:
+  uint64_t empty[NB];                 // buffer may be overwritten            (group that re-scanned it -> memory warp)
+  // per compute group (ONE waiter per barrier, so a waiter is never more than one phase behind: with NG > NB the
+  // consumers of one buffer alternate between groups and a per-buffer "full" barrier would alias phases):
+  uint64_t full[NG];                  // TMA bytes of the group's next item landed   (memory warp -> group)
+  uint64_t zeroed[NG];                // that item's output slice is zero-filled     (memory warp -> group)
+  uint64_t taken[NG];                 // group has observed full + zeroed            (group -> memory warp)
+  uint64_t xbar[NG][2];               // peers' candidates landed             (remote groups -> group), by item parity
+  PipeGroupShared<CAP> g[NG];
   uint32_t fail_bits[kPipeMaxItems / 32];   // work items that need the general path (kept LAST: survives norm_row)
 };
 
@@ -97,13 +99,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t phase)
 #define PIPE_PROF(item, slot, cond) do { if (p.prof != nullptr && (cond) && (item) < 32) \
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + (item)) * 16 + (slot)] = clock64(); } while (0)
 
-template <typename T, int G, int CAP>
-__global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_kernel(const NormParams p) {
+// NG compute groups share NB slice buffers: work item i uses buffer i % NB and is processed by group i % NG.  A buffer
+// is only held from the TMA issue to the end of the re-scan (~40 % of an item's latency), so NG > NB groups keep the
+// buffers — i.e. the HBM pipe — busier than one group per buffer would.
+template <typename T, int NG, int NB, int CAP>
+__global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe_kernel(const NormParams p) {
   constexpr int PV = Elem<T>::kPerVec;
   constexpr int GT = kPipeGroupThreads;
   constexpr int GW = kPipeGroupWarps;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PipeShared<G, CAP>& sh = *reinterpret_cast<PipeShared<G, CAP>*>(smem_raw + static_cast<size_t>(G) * p.slice_smem_bytes);
+  PipeShared<NG, NB, CAP>& sh = *reinterpret_cast<PipeShared<NG, NB, CAP>*>(smem_raw + static_cast<size_t>(NB) * p.slice_smem_bytes);
   cg::cluster_group cluster = cg::this_cluster();
   const int C = p.cluster;
   const int crank = C > 1 ? static_cast<int>(cluster.block_rank()) : 0;
@@ -125,10 +130,11 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
   }
 
   if (tid == 0) {
-    for (int g = 0; g < G; ++g) {
+    for (int b = 0; b < NB; ++b) mbar_init(&sh.empty[b], GW);
+    for (int g = 0; g < NG; ++g) {
       mbar_init(&sh.full[g], 1);
       mbar_init(&sh.zeroed[g], 1);
-      mbar_init(&sh.empty[g], GW);
+      mbar_init(&sh.taken[g], 1);
       mbar_init(&sh.xbar[g][0], 1);
       mbar_init(&sh.xbar[g][1], 1);
     }
@@ -143,15 +149,16 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
   bool shook = (C == 1);
 
   // =============================================================================== memory warp
-  if (warp == G * GW) {
+  if (warp == NG * GW) {
     auto issue_load = [&](int it) {
-      const int g = it % G;
+      const int g = it % NG;                                   // consuming group
+      const int b = it % NB;                                   // slice buffer
       const int row = cid + it * n_clusters;
       if (lane == 0 && n > 0) {
         const T* src = reinterpret_cast<const T*>(p.logits) + static_cast<long long>(row) * p.ld_in + start;
         const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(T);
         mbar_expect_tx(&sh.full[g], bytes);
-        unsigned char* dst = smem_raw + static_cast<size_t>(g) * p.slice_smem_bytes;
+        unsigned char* dst = smem_raw + static_cast<size_t>(b) * p.slice_smem_bytes;
         for (uint32_t off = 0; off < bytes; off += 32768u)
           tma_load_1d(dst + off, reinterpret_cast<const unsigned char*>(src) + off, min(32768u, bytes - off), &sh.full[g]);
       } else if (lane == 0) {
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
       }
     };
     auto zero_fill = [&](int it) {
-      const int g = it % G;
+      const int g = it % NG;
       const int row = cid + it * n_clusters;
       if (want_probs) {                                                     // zeros of this item's output slice
         float* o = p.probs + static_cast<long long>(row) * p.ld_out + start;
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     };
     // start-up: all G buffers are free.  (Issuing the G loads before the first zero-fill was measured slower: the
     // three store bursts then collide with the first item's pass 1 instead of hiding behind its load.)
-    const int n_first = min(G, n_items);
+    const int n_first = min(NB, n_items);
     for (int it = 0; it < n_first; ++it) {
       PIPE_PROF(it, 0, lane == 0); PIPE_PROF(it, 1, lane == 0);
       issue_load(it);
@@ -185,10 +192,9 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     }
     if (!shook) { cluster.barrier_wait(); shook = true; }
     for (int it = n_first; it < n_items; ++it) {
-      const int g = it % G;
-      const uint32_t use = static_cast<uint32_t>(it / G);
       PIPE_PROF(it, 0, lane == 0);
-      mbar_wait(&sh.empty[g], (use - 1) & 1);                               // group g is done with its buffer
+      mbar_wait(&sh.empty[it % NB], (static_cast<uint32_t>(it / NB) - 1) & 1);   // the re-scan of item it - NB is done
+      if (it >= NG) mbar_wait(&sh.taken[it % NG], (static_cast<uint32_t>(it / NG) - 1) & 1);   // its group saw item it - NG
       PIPE_PROF(it, 1, lane == 0);
       issue_load(it);
       zero_fill(it);
@@ -200,15 +206,16 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
   const int gt = tid - g * GT;               // thread index inside the group
   const int gw = warp - g * GW;              // warp index inside the group
   PipeGroupShared<CAP>& gs = sh.g[g];
-  const T* slice = reinterpret_cast<const T*>(smem_raw + static_cast<size_t>(g) * p.slice_smem_bytes);
-  const uint4* s4 = reinterpret_cast<const uint4*>(slice);
+
   const int bar_id = 1 + g;
   const int cap = CAP / C;
   const int vpt = (n_vec + GT - 1) / GT;
 
-  for (int it = g; it < n_items; it += G) {
-    const uint32_t use = static_cast<uint32_t>(it / G);
+  for (int it = g; it < n_items; it += NG) {
+    const uint32_t use = static_cast<uint32_t>(it / NG);      // how often this group's scratch / xbar have been used
     const int par = use & 1;
+    const int buf = it % NB;
+    const uint4* s4 = reinterpret_cast<const uint4*>(smem_raw + static_cast<size_t>(buf) * p.slice_smem_bytes);
     const int row = cid + it * n_clusters;
     float* orow = want_probs ? p.probs + static_cast<long long>(row) * p.ld_out : nullptr;
 
@@ -301,8 +308,9 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     PIPE_PROF(it, 7, gt == 0);
     mbar_wait(&sh.zeroed[g], use & 1);
     __syncwarp();
-    if (lane == 0) mbar_arrive_local(&sh.empty[g]);
+    if (lane == 0) mbar_arrive_local(&sh.empty[buf]);
     named_bar(bar_id, GT);
+    if (gt == 0) mbar_arrive_local(&sh.taken[g]);              // every warp of the group has observed full + zeroed
 
     PIPE_PROF(it, 8, gt == 0);
     // ---- publish: push my candidates into every peer's receive region, then signal its mbarrier
@@ -529,7 +537,7 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
     p2.prof = nullptr;
     for (int it = 0; it < n_items; ++it) {
       if ((sh.fail_bits[it >> 5] >> (it & 31)) & 1u) {
-        norm_row<T, 32 + G * kPipeGroupThreads>(p2, cid + it * n_clusters);
+        norm_row<T, 32 + NG * kPipeGroupThreads>(p2, cid + it * n_clusters);
         __syncthreads();
       }
     }
@@ -537,24 +545,29 @@ __global__ void __launch_bounds__(32 + G * kPipeGroupThreads, 1) norm_topk_pipe_
 }
 
 // ------------------------------------------------------------------------------------------------
-using PipeShared3S = PipeShared<3, kPipeCapSmall>;
-using PipeShared2S = PipeShared<2, kPipeCapSmall>;
+// The kernel variants that are compiled: (compute groups, slice buffers, merged-candidate capacity)
+struct PipeVariant { int ng, nb, cap; size_t fixed, mask_off, row_need; };
+#define SD_PIPE_VARIANT(NG, NB, CAP) \
+  {NG, NB, CAP, sizeof(PipeShared<NG, NB, CAP>), offsetof(PipeSharedAlias##NG##NB##CAP, fail_bits), sizeof(NormShared<32 + NG * kPipeGroupThreads>)}
+using PipeSharedAlias43128 = PipeShared<4, 3, 128>;
+using PipeSharedAlias33256 = PipeShared<3, 3, 256>;
+using PipeSharedAlias32128 = PipeShared<3, 2, 128>;
+using PipeSharedAlias22256 = PipeShared<2, 2, 256>;
+static const PipeVariant kPipeVariants[] = {      // in order of preference
+    SD_PIPE_VARIANT(4, 3, 128), SD_PIPE_VARIANT(3, 3, 256), SD_PIPE_VARIANT(3, 2, 128), SD_PIPE_VARIANT(2, 2, 256)};
+constexpr int kNumPipeVariants = 4;
 
-// static shared-memory need besides the G slice buffers, and whether the in-kernel fallback (norm_row) fits in front
-// of the failed-item mask
-static bool pipe_fits(int G, int CAP, size_t slice_bytes, size_t* fixed_out) {
-  size_t fixed, mask_off, row_need;
-  if (G >= 3 && CAP == kPipeCapSmall) { fixed = sizeof(PipeShared3S); mask_off = offsetof(PipeShared3S, fail_bits); row_need = sizeof(NormShared<32 + 3 * kPipeGroupThreads>); }
-  else if (G == 2 && CAP == kPipeCapSmall) { fixed = sizeof(PipeShared2S); mask_off = offsetof(PipeShared2S, fail_bits); row_need = sizeof(NormShared<32 + 2 * kPipeGroupThreads>); }
-  else return false;
-  *fixed_out = fixed;
-  if (static_cast<size_t>(G) * slice_bytes + fixed > 227 * 1024) return false;
-  return slice_bytes + row_need <= static_cast<size_t>(G) * slice_bytes + mask_off;
+// does variant v fit: NB slice buffers + its scratch within 227 KB, the in-kernel fallback (norm_row) in front of the
+// failed-item mask, and k + slack candidates per cluster rank
+static bool pipe_fits(const PipeVariant& v, size_t slice_bytes, int C, int kcap) {
+  if (kcap > v.cap / C) return false;
+  if (static_cast<size_t>(v.nb) * slice_bytes + v.fixed > 227 * 1024) return false;
+  return slice_bytes + v.row_need <= static_cast<size_t>(v.nb) * slice_bytes + v.mask_off;
 }
 
-template <typename T, int G, int CAP>
+template <typename T, int NG, int NB, int CAP>
 static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStream_t st, int* query_max_clusters) {
-  auto kern = norm_topk_pipe_kernel<T, G, CAP>;
+  auto kern = norm_topk_pipe_kernel<T, NG, NB, CAP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -562,8 +575,8 @@ static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStrea
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(32 + G * kPipeGroupThreads);
-  cfg.dynamicSmemBytes = static_cast<size_t>(G) * p.slice_smem_bytes + sizeof(PipeShared<G, CAP>);
+  cfg.blockDim = dim3(32 + NG * kPipeGroupThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(NB) * p.slice_smem_bytes + sizeof(PipeShared<NG, NB, CAP>);
   cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -582,8 +595,13 @@ static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStrea
 
 template <typename T>
 static cudaError_t pipe_dispatch(const NormParams& p, int rows, cudaStream_t st, int* q) {
-  if (p.pipe_groups >= 3) return pipe_launch_or_query<T, 3, kPipeCapSmall>(p, rows, st, q);
-  return pipe_launch_or_query<T, 2, kPipeCapSmall>(p, rows, st, q);
+  switch (p.pipe_groups * 100 + p.pipe_buffers * 10 + (p.pipe_cap == 128 ? 1 : 2)) {
+    case 431: return pipe_launch_or_query<T, 4, 3, 128>(p, rows, st, q);
+    case 332: return pipe_launch_or_query<T, 3, 3, 256>(p, rows, st, q);
+    case 321: return pipe_launch_or_query<T, 3, 2, 128>(p, rows, st, q);
+    case 222: return pipe_launch_or_query<T, 2, 2, 256>(p, rows, st, q);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 static cudaError_t pipe_dispatch_dtype(const NormParams& p, int dtype, int rows, cudaStream_t st, int* q) {
@@ -598,7 +616,7 @@ static cudaError_t pipe_dispatch_dtype(const NormParams& p, int dtype, int rows,
 // Decides whether the pipelined kernel applies and with which geometry: among the cluster sizes whose slices leave
 // room for >= 2 buffers, take the one that keeps the most SMs busy (clusters of 3..16 CTAs cannot use every SM).
 // The choice is cached per (dtype, V, top_k bucket).  Returns false if the kernel is not applicable.
-struct PipePlan { long long V; int dtype, kcap, cluster, groups, cap, max_clusters; };
+struct PipePlan { long long V; int dtype, kcap, cluster, groups, buffers, cap, max_clusters; };
 static PipePlan g_plans[32];
 static int g_n_plans = 0;
 
@@ -612,7 +630,7 @@ bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
   const PipePlan* plan = nullptr;
   for (int i = 0; i < g_n_plans; ++i)
     if (g_plans[i].V == p.V && g_plans[i].dtype == dtype && g_plans[i].kcap == kcap && tune_cluster == 0) plan = &g_plans[i];
-  PipePlan fresh = {p.V, dtype, kcap, 0, 0, 0, 0};
+  PipePlan fresh = {p.V, dtype, kcap, 0, 0, 0, 0, 0};
   if (plan == nullptr) {
     double best_score = 0.0;
     for (int C = 1; C <= kMaxPortableCluster; ++C) {
@@ -621,23 +639,24 @@ bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
       if (C > 1 && slice * (C - 1) >= p.V) continue;         // last rank would be empty
       if (slice / kPipeGroupThreads > 60000) continue;
       const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
-      const int CAP = C <= 8 ? kPipeCapSmall : kPipeCapLarge;
-      if (kcap > CAP / C) continue;
-      size_t fixed = 0;
-      int G = 0;
-      if (CAP == kPipeCapSmall && pipe_fits(3, CAP, slice_bytes, &fixed)) G = 3;
-      else if (pipe_fits(2, CAP, slice_bytes, &fixed)) G = 2;
-      if (G == 0) continue;
+      const PipeVariant* var = nullptr;
+      for (int vi = 0; vi < kNumPipeVariants && var == nullptr; ++vi)
+        if (pipe_fits(kPipeVariants[vi], slice_bytes, C, kcap)) var = &kPipeVariants[vi];
+      if (var == nullptr) continue;
       NormParams q = p;
       q.cluster = C; q.slice_elems = static_cast<int>(slice); q.slice_smem_bytes = static_cast<int>(slice_bytes);
-      q.pipe_groups = G; q.pipe_cap = CAP;
+      q.pipe_groups = var->ng; q.pipe_buffers = var->nb; q.pipe_cap = var->cap;
       int n = 0;
       if (pipe_dispatch_dtype(q, dtype, rows, nullptr, &n) != cudaSuccess || n < 1) { (void)cudaGetLastError(); continue; }
-      // busy SMs, mildly preferring three buffers (better latency hiding) and small clusters (less exchange)
-      const double score = static_cast<double>(n) * C * (G == 3 ? 1.0 : 0.93) * (1.0 - 0.01 * C);
+      // busy SMs, preferring three buffers (deeper prefetch), more groups than buffers, and small clusters
+      const double score = static_cast<double>(n) * C * (var->nb == 3 ? 1.0 : 0.93) * (var->ng > var->nb ? 1.0 : 0.96) * (1.0 - 0.01 * C);
       if (getenv("SD_DEBUG") != nullptr)
-        fprintf(stderr, "[specdec] pipe plan V=%lld es=%zu C=%d G=%d CAP=%d slice=%zuB: %d clusters, score %.1f\n", p.V, es, C, G, CAP, slice_bytes, n, score);
-      if (score > best_score) { best_score = score; fresh.cluster = C; fresh.groups = G; fresh.cap = CAP; fresh.max_clusters = n; }
+        fprintf(stderr, "[specdec] pipe plan V=%lld es=%zu C=%d groups=%d buffers=%d CAP=%d slice=%zuB: %d clusters, score %.1f\n",
+                p.V, es, C, var->ng, var->nb, var->cap, slice_bytes, n, score);
+      if (score > best_score) {
+        best_score = score; fresh.cluster = C; fresh.groups = var->ng; fresh.buffers = var->nb; fresh.cap = var->cap; fresh.max_clusters = n;
+      }
+      const int G = var->nb;
       if (tune_cluster == 0 && n * C >= 148 && G == 3) break;          // cannot do better than all SMs with three buffers
     }
     if (tune_cluster == 0 && g_n_plans < 32) { g_plans[g_n_plans] = fresh; plan = &g_plans[g_n_plans++]; }
@@ -652,6 +671,7 @@ bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
   p.slice_elems = static_cast<int>(slice);
   p.slice_smem_bytes = static_cast<int>((static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127));
   p.pipe_groups = plan->groups;
+  p.pipe_buffers = plan->buffers;
   p.pipe_cap = plan->cap;
   p.pipe_clusters = n_clusters;
   p.use_tma = 1;

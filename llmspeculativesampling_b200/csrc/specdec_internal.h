@@ -26,7 +26,7 @@ struct NormParams {
   long long* prof;                         // debug: per-CTA clock64 timestamps (16 slots per CTA), nullable
   int rows;                                // number of logits rows
   int pipe_groups;                         // persistent kernel: compute groups (= slice buffers) per CTA
-  int pipe_cap, pipe_clusters;             // ... merged-candidate capacity, clusters in the persistent grid
+  int pipe_buffers, pipe_cap, pipe_clusters;             // ... merged-candidate capacity, clusters in the persistent grid
   const int* row_filter;                   // norm_probs_kernel: process only rows with row_filter[row] != 0
 };
 cudaError_t launch_norm(const NormParams& p, int dtype, int rows, cudaStream_t st);
