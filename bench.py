@@ -197,7 +197,33 @@ def run_config1(args):
                                  "iterations": d["iterations"], "mean_accepted": sum(d["acc_len"]) / max(1, len(d["acc_len"])), "cuda_graph": d["cuda_graph"]},
                         "leading_tokens_identical_to_cpu_run": agree, "of": same})
             draft.cpu(); target.cpu()
-    print(json.dumps({"workload": "config 1: llama-68m-shape draft + target, gamma=4, batch=1, 128 new tokens, fp32", "results": out}))
+    # per-op micro-timings: one row, T=0.8 top_k=20 top_p=0.9, CPU oracle (1 thread) vs the kernels
+    from oracle import ref_ops
+    from llmspeculativesampling_b200 import ops
+    micro = []
+    for V_ in (32000, 50272):
+        x = torch.randn(1, V_, generator=torch.Generator().manual_seed(V_)) * 3.8
+        pr = ref_ops.norm_probs(x, 0.8, 20, 0.9)
+        dense = torch.softmax(x, -1)
+        cpu = {}
+        for name, fn in (("norm_logits", lambda: ref_ops.norm_probs(x, 0.8, 20, 0.9)), ("sample", lambda: ref_ops.icdf_sample(dense[0], 0.37)),
+                         ("max_fn", lambda: ref_ops.max_fn(dense - pr))):
+            fn(); t0 = time.perf_counter()
+            for _ in range(20): fn()
+            cpu[name] = (time.perf_counter() - t0) / 20 * 1e3
+        xg, dg, pg, ug = x.cuda(), dense.cuda(), pr.cuda(), torch.tensor([0.37], device="cuda")
+        gpu = {}
+        for name, fn in (("norm_logits", lambda: ops.norm_probs(xg, 0.8, 20, 0.9)), ("sample", lambda: ops.sample_rows(dg, ug)),
+                         ("max_fn", lambda: ops.max_fn(dg - pg))):
+            for _ in range(5): fn()
+            torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(50): fn()
+            e1.record(); torch.cuda.synchronize()
+            gpu[name] = e0.elapsed_time(e1) / 50
+        micro.append({"V": V_, "cpu_oracle_ms_per_row_1thread": cpu, "b200_ms_per_call_batch1": gpu})
+    print(json.dumps({"workload": "config 1: llama-68m-shape draft + target, gamma=4, batch=1, 128 new tokens, fp32", "results": out,
+                      "per_op_one_row": micro}))
     return 0
 
 

@@ -196,3 +196,34 @@ def test_compact_lists_and_sparse_verify_equal_dense(cuda_lib, V, dtype, pipelin
         wn, wt, wr, _ = ref_ops.verify_request(pc[b, gamma:], pc[b, :gamma], tok[b, :gamma].cpu(), u_acc[b].cpu().numpy(), float(u_fin[b]))
         assert (int(a_s[b]), int(t_s[b])) == (wn, wt)
         assert np.array_equal(ratios[b].cpu().numpy(), wr)
+
+
+def test_distribution_preservation_chi_square(cuda_lib):
+    """The reference authors' manual two-token check (kvcache_model.py:73-76, speculative_sampling.py:227-229: force
+    p = {1: .4, 12: .6}, q = {1: .6, 12: .4} and count emitted tokens) as a statistical test of the whole step:
+    draft from q (sd_sample), verify against p (sd_verify); the first emitted token must follow p whatever q is."""
+    from llmspeculativesampling_b200 import ops
+    N, V = 200000, 16
+    g = torch.Generator().manual_seed(11)
+    for strict in (False, True):
+        for (pd, qd) in [({1: 0.4, 12: 0.6}, {1: 0.6, 12: 0.4}), ({0: 0.1, 3: 0.2, 7: 0.3, 15: 0.4}, {0: 0.4, 3: 0.3, 7: 0.2, 9: 0.1})]:
+            p_row = torch.zeros(V); q_row = torch.zeros(V)
+            for k_, v_ in pd.items(): p_row[k_] = v_
+            for k_, v_ in qd.items(): q_row[k_] = v_
+            q = q_row.repeat(N, 1, 1).cuda()                      # (N, gamma=1, V)
+            p = p_row.repeat(N, 2, 1).cuda()                      # (N, gamma+1, V)
+            u = torch.rand(N, 4, generator=g).cuda()
+            draft = ops.sample_rows(q[:, 0].contiguous(), u[:, 0].contiguous()).view(N, 1)
+            n_acc, nxt = ops.verify(p, q, draft, u[:, 2:3].contiguous(), u[:, 3].contiguous(), strict=strict)
+            ops.default_flag("cuda").check()
+            first = torch.where(n_acc > 0, draft[:, 0], nxt)      # accepted draft token, else the resampled one
+            counts = torch.bincount(first.cpu(), minlength=V).double()
+            expect = p_row.double() * N
+            support = expect > 0
+            assert float(counts[~support].sum()) == 0.0
+            chi2 = float(((counts[support] - expect[support]) ** 2 / expect[support]).sum())
+            dof = int(support.sum()) - 1
+            assert chi2 < 30.0, f"chi2={chi2:.1f} (dof {dof}) strict={strict}: emitted tokens do not follow the target"
+            # acceptance rate = sum_i min(p_i, q_i)
+            want_acc = float(torch.minimum(p_row, q_row).sum())
+            assert abs(float(n_acc.float().mean()) - want_acc) < 0.01
