@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libspecdec_b200.so")
 SOURCES = ["norm.cu", "norm_pipe.cu", "verify.cu", "misc.cu", "api.cu"]
-HEADERS = ["common.cuh", "rowops.cuh", "specdec_internal.h", os.path.join("..", "..", "include", "specdec_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "specdec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

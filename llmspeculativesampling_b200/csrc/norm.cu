@@ -85,6 +85,11 @@ static cudaError_t launch_typed(NormParams p, int rows, cudaStream_t st) {
   int C = 1;
   while (C < kMaxPortableCluster && (row_bytes + C - 1) / C > 64 * 1024) C <<= 1;
   while (C < kMaxPortableCluster && static_cast<long long>(rows) * C < 148 && row_bytes / (2 * C) >= 8192) C <<= 1;
+  {
+    // every CTA publishes at least min(k, slice) candidates: keep the per-rank share of the merged list above that
+    const int kc = p.top_k > 0 ? p.top_k : (p.top_p > 0.f ? kTopPCandidates : 0);
+    while (C > 1 && kc > 0 && kc <= kFastK && kCapTotal / C < kc + kc / 2 + 16 && (row_bytes + C / 2 - 1) / (C / 2) <= 200 * 1024) C >>= 1;
+  }
   if (g_tune_cluster > 0) C = g_tune_cluster;
   // slice: multiple of 128 elements so that every slice start is 16-byte aligned in both dtypes
   long long slice = ((p.V + C - 1) / C + 127) & ~127LL;

@@ -11,6 +11,7 @@ namespace sd {
 
 constexpr int kCapTotal = 512;     // merged candidates per row
 constexpr int kFastK = 128;        // largest top_k served by the fast path
+constexpr int kTopPCandidates = 64;   // top-p-only rows: candidates tried before falling back to the general path
 constexpr int kMaxChunks = 4;      // TMA chunks per slice (pass 1 starts when the first lands)
 constexpr uint32_t kTieUlps = 8;   // pivot slack so that logits that tie AFTER the division by T are kept
 
@@ -26,8 +27,8 @@ struct alignas(16) NormShared {
   // [r * cap, r * cap + recv_cnt[r]) of EVERY peer (distributed shared memory stores); after the merge it holds the
   // row's candidate list sorted by (value desc, index asc)
   float r_val[kCapTotal]; int r_idx[kCapTotal];
-  union {
-    struct { float a_val[kCapTotal]; int a_idx[kCapTotal]; };   // merged unsorted list, later (a_val) final probabilities
+  union alignas(8) {
+    struct { float a_val[kCapTotal]; int a_idx[kCapTotal]; };   // merged list as 64-bit sort keys, later (a_val) final probabilities
     float tm[THREADS];                                          // per-warp sorted thread maxima (pivot phase only)
   };
 };
@@ -79,7 +80,12 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
   const int k_eff = p.top_k > 0 ? min(p.top_k, V) : 0;
   const bool want_probs = p.probs != nullptr;
   float* orow = want_probs ? p.probs + static_cast<long long>(row) * p.ld_out : nullptr;
-  const bool fast = k_eff > 0 && k_eff <= kFastK && !p.force_general;
+  // top-p without top-k: try the candidate machinery on the kTopPCandidates largest logits — the nucleus of a peaked
+  // distribution is far smaller than that; if the cumulative mass of the candidates never crosses top_p the row
+  // goes to the general path (exactness is never at stake: the crossing must be FOUND among complete candidates)
+  const bool topp_only = k_eff == 0 && p.top_p > 0.f && !p.force_general;
+  const int k_sel = topp_only ? min(kTopPCandidates, V) : k_eff;
+  const bool fast = k_sel > 0 && k_sel <= kFastK && !p.force_general;
   if (fast && C > 1) cx.cluster.barrier_arrive();   // matched by the wait right before candidates are pushed to peers
   SD_PROF(0);
 
@@ -146,7 +152,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
     if (tid == 0) { sh.cand_cnt = 0; sh.hot_cnt = 0; sh.tau = -INFINITY; }
     __syncthreads();
     SD_PROF(11);
-    if (lane < min(k_eff, 32)) {
+    if (lane < min(k_sel, 32)) {
       // W-1 independent binary searches, interleaved so that their shared-memory latencies overlap
       int lo[W], hi[W];
 #pragma unroll
@@ -165,7 +171,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
       int rank = lane;
 #pragma unroll
       for (int w = 0; w < W; ++w) rank += (w == warp) ? 0 : lo[w];
-      if (rank == k_eff - 1) sh.tau = sv;
+      if (rank == k_sel - 1) sh.tau = sv;
     }
     __syncthreads();
     SD_PROF(12);
@@ -204,7 +210,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
       // self-check: a slice that collected every element >= its pivot and at least min(k, n) of them cannot miss a
       // member of the row's top-k, whatever the pivot was; anything else sends the row to the general path
       const int c = sh.cand_cnt;
-      const int mine = (c > cap || c < min(k_eff, n)) ? -1 : c;
+      const int mine = (c > cap || c < min(k_sel, n)) ? -1 : c;
       if (C > 1) {
         cx.cluster.barrier_wait();                            // (arrive at kernel start) every peer is running
         for (int r = 0; r < C; ++r) {
@@ -222,52 +228,59 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
     if (C > 1) cx.cluster.sync(); else __syncthreads();       // pushes visible; no remote access after this point
     SD_PROF(5);
 
-    // merge: compact the C receive regions into one list (identical in every CTA of the cluster)
+    // merge: concatenate the C receive regions as 64-bit sort keys (value key << 32 | ~index) — identical in every
+    // CTA of the cluster; the key array overlays a_val/a_idx, which are only needed again after the sort
+    unsigned long long* a_key = reinterpret_cast<unsigned long long*>(sh.a_val);
     int n_tot = 0;
     bool ok = true;
-    int offs[kMaxCluster + 1];
-#pragma unroll
-    for (int r = 0; r < kMaxCluster; ++r) {
-      offs[r] = n_tot;
-      if (r < C) { const int c = sh.recv_cnt[r]; ok &= c >= 0; n_tot += max(c, 0); }
-    }
-    offs[kMaxCluster] = n_tot;
-    ok &= n_tot >= k_eff;
-    if (ok) {
-#pragma unroll
-      for (int r = 0; r < kMaxCluster; ++r) {
-        if (r < C) {
-          const int cnt = offs[r + 1] - offs[r];
-          for (int i = tid; i < cnt; i += THREADS) { sh.a_val[offs[r] + i] = sh.r_val[r * cap + i]; sh.a_idx[offs[r] + i] = sh.r_idx[r * cap + i]; }
-        }
+    for (int r = 0; r < C; ++r) {
+      const int c = sh.recv_cnt[r];
+      ok &= c >= 0;
+      for (int i = tid; i < c; i += THREADS) {
+        const float xv = sh.r_val[r * cap + i] + 0.0f;                       // -0 -> +0: equal values tie on the index
+        a_key[n_tot + i] = (static_cast<unsigned long long>(f2key(xv)) << 32) | (0xffffffffu - static_cast<uint32_t>(sh.r_idx[r * cap + i]));
       }
+      n_tot += max(c, 0);
     }
+    ok &= n_tot >= k_sel;
+    if (p.prof != nullptr && tid == 0) p.prof[static_cast<long long>(blockIdx.x) * 16 + 14] = n_tot;
     __syncthreads();
 
     if (ok) {
-      // rank sort (value descending, vocabulary index ascending): four threads per candidate split the comparisons
+      // rank sort (value descending, vocabulary index ascending): four threads per candidate, branch-free inner loop
       for (int base = 0; base < n_tot; base += THREADS / 4) {
         const int i = base + (tid >> 2);
         const bool live = i < n_tot;
-        const float x = live ? sh.a_val[i] : 0.f;
-        const int id = live ? sh.a_idx[i] : 0;
+        const unsigned long long ki = live ? a_key[i] : 0ull;
         int r = 0;
-        if (live)
-          for (int j = tid & 3; j < n_tot; j += 4) {
-            const float y = sh.a_val[j];
-            r += (y > x || (y == x && sh.a_idx[j] < id)) ? 1 : 0;
-          }
+        if (live) {
+#pragma unroll 4
+          for (int j = tid & 3; j < n_tot; j += 4) r += a_key[j] > ki ? 1 : 0;
+        }
         r += __shfl_xor_sync(0xffffffffu, r, 1);
         r += __shfl_xor_sync(0xffffffffu, r, 2);
-        if (live && (tid & 3) == 0) { sh.r_val[r] = x; sh.r_idx[r] = id; }
+        if (live && (tid & 3) == 0) {
+          sh.r_val[r] = key2f(static_cast<uint32_t>(ki >> 32));
+          sh.r_idx[r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(ki & 0xffffffffull));
+        }
       }
       __syncthreads();
       SD_PROF(6);
-      const float kth = sh.r_val[k_eff - 1];
+      const float kth = sh.r_val[k_sel - 1];
       for (int i = tid; i < n_tot; i += THREADS)
         if (sh.r_val[i] >= kth && (i + 1 == n_tot || sh.r_val[i + 1] < kth)) sh.n_keep_k = i + 1;
       __syncthreads();
       const int nk = sh.n_keep_k;
+      double zfull = 0.0;              // top-p only: softmax denominator of the WHOLE row (reference utils.py:172)
+      if (topp_only && nk < V) {       // cluster-uniform
+        const float Mx = sh.r_val[0];
+        const float r_temp = 1.0f / temp;
+        float acc = 0.f;
+        for_each_elem<T, THREADS>(slice, n_vec, start, tid, [&](float l, int) {
+          const float x = temp == 1.0f ? l : div_fast(l, temp, r_temp);
+          acc += exp2f((x - Mx) * 1.4426950408889634f); });            // padding is -inf -> 0
+        zfull = cx.allreduce_sum(static_cast<double>(acc));
+      }
 
       if (warp == 0 && nk <= 32) {   // usual case: the whole kept list lives in one warp's registers
         const bool in_k = lane < nk;
@@ -317,12 +330,14 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
               p.tok_out[row] = (pr < kProbGuard) ? top_id : id;          // utils.py:228-230 guard
           }
         }
-      } else if (warp == 0) {   // long kept list (large top_k or many ties): same steps, strided over the list
+      } else if (warp == 0) {   // long kept list (large top_k, many ties, top-p-only candidates): strided over the list
         const float M = sh.r_val[0];
         double zs = 0.0;
         for (int i = lane; i < nk; i += 32) zs += static_cast<double>(expf(sh.r_val[i] - M));
         zs = warp_sum(zs);
+        if (topp_only && nk < V) zs = zfull;
         int np = nk;
+        bool crossed = false;
         if (p.top_p > 0.f) {
           const float rz = 1.0f / static_cast<float>(zs);
           double run = 0.0;
@@ -332,14 +347,15 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
             const double cum = warp_scan_incl(static_cast<double>(sp), lane) + run;
             const bool over = i < nk && static_cast<float>(cum) > p.top_p;
             const unsigned ball = __ballot_sync(0xffffffffu, over);
-            if (ball) { np = min(nk, base + __ffs(ball)); break; }
+            if (ball) { np = min(nk, base + __ffs(ball)); crossed = true; break; }
             run = __shfl_sync(0xffffffffu, cum, 31);
           }
         }
+        if (topp_only && nk < V && !crossed) np = -1;      // nucleus larger than the candidate list: general path
         double z2 = 0.0;
         for (int i = lane; i < np; i += 32) z2 += static_cast<double>(expf(sh.r_val[i] - M));
         z2 = warp_sum(z2);
-        const float logz = logf(static_cast<float>(z2));
+        const float logz = np > 0 ? logf(static_cast<float>(z2)) : 0.f;
         bool badp = false;
         for (int i = lane; i < np; i += 32) {
           const float pr = expf((sh.r_val[i] - M) - logz);
@@ -349,14 +365,14 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         if (badp) atomicOr(p.err_flag, kErrNanLogit);
         if (lane == 0) sh.n_keep_p = np;
         __syncwarp();
-        if (p.cmp.cnt != nullptr && cx.crank == 0) {
+        if (np >= 0 && p.cmp.cnt != nullptr && cx.crank == 0) {
           const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
           if (np <= p.cmp.cap) {
             for (int i = lane; i < np; i += 32) { p.cmp.idx[cr * p.cmp.cap + i] = sh.r_idx[i]; p.cmp.val[cr * p.cmp.cap + i] = sh.a_val[i]; }
             if (lane == 0) p.cmp.cnt[cr] = np;
           } else if (lane == 0) p.cmp.cnt[cr] = -1;
         }
-        if (p.u != nullptr && cx.crank == 0 && p.u[row] >= 0.f) {
+        if (np >= 0 && p.u != nullptr && cx.crank == 0 && p.u[row] >= 0.f) {
           const int e = frexp_exp(sh.a_val[0]);
           unsigned long long tot = 0ull;
           for (int i = lane; i < np; i += 32) tot += weight_of(sh.a_val[i], e);
@@ -377,14 +393,16 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         }
       }
       __syncthreads();
-      if (want_probs) {
-        const int np = sh.n_keep_p;
-        for (int i = tid; i < np; i += THREADS) {
-          const int id = sh.r_idx[i];
-          if (id >= start && id < start + n) orow[id] = sh.a_val[i];
+      if (sh.n_keep_p >= 0) {            // (< 0: top-p-only nucleus larger than the candidate list -> general path below)
+        if (want_probs) {
+          const int np = sh.n_keep_p;
+          for (int i = tid; i < np; i += THREADS) {
+            const int id = sh.r_idx[i];
+            if (id >= start && id < start + n) orow[id] = sh.a_val[i];
+          }
         }
+        done = true;
       }
-      done = true;
     }
     SD_PROF(7);
     if (!done) __syncthreads();

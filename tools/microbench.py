@@ -17,6 +17,7 @@ from llmspeculativesampling_b200 import ops, build  # noqa: E402
 
 
 PIPELINE = True
+SCALE = 3.8
 
 
 def time_norm(rows, V, dtype, T, k, p, iters=40, sample=False, write=True):
@@ -24,7 +25,7 @@ def time_norm(rows, V, dtype, T, k, p, iters=40, sample=False, write=True):
     per_set = rows * V * (es + (4 if write else 0))
     n_sets = max(2, int(2.2 * 126e6 / per_set) + 1)
     g = torch.Generator(device="cuda").manual_seed(1)
-    ins = [(torch.randn(rows, V, device="cuda", generator=g) * 3.8).to(dtype) for _ in range(n_sets)]
+    ins = [(torch.randn(rows, V, device="cuda", generator=g) * SCALE).to(dtype) for _ in range(n_sets)]
     outs = [torch.empty(rows, V, device="cuda") for _ in range(n_sets)] if write else [None] * n_sets
     u = torch.rand(rows, device="cuda")
     tok = torch.empty(rows, dtype=torch.int64, device="cuda")
@@ -56,30 +57,36 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--mode", default="")
     ap.add_argument("--prof", action="store_true")
+    ap.add_argument("--scale", type=float, default=3.8, help="standard deviation of the synthetic logits")
     ap.add_argument("--classic", action="store_true")
     ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--k", type=int, default=-1, help="override the mode's top_k")
+    ap.add_argument("--p", type=float, default=-1.0, help="override the mode's top_p")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     a = ap.parse_args()
-    global PIPELINE
+    global PIPELINE, SCALE
     PIPELINE = not a.classic
+    SCALE = a.scale
     build.build()
     dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[a.dtype]
     modes_all = {"topk": ("topk20_p0.9", 0.8, 20, 0.9), "dense": ("dense", 1.0, 0, 0.0), "topp": ("top_p_only", 1.0, 0, 0.9)}
     if a.mode:
         ops.set_tuning(a.cluster, a.threads, 0)
         name, T, k, p = modes_all[a.mode]
+        k = a.k if a.k >= 0 else k
+        p = a.p if a.p >= 0 else p
         ms, gbs = time_norm(a.rows, a.V, dt, T, k, p, iters=a.iters)
         print(json.dumps(dict(kernel="norm", mode=name, rows=a.rows, V=a.V, dtype=a.dtype, ms=round(ms, 4), GBs=round(gbs, 1))))
         if a.prof:
             from llmspeculativesampling_b200 import _cabi
             buf = torch.zeros(a.rows * 8 + 8192, 16, dtype=torch.int64, device="cuda")
-            x = (torch.randn(a.rows, a.V, device="cuda") * 3.8).to(dt)
+            x = (torch.randn(a.rows, a.V, device="cuda") * SCALE).to(dt)
             out = torch.empty(a.rows, a.V, device="cuda")
-            ops.norm_probs(x, T, k, p, out=out)
+            ops.norm_probs(x, T, k, p, out=out, pipeline=PIPELINE)
             torch.cuda.synchronize()
             _cabi.load().sd_debug_set_prof(buf.data_ptr())
-            ops.norm_probs(x, T, k, p, out=out)
+            ops.norm_probs(x, T, k, p, out=out, pipeline=PIPELINE)
             torch.cuda.synchronize()
             _cabi.load().sd_debug_set_prof(None)
             b = buf.cpu()
@@ -116,6 +123,8 @@ def main():
                     d = (b[m, s_] - b[m, prev]).float()
                     print(f"  slot {s_:2d} {names[s_]:20s} +{d.mean():9.0f} cyc (p10 {d.quantile(0.1):7.0f}, p90 {d.quantile(0.9):7.0f})")
                     prev = s_
+            if (b[:, 14] != 0).any():
+                print(f"  merged candidates per row: mean {b[:, 14].float().mean():.1f}, max {int(b[:, 14].max())}")
             tot = (b[:, 10] - b[:, 0]).float()
             print(f"  CTA lifetime mean {tot.mean():.0f} cyc, p90 {tot.quantile(0.9):.0f}")
         return
