@@ -163,6 +163,14 @@ __device__ __forceinline__ unsigned long long warp_scan_incl(unsigned long long 
   }
   return v;
 }
+__device__ __forceinline__ int warp_scan_incl(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
 __device__ __forceinline__ double warp_scan_incl(double v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {

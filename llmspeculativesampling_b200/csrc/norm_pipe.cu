@@ -223,15 +223,44 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     PIPE_PROF(it, 3, gt == 0);
     mbar_wait(&sh.full[g], use & 1);
     PIPE_PROF(it, 4, gt == 0);
-    float tmax = -INFINITY;
+    // Per thread: the three largest VECTOR maxima (tmax >= m2 >= m3) and the rounds i1, i2 of the first two — the
+    // re-scan below then only has to touch vectors i1 / i2 of a thread unless its third vector also reaches the pivot.
+    float tmax = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    int i1 = 0, i2 = 0;
+    bool bad = false;
     // ownership: in round i thread t owns vector i*GT + ((t + i) mod GT): consecutive lanes read consecutive vectors
     // here, and a warp that later re-reads ONE thread's vectors (lane = round) also walks consecutive banks
-    for (int i = 0; i < vpt; ++i) {
-      const int v = i * GT + ((gt + i) & (GT - 1));
-      if (v >= n_vec) continue;
-      tmax = vec_max_nan<T>(tmax, s4[v]);
+    float nan_acc = -INFINITY;                                // NaN-propagating running maximum: NaN / +inf detection only
+    constexpr int kBatch = 8;                                 // loads of a batch are issued before their results are used
+    for (int i0 = 0; i0 < vpt; i0 += kBatch) {
+      uint4 raw[kBatch];
+      bool valid[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int i = i0 + j;
+        const int v = i * GT + ((gt + i) & (GT - 1));
+        valid[j] = i < vpt && v < n_vec;
+        raw[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (valid[j]) raw[j] = s4[v];
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int i = i0 + j;
+        float vm = vec_max_nan<T>(-INFINITY, raw[j]);
+        vm = valid[j] ? vm : -INFINITY;
+        asm("max.NaN.f32 %0, %0, %1;" : "+f"(nan_acc) : "f"(vm));
+        const float lo1 = fminf(tmax, vm);                    // (fminf / fmaxf / > ignore a NaN operand: flagged through nan_acc)
+        const bool c1 = vm > tmax;
+        tmax = fmaxf(tmax, vm);
+        const bool c2 = lo1 > m2;
+        m3 = fmaxf(m3, fminf(m2, lo1));
+        m2 = fmaxf(m2, lo1);
+        i2 = c1 ? i1 : (c2 ? i : i2);
+        i1 = c1 ? i : i1;
+      }
     }
-    if (tmax != tmax || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
+    bad = nan_acc != nan_acc;
+    if (bad || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
 
     PIPE_PROF(it, 5, gt == 0);
     // ---- pivot = k-th largest of the GT thread maxima (see norm.cu)
@@ -266,13 +295,51 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     PIPE_PROF(it, 6, gt == 0);
     const float tau = float_down(gs.tau, temp == 1.0f ? 0u : kPipeTieUlps);
 
-    // ---- pass 2: every warp re-scans the vectors of ITS OWN threads whose maximum reaches the pivot (lane = round
-    //      index: bank-conflict free thanks to the swizzled ownership) and appends to a private candidate region:
-    //      no shared-memory atomics, no hot list, no barrier
+    // ---- pass 2: collect every element >= pivot of the threads whose maximum reaches it, into a per-warp candidate
+    //      region (no shared-memory atomics, no hot list, no barrier).  Usual case: the thread's candidates sit in its
+    //      vectors i1 (and i2), which it re-reads itself; a thread whose THIRD vector also reaches the pivot is
+    //      re-scanned completely by its warp (lane = round index: bank-conflict free thanks to the swizzled ownership).
     uint2* my_pair = gs.r_pair[par] + crank * cap;
     int wc = 0;                                               // candidates found by this warp (warp-uniform)
     {
-      unsigned hm = __ballot_sync(0xffffffffu, tmax >= tau);
+      const bool hot = tmax >= tau;
+      const bool slow = hot && m3 >= tau;
+      const bool quick = hot && !slow;
+      const int v1 = i1 * GT + ((gt + i1) & (GT - 1)), v2 = i2 * GT + ((gt + i2) & (GT - 1));
+      const bool two = quick && m2 >= tau && v2 < n_vec;
+      const int g1 = static_cast<int>(start) + v1 * PV, g2 = static_cast<int>(start) + v2 * PV;
+      float o1[PV], o2[PV];
+      int c = 0;
+      if (quick && v1 < n_vec) {
+        Elem<T>::unpack(s4[v1], o1);
+#pragma unroll
+        for (int j = 0; j < PV; ++j) c += (o1[j] >= tau && g1 + j < V) ? 1 : 0;
+        if (two) {
+          Elem<T>::unpack(s4[v2], o2);
+#pragma unroll
+          for (int j = 0; j < PV; ++j) c += (o2[j] >= tau && g2 + j < V) ? 1 : 0;
+        }
+      }
+      const int incl = warp_scan_incl(c, lane);
+      wc = __shfl_sync(0xffffffffu, incl, 31);
+      if (c > 0) {
+        int w = incl - c;
+#pragma unroll
+        for (int j = 0; j < PV; ++j)
+          if (o1[j] >= tau && g1 + j < V) {
+            if (w < kPipeWarpCap) gs.w_pair[gw][w] = make_uint2(__float_as_uint(o1[j]), static_cast<uint32_t>(g1 + j));
+            ++w;
+          }
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < PV; ++j)
+            if (o2[j] >= tau && g2 + j < V) {
+              if (w < kPipeWarpCap) gs.w_pair[gw][w] = make_uint2(__float_as_uint(o2[j]), static_cast<uint32_t>(g2 + j));
+              ++w;
+            }
+        }
+      }
+      unsigned hm = __ballot_sync(0xffffffffu, slow);
       while (hm) {
         const int t = gw * 32 + (__ffs(hm) - 1);
         hm &= hm - 1;
@@ -282,9 +349,9 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
           uint4 raw = make_uint4(0u, 0u, 0u, 0u);
           if (inb) raw = s4[v];
           const float vmax = inb ? vec_max_nan<T>(-INFINITY, raw) : -INFINITY;
-          unsigned vm = __ballot_sync(0xffffffffu, vmax >= tau);      // vectors holding at least one candidate (1-2 per hot thread)
+          unsigned vm = __ballot_sync(0xffffffffu, vmax >= tau);      // vectors holding at least one candidate
           float o[PV];
-          if (vm) Elem<T>::unpack(raw, o);                            // warp-uniform, rare
+          if (vm) Elem<T>::unpack(raw, o);                            // warp-uniform
           const int gi = static_cast<int>(start) + v * PV;
           while (vm) {
             const int src = __ffs(vm) - 1;
@@ -301,6 +368,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
           }
         }
       }
+      __syncwarp();
       if (lane == 0) gs.w_cnt[gw] = wc;
     }
     PIPE_PROF(it, 14, gt == 0);

@@ -100,16 +100,24 @@ def main():
                       f"globaltimer: first entry -> last exit {(g1.max() - g0.min()).item() / 1000:.2f} us, "
                       f"entry spread {(g0.max() - g0.min()).item() / 1000:.2f} us, exit spread {(g1.max() - g1.min()).item() / 1000:.2f} us")
                 t0 = t[:, 0, 0].clone()
+                last_done = t[:, :, 11].max(dim=1).values
+                tail = (ext - last_done).double() / 1000
+                life = (ext - ent).double() / 1000
+                n_it = (t[:, :, 11] != 0).sum(dim=1)
+                print(f"  exit - last item done: mean {tail.mean():.2f} kcyc, max {tail.max():.2f}; lifetime p10/p50/p90/max "
+                      f"{life.quantile(0.1):.1f}/{life.quantile(0.5):.1f}/{life.quantile(0.9):.1f}/{life.max():.1f} kcyc; "
+                      f"items per CTA {int(n_it.min())}..{int(n_it.max())}; lifetime of CTAs with max items {life[n_it == n_it.max()].mean():.1f}, others {life[n_it != n_it.max()].mean() if (n_it != n_it.max()).any() else float('nan'):.1f}")
                 names = ["mem: item start", "mem: buffer free", "mem: load issued + zero-filled", "grp: wait for data", "grp: data landed",
                          "grp: pass1 done", "grp: pivot done", "grp: rescan done", "grp: buffer released", "grp: peers landed",
                          "grp: sorted", "grp: item done", "grp: compacted", "grp: ranks done", "grp: hot list"]
-                for it in range(0, 9):
+                for it in range(0, 32):
                     row = []
                     for s_ in [0, 1, 2, 3, 4, 5, 6, 14, 7, 8, 9, 12, 13, 10, 11]:
                         v = t[:, it, s_]
                         m = v != 0
                         row.append(f"{((v - t0)[m]).double().mean() / 1000:6.2f}" if m.any() else "   -  ")
-                    print(f"  item {it}: " + " ".join(row))
+                    if (t[:, it, 0] != 0).any() or it == 0:
+                        print(f"  item {it:2d}: " + " ".join(row))
                 order = [0, 1, 2, 3, 4, 5, 6, 14, 7, 8, 9, 12, 13, 10, 11]
                 print("  columns (kcycles since kernel start, mean over CTAs): " + " | ".join(names[o] if o < 12 else names[o] for o in [0,1,2,3,4,5,6] ) + " | hot list | rescan done | released | peers landed | compacted | ranks done | sorted | item done")
                 return
