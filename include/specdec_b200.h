@@ -90,10 +90,17 @@ void sd_debug_set_prof(int64_t* device_buf);
  * Sets SD_ERR_NORM_LOGITS where the reference raises 'norm logits error' (utils.py:203-207). */
 int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
                   float top_p, float* probs, int64_t ld_out, const sd_compact_t* compact, int* err_flag, int flags,
-                  void* stream);
+                  void* workspace, void* stream);
+
+/* `workspace` of the two norm entry points: SD_NORM_WORKSPACE_BYTES of device memory, zeroed ONCE by the caller.  The
+ * persistent kernel hands rows to its clusters through a ticket counter that lives there (SMs run at visibly different
+ * speeds under full HBM load; a static split waits for the slowest) and leaves it zeroed when it ends, so the same
+ * block serves any number of launches that are ordered after one another (one stream, one CUDA graph).  Launches that
+ * may run CONCURRENTLY must use different blocks.  NULL is always safe: it selects the one-cluster-per-row kernel. */
+#define SD_NORM_WORKSPACE_BYTES 16
 
 /* `flags` of the two norm entry points.  By default, for 0 < top_k <= 128 and 16-byte aligned rows the persistent,
- * warp-specialised pipeline kernel runs (one CTA per SM: a memory warp streams slices in by TMA and zero-fills the
+ * warp-specialised pipeline kernel runs if a `workspace` is given (one CTA per SM: a memory warp streams slices in by TMA and zero-fills the
  * output while compute groups select; rows it cannot serve — massive ties — are re-run on the general path by the same
  * cluster before the kernel ends); every other case uses the one-cluster-per-row kernel. */
 #define SD_NORM_DEFAULT 0
@@ -106,7 +113,7 @@ int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_
  * sampling/autoregressive_sampling.py:41-44.  `probs` may be NULL (token only). */
 int sd_norm_sample(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
                    float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
-                   const sd_compact_t* compact, int* err_flag, int flags, void* stream);
+                   const sd_compact_t* compact, int* err_flag, int flags, void* workspace, void* stream);
 
 /* sample — one inverse-CDF draw per row of non-negative weights.  Replaces sampling/utils.py:213-233. */
 int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const float* u, int64_t* tok_out, int* err_flag,

@@ -47,7 +47,7 @@ static sd::Compact to_compact(const sd_compact_t* c) {
 
 static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
                        int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
-                       const sd_compact_t* compact, int* err_flag, int flags, void* stream) {
+                       const sd_compact_t* compact, int* err_flag, int flags, void* workspace, void* stream) {
   if (rows == 0) return SD_OK;
   if (logits == nullptr || err_flag == nullptr || rows < 0 || V <= 0 || ld_in < V) return fail(SD_EINVAL, "sd_norm: bad logits/shape");
   if (!(temperature > 0.f) || std::isinf(temperature)) return fail(SD_EINVAL, "sd_norm: temperature must be finite and > 0");
@@ -63,24 +63,25 @@ static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, i
   p.err_flag = err_flag;
   p.cmp = to_compact(compact);
   p.force_general = (flags & SD_NORM_FORCE_GENERAL) ? 1 : 0;
-  p.no_pipeline = (flags & SD_NORM_NO_PIPELINE) ? 1 : 0;
+  p.no_pipeline = ((flags & SD_NORM_NO_PIPELINE) || workspace == nullptr) ? 1 : 0;
+  p.sched = static_cast<unsigned int*>(workspace);
   return done("sd_norm launch", sd::launch_norm(p, dtype, static_cast<int>(rows), static_cast<cudaStream_t>(stream)));
 }
 
 int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
                   float top_p, float* probs, int64_t ld_out, const sd_compact_t* compact, int* err_flag, int flags,
-                  void* stream) {
+                  void* workspace, void* stream) {
   if (probs == nullptr) return fail(SD_EINVAL, "sd_norm_probs: probs is null");
   return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, nullptr, nullptr,
-                     compact, err_flag, flags, stream);
+                     compact, err_flag, flags, workspace, stream);
 }
 
 int sd_norm_sample(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature, int top_k,
                    float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
-                   const sd_compact_t* compact, int* err_flag, int flags, void* stream) {
+                   const sd_compact_t* compact, int* err_flag, int flags, void* workspace, void* stream) {
   if (u == nullptr || tok_out == nullptr) return fail(SD_EINVAL, "sd_norm_sample: u/tok_out is null");
   return norm_common(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, compact,
-                     err_flag, flags, stream);
+                     err_flag, flags, workspace, stream);
 }
 
 int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const float* u, int64_t* tok_out, int* err_flag,

@@ -32,7 +32,9 @@ constexpr int kPipeMaxGroups = 3;
 constexpr int kPipeFastK = 128;
 constexpr uint32_t kPipeTieUlps = 8;
 constexpr int kPipeWarpCap = 48;       // candidates one warp may collect per work item
-constexpr int kPipeMaxItems = 4096;    // work items one cluster can walk (bit mask of failed items)
+constexpr int kPipeMaxFail = 256;      // rows per cluster and round that may be deferred to the general path
+constexpr int kPipeFailSlack = 24;     // ... minus the items that can still be in flight when the leader stops taking rows
+constexpr int kPipeRowRing = 32;       // row indices of the items in flight (the leader is < 16 items ahead of a peer)
 
 template <int CAP>
 struct alignas(16) PipeGroupShared {
@@ -58,9 +60,18 @@ struct alignas(16) PipeShared {
   uint64_t zeroed[NG];                // that item's output slice is zero-filled     (memory warp -> group)
   uint64_t taken[NG];                 // group has observed full + zeroed            (group -> memory warp)
   uint64_t xbar[NG][2];               // peers' candidates landed             (remote groups -> group), by item parity
+  uint64_t rowbar[kPipeRowRing];      // row index of item it (slot it % ring) landed  (leader CTA's memory warp -> peer's)
+  uint2 row_in[kPipeRowRing];         // landing slots of those pushes (slot = dynamic item index % ring)
+  uint2 item_row[kPipeRowRing];       // .x = row of item it (slot it % ring), written by this CTA's memory warp for its
+                                      // groups; < 0: no more items (kPipeEndDone / kPipeEndPause)
   PipeGroupShared<CAP> g[NG];
-  uint32_t fail_bits[kPipeMaxItems / 32];   // work items that need the general path (kept LAST: survives norm_row)
+  // kept LAST (survives norm_row, which re-purposes everything in front of it):
+  int n_fail;                         // rows deferred to the general path in this round ...
+  int end_reason;                     // ... and why the round ended
+  int fail_rows[kPipeMaxFail];
 };
+constexpr int kPipeEndDone = -1;       // every row has been handed out
+constexpr int kPipeEndPause = -2;      // the deferred-row list is nearly full: run the general path, then resume
 
 __device__ __forceinline__ void named_bar(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -121,14 +132,20 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
   const float temp = p.temperature;
   const int k_eff = min(p.top_k, V);
   const bool want_probs = p.probs != nullptr;
-  const int n_items = p.rows > cid ? (p.rows - cid + n_clusters - 1) / n_clusters : 0;   // rows cid, cid+n_clusters, ...
+  // Rows are handed out dynamically: the first NB items of a cluster are rows cid, cid + n_clusters, ... (so that the
+  // loads start without any exchange), every later item is the next ticket of a global counter, drawn by the leader
+  // CTA's memory warp one item ahead and pushed to its peers.  SMs run at visibly different speeds under full HBM load
+  // (lifetimes of CTAs with identical work differ by +-20 %), a static split would wait for the slowest.
+  const int static_rows = NB * n_clusters;                  // rows covered by the static prefix
   if (p.prof != nullptr && tid == 0) {
     unsigned long long gt0;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + 0) * 16 + 15] = clock64();
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + 2) * 16 + 15] = static_cast<long long>(gt0);
   }
+  bool shook = (C == 1);
 
+  for (int round = 0;; ++round) {                            // (a second round only after a kPipeEndPause)
   if (tid == 0) {
     for (int b = 0; b < NB; ++b) mbar_init(&sh.empty[b], GW);
     for (int g = 0; g < NG; ++g) {
@@ -138,22 +155,27 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
       mbar_init(&sh.xbar[g][0], 1);
       mbar_init(&sh.xbar[g][1], 1);
     }
+    for (int i = 0; i < kPipeRowRing; ++i) mbar_init(&sh.rowbar[i], 1);
+    sh.n_fail = 0;
+    sh.end_reason = kPipeEndDone;
     fence_barrier_init();
   }
-  for (int i = tid; i < kPipeMaxItems / 32; i += blockDim.x) sh.fail_bits[i] = 0u;
   __syncthreads();
-  pdl_wait();                                          // everything above overlapped the previous kernel's tail
-  // "my mbarriers are initialised": peers may only push candidates to me (st.async) after they waited on this; the
-  // wait is deferred to the first push so that the loads start immediately
-  if (C > 1) cluster.barrier_arrive();
-  bool shook = (C == 1);
+  if (round == 0) {
+    pdl_wait();                                        // everything above overlapped the previous kernel's tail
+    // "my mbarriers are initialised": peers may only push to me (st.async) after they waited on this; the wait is
+    // deferred to the first push so that the loads start immediately
+    if (C > 1) cluster.barrier_arrive();
+  } else if (C > 1) {
+    cluster.sync();
+    shook = true;
+  }
 
   // =============================================================================== memory warp
   if (warp == NG * GW) {
-    auto issue_load = [&](int it) {
+    auto issue_load = [&](int it, int row) {
       const int g = it % NG;                                   // consuming group
       const int b = it % NB;                                   // slice buffer
-      const int row = cid + it * n_clusters;
       if (lane == 0 && n > 0) {
         const T* src = reinterpret_cast<const T*>(p.logits) + static_cast<long long>(row) * p.ld_in + start;
         const uint32_t bytes = static_cast<uint32_t>(n) * sizeof(T);
@@ -165,9 +187,8 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
         mbar_arrive_local(&sh.full[g]);
       }
     };
-    auto zero_fill = [&](int it) {
+    auto zero_fill = [&](int it, int row) {
       const int g = it % NG;
-      const int row = cid + it * n_clusters;
       if (want_probs) {                                                     // zeros of this item's output slice
         float* o = p.probs + static_cast<long long>(row) * p.ld_out + start;
         if (p.vec_out) {
@@ -181,24 +202,79 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
       __syncwarp();
       if (lane == 0) mbar_arrive_local(&sh.zeroed[g]);
     };
-    // start-up: all G buffers are free.  (Issuing the G loads before the first zero-fill was measured slower: the
-    // three store bursts then collide with the first item's pass 1 instead of hiding behind its load.)
-    const int n_first = min(NB, n_items);
-    for (int it = 0; it < n_first; ++it) {
-      PIPE_PROF(it, 0, lane == 0); PIPE_PROF(it, 1, lane == 0);
-      issue_load(it);
-      zero_fill(it);
-      PIPE_PROF(it, 2, lane == 0);
-    }
-    if (!shook) { cluster.barrier_wait(); shook = true; }
-    for (int it = n_first; it < n_items; ++it) {
+    // row of item `it` in the static prefix (round 0 only)
+    auto static_row = [&](int it) { const int r = cid + it * n_clusters; return r < p.rows ? r : kPipeEndDone; };
+    const int n_static = round == 0 ? NB : 0;
+    int row = n_static > 0 ? static_row(0) : 0;             // (dynamic first item: drawn below)
+    bool have_row = n_static > 0;
+    for (int it = 0;; ++it) {
+      const int slot = it % kPipeRowRing;
+      if (!have_row) {                                        // first item of a later round: nothing was prefetched
+        if (crank == 0) {
+          int t = 0;
+          if (lane == 0) {
+            t = static_cast<int>(atomicAdd(p.sched, 1u)) + static_rows;
+            t = t < p.rows ? t : kPipeEndDone;
+            for (int r = 1; r < C; ++r) st_async_remote_v2(&sh.row_in[0], static_cast<uint32_t>(t), 0u, &sh.rowbar[0], r);
+          }
+          row = __shfl_sync(0xffffffffu, t, 0);
+        } else {
+          if (lane == 0) { mbar_expect_tx(&sh.rowbar[0], 8u); mbar_wait_cluster(&sh.rowbar[0], 0u); }
+          __syncwarp();
+          row = static_cast<int>(*reinterpret_cast<volatile uint32_t*>(&sh.row_in[0].x));
+        }
+        have_row = true;
+      }
+      if (row < 0) {
+        // no more items: tell each group (its next NG item slots), in item order
+        if (lane == 0) {
+          sh.end_reason = row;
+          for (int j = 0; j < NG; ++j) {
+            const int e = it + j;
+            if (e >= NG) mbar_wait(&sh.taken[e % NG], (static_cast<uint32_t>(e / NG) - 1) & 1);
+            sh.item_row[e % kPipeRowRing] = make_uint2(static_cast<uint32_t>(row), 0u);
+            mbar_arrive_local(&sh.full[e % NG]);
+          }
+        }
+        break;
+      }
       PIPE_PROF(it, 0, lane == 0);
-      mbar_wait(&sh.empty[it % NB], (static_cast<uint32_t>(it / NB) - 1) & 1);   // the re-scan of item it - NB is done
+      if (it >= NB) mbar_wait(&sh.empty[it % NB], (static_cast<uint32_t>(it / NB) - 1) & 1);   // the re-scan of item it - NB is done
       if (it >= NG) mbar_wait(&sh.taken[it % NG], (static_cast<uint32_t>(it / NG) - 1) & 1);   // its group saw item it - NG
       PIPE_PROF(it, 1, lane == 0);
-      issue_load(it);
-      zero_fill(it);
+      if (lane == 0) sh.item_row[slot] = make_uint2(static_cast<uint32_t>(row), 0u);          // (released by the arrive on full[g])
+      issue_load(it, row);
+      // draw the next item's row while this item's zeros are written
+      const int nd = it + 1 - n_static;                      // dynamic index of the next item: landing slot and phase
+      const int nslot = nd % kPipeRowRing;
+      const uint32_t nphase = static_cast<uint32_t>(nd / kPipeRowRing) & 1u;
+      int next = 0;
+      const bool next_static = it + 1 < n_static;
+      if (next_static) next = static_row(it + 1);
+      else if (crank == 0 && lane == 0) {
+        if (sh.n_fail >= kPipeMaxFail - kPipeFailSlack) next = kPipeEndPause;
+        else {
+          next = static_cast<int>(atomicAdd(p.sched, 1u)) + static_rows;
+          next = next < p.rows ? next : kPipeEndDone;
+        }
+      }
+      zero_fill(it, row);
+      if (!next_static) {
+        if (crank == 0) {
+          if (C > 1) {
+            if (!shook) { cluster.barrier_wait(); shook = true; }
+            if (lane == 0)
+              for (int r = 1; r < C; ++r) st_async_remote_v2(&sh.row_in[nslot], static_cast<uint32_t>(next), 0u, &sh.rowbar[nslot], r);
+          }
+          next = __shfl_sync(0xffffffffu, next, 0);
+        } else {
+          if (lane == 0) { mbar_expect_tx(&sh.rowbar[nslot], 8u); mbar_wait_cluster(&sh.rowbar[nslot], nphase); }
+          __syncwarp();
+          next = static_cast<int>(*reinterpret_cast<volatile uint32_t*>(&sh.row_in[nslot].x));
+        }
+      }
       PIPE_PROF(it, 2, lane == 0);
+      row = next;
     }
   } else {
   // =============================================================================== compute groups
@@ -211,17 +287,18 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
   const int cap = CAP / C;
   const int vpt = (n_vec + GT - 1) / GT;
 
-  for (int it = g; it < n_items; it += NG) {
+  for (int it = g;; it += NG) {
     const uint32_t use = static_cast<uint32_t>(it / NG);      // how often this group's scratch / xbar have been used
     const int par = use & 1;
     const int buf = it % NB;
     const uint4* s4 = reinterpret_cast<const uint4*>(smem_raw + static_cast<size_t>(buf) * p.slice_smem_bytes);
-    const int row = cid + it * n_clusters;
-    float* orow = want_probs ? p.probs + static_cast<long long>(row) * p.ld_out : nullptr;
 
     // ---- pass 1: thread maxima (NaN-propagating)
     PIPE_PROF(it, 3, gt == 0);
     mbar_wait(&sh.full[g], use & 1);
+    const int row = static_cast<int>(*reinterpret_cast<volatile uint32_t*>(&sh.item_row[it % kPipeRowRing].x));
+    if (row < 0) break;                                       // no more items (every group gets its own end marker)
+    float* orow = want_probs ? p.probs + static_cast<long long>(row) * p.ld_out : nullptr;
     PIPE_PROF(it, 4, gt == 0);
     // Per thread: the three largest VECTOR maxima (tmax >= m2 >= m3) and the rounds i1, i2 of the first two — the
     // re-scan below then only has to touch vectors i1 / i2 of a thread unless its third vector also reaches the pivot.
@@ -428,7 +505,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     }
     ok &= n_tot >= k_eff;
     if (!ok) {                               // (keys written above are simply discarded)
-      if (gt == 0) atomicOr(&sh.fail_bits[it >> 5], 1u << (it & 31));   // same decision in every CTA of the cluster
+      if (gt == 0) sh.fail_rows[atomicAdd(&sh.n_fail, 1)] = row;        // same decision in every CTA of the cluster
       named_bar(bar_id, GT);
       continue;
     }
@@ -586,28 +663,47 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
   }
   }  // compute groups
 
-  // =============================================================================== drained: general path for failed items
-  pdl_launch_dependents();                             // the next kernel may start occupying freed SMs
-  if (!shook) cluster.barrier_wait();
+  // =============================================================================== drained: general path for deferred rows
+  if (!shook) { cluster.barrier_wait(); shook = true; }
   __syncthreads();
-  if (p.prof != nullptr && tid == 0) {
+  const int reason = sh.end_reason;
+  if (reason == kPipeEndDone) pdl_launch_dependents();   // the next kernel may start occupying freed SMs
+  if (round == 0 && p.prof != nullptr && tid == 0) {
     unsigned long long gt1;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + 1) * 16 + 15] = clock64();
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + 3) * 16 + 15] = static_cast<long long>(gt1);
   }
-  bool any = false;
-  for (int i = 0; i < (n_items + 31) / 32; ++i) any |= sh.fail_bits[i] != 0u;
-  if (any) {                                  // uniform across the cluster (every CTA recorded the same items)
-    if (C > 1) cluster.sync();                // peers have drained too: their shared memory may be re-purposed
+  const int n_fail = sh.n_fail;                 // identical in every CTA of the cluster (same rows, same decisions) ...
+  if (n_fail > 0) {
+    // ... but appended in racing order: sort, so that the CTAs of a cluster walk the rows in lock step
+    int mine = 0, rank = 0;
+    if (tid < n_fail) {
+      mine = sh.fail_rows[tid];
+      for (int j = 0; j < n_fail; ++j) rank += sh.fail_rows[j] < mine ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid < n_fail) sh.fail_rows[rank] = mine;
+    __syncthreads();
+    if (C > 1) cluster.sync();                  // peers have drained too: their shared memory may be re-purposed
     NormParams p2 = p;
     p2.force_general = 1;
     p2.prof = nullptr;
-    for (int it = 0; it < n_items; ++it) {
-      if ((sh.fail_bits[it >> 5] >> (it & 31)) & 1u) {
-        norm_row<T, 32 + NG * kPipeGroupThreads>(p2, cid + it * n_clusters);
-        __syncthreads();
-      }
+    for (int i = 0; i < n_fail; ++i) {
+      norm_row<T, 32 + NG * kPipeGroupThreads>(p2, sh.fail_rows[i]);
+      __syncthreads();
+    }
+  }
+  if (reason == kPipeEndDone) break;
+  }  // rounds
+
+  // the last cluster to finish re-arms the row counter for the next launch that uses this scheduler block
+  if (crank == 0 && tid == 0) {
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1u) == static_cast<unsigned>(n_clusters) - 1u) {
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+      __threadfence();
     }
   }
 }
@@ -616,7 +712,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
 // The kernel variants that are compiled: (compute groups, slice buffers, merged-candidate capacity)
 struct PipeVariant { int ng, nb, cap; size_t fixed, mask_off, row_need; };
 #define SD_PIPE_VARIANT(NG, NB, CAP) \
-  {NG, NB, CAP, sizeof(PipeShared<NG, NB, CAP>), offsetof(PipeSharedAlias##NG##NB##CAP, fail_bits), sizeof(NormShared<32 + NG * kPipeGroupThreads>)}
+  {NG, NB, CAP, sizeof(PipeShared<NG, NB, CAP>), offsetof(PipeSharedAlias##NG##NB##CAP, n_fail), sizeof(NormShared<32 + NG * kPipeGroupThreads>)}
 using PipeSharedAlias43128 = PipeShared<4, 3, 128>;
 using PipeSharedAlias33256 = PipeShared<3, 3, 256>;
 using PipeSharedAlias32128 = PipeShared<3, 2, 128>;
@@ -689,6 +785,7 @@ static PipePlan g_plans[32];
 static int g_n_plans = 0;
 
 bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
+  if (p.sched == nullptr) return false;
   const size_t es = dtype == kF32 ? 4 : 2;
   if (p.top_k <= 0 || p.top_k > kPipeFastK || p.force_general || rows < 2) return false;
   const long long row_bytes = p.V * static_cast<long long>(es);
@@ -734,7 +831,6 @@ bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
   const int C = plan->cluster;
   const long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
   const int n_clusters = plan->max_clusters < rows ? plan->max_clusters : rows;
-  if ((rows + n_clusters - 1) / n_clusters > kPipeMaxItems) return false;
   p.cluster = C;
   p.slice_elems = static_cast<int>(slice);
   p.slice_smem_bytes = static_cast<int>((static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127));

@@ -25,6 +25,7 @@ struct NormParams {
   int no_pipeline;                         // use the one-cluster-per-row kernel even where the persistent one applies
   long long* prof;                         // debug: per-CTA clock64 timestamps (16 slots per CTA), nullable
   int rows;                                // number of logits rows
+  unsigned int* sched;                     // pipelined kernel: {next row ticket, finished clusters}; zero between launches
   int pipe_groups;                         // persistent kernel: compute groups (= slice buffers) per CTA
   int pipe_buffers, pipe_cap, pipe_clusters;             // ... merged-candidate capacity, clusters in the persistent grid
   const int* row_filter;                   // norm_probs_kernel: process only rows with row_filter[row] != 0

@@ -32,13 +32,19 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class ErrFlag:
-    """Device int32 word the kernels OR error bits into."""
+    """Device int32 word the kernels OR error bits into, plus the norm kernels' scheduler workspace
+    (SD_NORM_WORKSPACE_BYTES, include/specdec_b200.h).  One object serves launches that are ordered after one another
+    (one stream, one CUDA graph); launches that may run concurrently need their own."""
 
     def __init__(self, device):
         self.t = torch.zeros(1, dtype=torch.int32, device=device)
+        self.ws = torch.zeros(4, dtype=torch.int32, device=device)
 
     def ptr(self) -> int:
         return self.t.data_ptr()
+
+    def ws_ptr(self) -> int:
+        return self.ws.data_ptr()
 
     def check(self) -> None:
         """Synchronising read; raises the reference's exceptions and clears the flag."""
@@ -61,6 +67,23 @@ def default_flag(device) -> ErrFlag:
     if key not in _flags:
         _flags[key] = ErrFlag(torch.device("cuda", key))
     return _flags[key]
+
+
+_workspaces = {}
+
+
+def _default_workspace(device) -> int:
+    """Scheduler workspace of the calling stream (launches on different streams may overlap, so each stream gets its
+    own).  None can be created while the stream is capturing: 0 (NULL) then selects the one-cluster-per-row kernel —
+    pass an ErrFlag made before the capture to get the persistent kernel inside a graph."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream())
+    ws = _workspaces.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return 0
+        ws = _workspaces[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+    return ws.data_ptr()
 
 
 NORM_NO_PIPELINE, NORM_FORCE_GENERAL = 1, 2
@@ -124,13 +147,14 @@ def norm_probs(logits: torch.Tensor, temperature: float, top_k: int, top_p: floa
     if out is None:
         out = torch.empty(rows, V, dtype=torch.float32, device=x.device)
     assert out.dtype == torch.float32 and out.shape == (rows, V) and out.stride(1) == 1
+    ws = err.ws_ptr() if err is not None else _default_workspace(x.device)
     err = err or default_flag(x.device)
     lib = _cabi.load()
     k = int(top_k) if top_k else 0
     p = float(top_p) if top_p else 0.0
     flags = (NORM_FORCE_GENERAL if general else 0) | (0 if pipeline else NORM_NO_PIPELINE)
     rc = lib.sd_norm_probs(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), k, p,
-                           out.data_ptr(), out.stride(0), _cref(compact), err.ptr(), flags, _stream())
+                           out.data_ptr(), out.stride(0), _cref(compact), err.ptr(), flags, ws, _stream())
     _cabi.check(rc, "sd_norm_probs")
     return out
 
@@ -149,12 +173,13 @@ def norm_sample(logits: torch.Tensor, temperature: float, top_k: int, top_p: flo
     assert tok_out.dtype == torch.int64 and tok_out.numel() == rows and tok_out.is_contiguous()
     if probs_out is not None:
         assert probs_out.dtype == torch.float32 and probs_out.shape == (rows, V) and probs_out.stride(1) == 1
+    ws = err.ws_ptr() if err is not None else _default_workspace(x.device)
     err = err or default_flag(x.device)
     flags = (NORM_FORCE_GENERAL if general else 0) | (0 if pipeline else NORM_NO_PIPELINE)
     rc = _cabi.load().sd_norm_sample(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature),
                                      int(top_k or 0), float(top_p or 0.0), _ptr(probs_out),
                                      probs_out.stride(0) if probs_out is not None else V, u.data_ptr(),
-                                     tok_out.data_ptr(), _cref(compact), err.ptr(), flags, _stream())
+                                     tok_out.data_ptr(), _cref(compact), err.ptr(), flags, ws, _stream())
     _cabi.check(rc, "sd_norm_sample")
     return tok_out
 

@@ -180,6 +180,31 @@ def test_pipeline_kernel_many_rows_with_sampling(cuda_lib, V, dtype, rows):
     assert compare_probs(pa[sel], want, "pipeline vs oracle") == 0
 
 
+@pytest.mark.parametrize("V,rows,n_tied", [(4096, 9000, 3), (32000, 2400, 40), (2048, 40000, 40000), (4096, 30000, 15000)])
+def test_pipeline_kernel_dynamic_rows_and_deferred_rows(cuda_lib, V, rows, n_tied):
+    """Rows are handed to the clusters through a ticket counter (tens of items per cluster: the row-index ring wraps), and
+    rows the candidate path cannot serve (all ties) are deferred to the general path in bounded batches — with tens of
+    thousands of them every cluster pauses, drains its list and resumes several times.  Two launches back to back check
+    that the counter is re-armed."""
+    from llmspeculativesampling_b200 import ops
+    x = make_logits(rows, V, 3.8, seed=rows, dtype=torch.float32).cuda()
+    g = torch.Generator().manual_seed(3)
+    tied = torch.randperm(rows, generator=g)[:n_tied].cuda()
+    x[tied] = 0.25
+    u = torch.rand(rows, generator=g).cuda()
+    pa = torch.empty(rows, V, device="cuda"); pb = torch.empty(rows, V, device="cuda")
+    tb = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pb, pipeline=False)
+    for _ in range(2):
+        pa.fill_(-1.0)
+        ta = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pa, pipeline=True)
+        ops.default_flag("cuda").check()
+        assert torch.equal(pa, pb), "pipelined and classic kernels must agree bit for bit"
+        assert torch.equal(ta, tb)
+    sel = [0, int(tied[0]), rows // 2, rows - 1]
+    want = oracle_probs(x[sel].cpu(), 0.8, 20, 0.9)
+    assert compare_probs(pa[sel], want, "pipeline vs oracle") == 0
+
+
 def test_fuzz_shapes_parameters_and_ties_against_oracle(cuda_lib):
     """Randomised sweep (fixed seed) over V, rows, dtype, T, top_k, top_p, tie density, -inf masks and row strides, on
     every kernel path; probabilities must match the oracle and the support must be identical."""
