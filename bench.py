@@ -350,6 +350,23 @@ def main():
     n1.record()
     torch.cuda.synchronize()
     norm_ms = n0.elapsed_time(n1) / (reps * n_sets)
+    # the verify kernel alone, same way (its inputs are the probabilities / lists the norm launches above left behind)
+    with torch.cuda.stream(side):
+        g_ver = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_ver, stream=side):
+            for i in range(n_sets):
+                ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
+                           next_tok=next_tok, err=err, p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        g_ver.replay()
+    torch.cuda.synchronize()
+    n0.record()
+    for _ in range(reps):
+        g_ver.replay()
+    n1.record()
+    torch.cuda.synchronize()
+    verify_ms = n0.elapsed_time(n1) / (reps * n_sets)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(min(args.steps, 200))]
     for s in range(len(ev)):
         i = s % n_sets
@@ -446,6 +463,7 @@ def main():
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "timing": "CUDA events around back-to-back graph replays of the norm launch (4 rotating input sets)",
                      "kernel_ms_eager_with_events": {"norm": t_norm, "verify": t_verify},
+                     "kernel_ms_graph_back_to_back": {"norm": norm_ms, "verify": verify_ms},
                      "norm_share_of_step": t_norm / (t_norm + t_verify)},
     }
     if not args.no_cpu_baseline:

@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     sh.end_reason = kPipeEndDone;
     fence_barrier_init();
   }
+  // later rounds: the general path just used this shared memory through the generic proxy; order those accesses
+  // before the TMA (async proxy) writes of the new round
+  if (round > 0) fence_proxy_async();
   __syncthreads();
   if (round == 0) {
     pdl_wait();                                        // everything above overlapped the previous kernel's tail

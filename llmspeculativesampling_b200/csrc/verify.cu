@@ -174,12 +174,12 @@ __global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParam
 constexpr int kSparseThreads = 128;
 constexpr int kSparseCap = 64;
 
-__device__ __forceinline__ void verify_commit(const VerifyParams& p, int b, int n_acc, long long out) {
+__device__ __forceinline__ void verify_commit(const VerifyParams& p, int b, int n_acc, long long out, int L_pre = -1) {
   p.next_tok[b] = out;
   if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc;
   if (p.stats != nullptr) { atomicAdd(&p.stats[0], static_cast<unsigned long long>(n_acc)); atomicAdd(&p.stats[1], 1ull); }
   if (p.tokens != nullptr) {
-    const int L = p.seq_len[b];
+    const int L = L_pre >= 0 ? L_pre : p.seq_len[b];
     p.tokens[b * p.tokens_stride + L + n_acc] = out;
     p.seq_len[b] = L + n_acc + 1;
   }
@@ -197,14 +197,26 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
   __shared__ unsigned long long e_w[kSparseCap];
   const int b = blockIdx.x;
   pdl_wait();
+  pdl_launch_dependents();                                    // the next kernel's prologue may overlap this (short) kernel
   if (p.active != nullptr && p.active[b] == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = static_cast<int>(p.V), gamma = p.gamma;
   const int n_pre_p = min(gamma + 1, kPre), n_pre_q = min(gamma, kPre);
 
-  if (warp > 0) {
-    // warps 1..3: while warp 0 chases token -> p[token], q[token], pull the (tiny) compact lists of every row that
-    // could become the residual row into shared memory — the dependent chain of global loads shrinks to two
+  // warp 0: everything the accept scan needs that does not depend on another load is requested up front
+  long long tok = 0;
+  float u_a = 0.f, u_f = 0.f;
+  int L_pre = -1;
+  if (warp == 0) {
+    if (p.tokens != nullptr) L_pre = p.seq_len[b];
+    if (lane < gamma) {
+      tok = p.draft[b * p.draft_stride + lane];
+      u_a = p.u_acc[b * p.u_acc_stride + lane];
+    }
+    u_f = p.u_final[b];
+  } else {
+    // warps 1..3 pull the (tiny) compact lists of every row into shared memory: p[token] / q[token] of the accept
+    // scan and the residual row are then looked up there — no dependent chain of global loads
     for (int i = tid - 32; i < (n_pre_p + n_pre_q) * kSparseCap; i += kSparseThreads - 32) {
       const int rr = i / kSparseCap, j = i - rr * kSparseCap;
       if (rr < n_pre_p) {
@@ -219,23 +231,33 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
       }
     }
   }
+  __syncthreads();                                            // lists are in shared memory  
   int n_acc_w0 = 0;
   bool tie_w0 = false;
   if (warp == 0) {
-    // ---- accept scan (dense gathers of single elements, as in verify_kernel)
+    // ---- accept scan: p[token], q[token] from the compact lists (an index that is not listed has probability 0);
+    //      rows without a list (count -1 / too long) gather the single elements from the dense rows
     bool acc = true, tie = false;
     float ratio = 0.f;
     if (lane < gamma) {
-      long long tok = p.draft[b * p.draft_stride + lane];
       if (tok < 0 || tok >= V) { atomicOr(p.err_flag, kErrBadToken); tok = 0; }
-      const float pv = p.p[b * p.p_req_stride + lane * p.p_row_stride + tok];
-      const float qv = p.q[b * p.q_req_stride + lane * p.q_row_stride + tok];
+      float pv = 0.f, qv = 0.f;
+      const int cpl = lane < kPre ? p_cnt_pre[lane] : -1, cql = lane < kPre ? q_cnt_pre[lane] : -1;
+      if (cpl >= 0 && cpl <= kSparseCap && cpl <= p.pc.cap) {
+        for (int t = 0; t < cpl; ++t) pv = static_cast<long long>(p_pre[lane][t].x) == tok ? __uint_as_float(p_pre[lane][t].y) : pv;
+      } else {
+        pv = p.p[b * p.p_req_stride + lane * p.p_row_stride + tok];
+      }
+      if (cql >= 0 && cql <= kSparseCap && cql <= p.qc.cap) {
+        for (int t = 0; t < cql; ++t) qv = static_cast<long long>(q_pre[lane][t].x) == tok ? __uint_as_float(q_pre[lane][t].y) : qv;
+      } else {
+        qv = p.q[b * p.q_req_stride + lane * p.q_row_stride + tok];
+      }
       if (qv == 0.f) atomicOr(p.err_flag, kErrZeroQ);
       ratio = __fdiv_rn(pv, qv);
-      const float u = p.u_acc[b * p.u_acc_stride + lane];
       const float thr = p.strict ? fminf(1.0f, ratio) : ratio;
-      acc = p.strict ? (u < thr) : !(u > thr);
-      tie = (u == thr);
+      acc = p.strict ? (u_a < thr) : !(u_a > thr);
+      tie = (u_a == thr);
       if (p.ratios != nullptr) p.ratios[b * gamma + lane] = ratio;
     }
     const unsigned rej = __ballot_sync(0xffffffffu, !acc);
@@ -243,7 +265,6 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
     tie_w0 = tie && lane < gamma && lane <= n_acc_w0;
     if (p.tie_count != nullptr && tie_w0) atomicAdd(p.tie_count, 1);
   }
-  __syncthreads();                                            // lists are in shared memory
   if (warp == 0) {
     const int n_acc = n_acc_w0;
     bool use_q = n_acc < gamma;
@@ -302,7 +323,7 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
         }
         tot = warp_sum(tot);
         __syncwarp();
-        const unsigned long long target = scale_target(tot, u_to_int(p.u_final[b]));
+        const unsigned long long target = scale_target(tot, u_to_int(u_f));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           unsigned long long before = 0ull;
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
           if (w[h] > 0ull && target >= before && target < before + w[h]) {
             float guard_val = r[h];
             if (use_q) guard_val = __fdiv_rn(r[h], ldexpf(__ull2float_rn(tot), e - kScaleBits) + 1e-6f);
-            verify_commit(p, b, n_acc, guard_val < kProbGuard ? argmax : id[h]);
+            verify_commit(p, b, n_acc, guard_val < kProbGuard ? argmax : id[h], L_pre);
           }
         }
         break;
@@ -365,11 +386,11 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
   const int argmax = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffu));
   unsigned long long total = 0ull;
   float psel = 1.f;
-  const int tok = cluster_icdf<4, kSparseThreads>(cx, n_vec, 0, rmax, p.u_final[b], vecw, &total, &psel);
-  if (tok >= 0) {
+  const int tok_d = cluster_icdf<4, kSparseThreads>(cx, n_vec, 0, rmax, p.u_final[b], vecw, &total, &psel);
+  if (tok_d >= 0) {
     float guard_val = psel;
     if (use_q) guard_val = __fdiv_rn(psel, ldexpf(__ull2float_rn(total), frexp_exp(rmax) - kScaleBits) + 1e-6f);
-    verify_commit(p, b, n_acc, guard_val < kProbGuard ? argmax : tok);
+    verify_commit(p, b, n_acc, guard_val < kProbGuard ? argmax : tok_d);
   }
 }
 
