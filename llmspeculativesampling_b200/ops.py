@@ -36,9 +36,10 @@ class ErrFlag:
     (SD_NORM_WORKSPACE_BYTES, include/specdec_b200.h).  One object serves launches that are ordered after one another
     (one stream, one CUDA graph); launches that may run concurrently need their own."""
 
-    def __init__(self, device):
+    def __init__(self, device, shared: bool = False):
         self.t = torch.zeros(1, dtype=torch.int32, device=device)
         self.ws = torch.zeros(4, dtype=torch.int32, device=device)
+        self.shared = shared          # per-device default flag: any stream may use it, so its workspace is not used
 
     def ptr(self) -> int:
         return self.t.data_ptr()
@@ -65,7 +66,7 @@ _flags = {}
 def default_flag(device) -> ErrFlag:
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     if key not in _flags:
-        _flags[key] = ErrFlag(torch.device("cuda", key))
+        _flags[key] = ErrFlag(torch.device("cuda", key), shared=True)
     return _flags[key]
 
 
@@ -147,7 +148,7 @@ def norm_probs(logits: torch.Tensor, temperature: float, top_k: int, top_p: floa
     if out is None:
         out = torch.empty(rows, V, dtype=torch.float32, device=x.device)
     assert out.dtype == torch.float32 and out.shape == (rows, V) and out.stride(1) == 1
-    ws = err.ws_ptr() if err is not None else _default_workspace(x.device)
+    ws = err.ws_ptr() if (err is not None and not err.shared) else _default_workspace(x.device)
     err = err or default_flag(x.device)
     lib = _cabi.load()
     k = int(top_k) if top_k else 0
@@ -173,7 +174,7 @@ def norm_sample(logits: torch.Tensor, temperature: float, top_k: int, top_p: flo
     assert tok_out.dtype == torch.int64 and tok_out.numel() == rows and tok_out.is_contiguous()
     if probs_out is not None:
         assert probs_out.dtype == torch.float32 and probs_out.shape == (rows, V) and probs_out.stride(1) == 1
-    ws = err.ws_ptr() if err is not None else _default_workspace(x.device)
+    ws = err.ws_ptr() if (err is not None and not err.shared) else _default_workspace(x.device)
     err = err or default_flag(x.device)
     flags = (NORM_FORCE_GENERAL if general else 0) | (0 if pipeline else NORM_NO_PIPELINE)
     rc = _cabi.load().sd_norm_sample(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature),
