@@ -423,31 +423,47 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
 #pragma unroll
     for (int w = 1; w < W; ++w) lmax = fmaxf(lmax, sh.rs.wf[w]);
     const float Mc = temp == 1.0f ? lmax : __fdiv_rn(lmax, temp);        // -inf for an empty / fully masked slice
+    const bool do_sample = p.u != nullptr && p.u[row] >= 0.f;              // row-uniform
     float acc = 0.f;
-    if (Mc > -INFINITY)
-      for_each_elem<T, THREADS>(slice, n_vec, start, tid, [&](float l, int) { acc += exp2f((xof(l) - Mc) * kLog2e); });
+    int amin = 0x7fffffff;                                                // first index holding this CTA's maximum
+    if (Mc > -INFINITY) {
+      if (do_sample)
+        for_each_elem<T, THREADS>(slice, n_vec, start, tid, [&](float l, int g) {
+          acc += exp2f((xof(l) - Mc) * kLog2e);
+          if (l == lmax && g < V) amin = min(amin, g); });
+      else
+        for_each_elem<T, THREADS>(slice, n_vec, start, tid, [&](float l, int) { acc += exp2f((xof(l) - Mc) * kLog2e); });
+    }
     double lsum = warp_sum(static_cast<double>(acc));                     // padding is -inf -> contributes 0
-    if (lane == 0) sh.rs.wd[warp] = lsum;
+    if (do_sample) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+    }
+    if (lane == 0) { sh.rs.wd[warp] = lsum; sh.rs.wi[warp] = amin; }
     __syncthreads();
     if (tid == 0) {
       double a = 0.0;
-      for (int w = 0; w < W; ++w) a += sh.rs.wd[w];
+      int am = 0x7fffffff;
+      for (int w = 0; w < W; ++w) { a += sh.rs.wd[w]; am = min(am, sh.rs.wi[w]); }
       sh.rs.xf[cx.parity][0] = lmax;
       sh.rs.xd[cx.parity] = a;
+      sh.rs.xi[cx.parity][0] = am;
     }
     cx.xchg_sync();
     float Ml = -INFINITY;
     for (int r = 0; r < C; ++r) Ml = fmaxf(Ml, cx.peer(r)->xf[cx.parity][0]);
     const float M = temp == 1.0f ? Ml : __fdiv_rn(Ml, temp);
     double z = 0.0;
+    int argmax = 0x7fffffff;                                              // first index holding the ROW maximum
     for (int r = 0; r < C; ++r) {
       const float mr_l = cx.peer(r)->xf[cx.parity][0];
       const float mr = temp == 1.0f ? mr_l : __fdiv_rn(mr_l, temp);
       if (mr > -INFINITY) z += cx.peer(r)->xd[cx.parity] * static_cast<double>(exp2f((mr - M) * kLog2e));
+      if (mr_l == Ml) argmax = min(argmax, cx.peer(r)->xi[cx.parity][0]);
     }
     cx.parity ^= 1;
     bool pending_wait = false;
-    if (C > 1 && p.u == nullptr) { cx.cluster.barrier_arrive(); pending_wait = true; }   // done with peers' memory
+    if (C > 1 && !do_sample) { cx.cluster.barrier_arrive(); pending_wait = true; }   // done with peers' memory
     const float logz = logf(static_cast<float>(z));
     if (!(z > 0.0) || isinf(logz) || logz != logz) atomicOr(p.err_flag, kErrNanLogit);
     const float c2 = -logz * kLog2e;
@@ -458,28 +474,47 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
       for (int j = 0; j < PV; ++j) pr[j] = exp2f(fmaf(xof(o[j]) - M, kLog2e, c2));   // exp((x - M) - logZ), utils.py:199
     };
     SD_PROF(8);
-    if (want_probs) {
-      float* o = orow + start;
-      const int nfull = p.vec_out ? n / PV : 0;
-      for (int v = tid; v < nfull; v += THREADS) {
+    if (!do_sample) {
+      if (want_probs) {
+        float* o = orow + start;
+        const int nfull = p.vec_out ? n / PV : 0;
+        for (int v = tid; v < nfull; v += THREADS) {
+          float pr[PV];
+          vec_probs(v, pr);
+#pragma unroll
+          for (int j = 0; j < PV; j += 4) st_cs_v4(o + v * PV + j, pr[j], pr[j + 1], pr[j + 2], pr[j + 3]);
+        }
+        for (int v = nfull + tid; v < n_vec; v += THREADS) {
+          float pr[PV];
+          vec_probs(v, pr);
+          for (int j = 0; j < PV; ++j) if (v * PV + j < n) o[v * PV + j] = pr[j];
+        }
+      }
+    } else {
+      // write pass and the sampler's weight sums in one sweep, in the sampler's segment order (one contiguous segment of
+      // vectors per warp, lanes strided: still 512 contiguous bytes per warp store)
+      const float pmax = exp2f(c2);
+      const int e = frexp_exp(pmax);
+      const int vpw = (n_vec + W - 1) / W;
+      const int v_begin = warp * vpw, v_end = min(n_vec, v_begin + vpw);
+      const int nfull = (want_probs && p.vec_out) ? n / PV : 0;
+      float* o = want_probs ? orow + start : nullptr;
+      unsigned long long lane_w = 0ull;
+      for (int v = v_begin + lane; v < v_end; v += 32) {
         float pr[PV];
         vec_probs(v, pr);
 #pragma unroll
-        for (int j = 0; j < PV; j += 4) st_cs_v4(o + v * PV + j, pr[j], pr[j + 1], pr[j + 2], pr[j + 3]);
+        for (int j = 0; j < PV; ++j) lane_w += weight_of(pr[j], e);
+        if (v < nfull) {
+#pragma unroll
+          for (int j = 0; j < PV; j += 4) st_cs_v4(o + v * PV + j, pr[j], pr[j + 1], pr[j + 2], pr[j + 3]);
+        } else if (want_probs) {
+          for (int j = 0; j < PV; ++j) if (v * PV + j < n) o[v * PV + j] = pr[j];
+        }
       }
-      for (int v = nfull + tid; v < n_vec; v += THREADS) {
-        float pr[PV];
-        vec_probs(v, pr);
-        for (int j = 0; j < PV; ++j) if (v * PV + j < n) o[v * PV + j] = pr[j];
-      }
-    }
-    if (p.u != nullptr && p.u[row] >= 0.f) {
-      int amin = 0x7fffffff;
-      for_each_elem<T, THREADS>(slice, n_vec, start, tid, [&](float l, int g) { if (l == Ml && g < V) amin = min(amin, g); });
-      const int argmax = cx.allreduce_min(amin);
       unsigned long long total = 0ull;
       float psel = 1.f;
-      const int tok = cluster_icdf<PV, THREADS>(cx, n_vec, start, exp2f(c2), p.u[row], vec_probs, &total, &psel);
+      const int tok = cluster_icdf<PV, THREADS>(cx, n_vec, start, pmax, p.u[row], vec_probs, &total, &psel, &lane_w);
       if (total == 0ull) {
         if (tid == 0 && cx.crank == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
       } else if (tok >= 0) {

@@ -238,17 +238,22 @@ __device__ uint32_t search16(RowCtx<THREADS>& cx, uint32_t lo, int top_bit, Each
 // `total_out` receives the cluster-wide weight total (0 => nothing to sample from).
 template <int PV, int THREADS, class VecProbs>
 __device__ int cluster_icdf(RowCtx<THREADS>& cx, int n_vec, long long slice_start, float pmax, float u,
-                            VecProbs vec_probs, unsigned long long* total_out, float* prob_out) {
+                            VecProbs vec_probs, unsigned long long* total_out, float* prob_out,
+                            const unsigned long long* lane_weights = nullptr) {
   constexpr int W = THREADS / 32;
   const int e = frexp_exp(pmax);
   const int vpw = (n_vec + W - 1) / W;                       // vectors per warp segment
   const int v_begin = cx.warp * vpw, v_end = min(n_vec, v_begin + vpw);
   unsigned long long mine = 0ull;
-  for (int v = v_begin + cx.lane; v < v_end; v += 32) {
-    float pr[PV];
-    vec_probs(v, pr);
+  if (lane_weights != nullptr) {
+    mine = *lane_weights;          // caller already summed weight_of(p, e) over this lane's vectors of this warp's segment
+  } else {
+    for (int v = v_begin + cx.lane; v < v_end; v += 32) {
+      float pr[PV];
+      vec_probs(v, pr);
 #pragma unroll
-    for (int j = 0; j < PV; ++j) mine += weight_of(pr[j], e);
+      for (int j = 0; j < PV; ++j) mine += weight_of(pr[j], e);
+    }
   }
   mine = warp_sum(mine);
   if (cx.lane == 0) cx.s->wu[cx.warp] = mine;

@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--prof", action="store_true")
     ap.add_argument("--scale", type=float, default=3.8, help="standard deviation of the synthetic logits")
     ap.add_argument("--classic", action="store_true")
+    ap.add_argument("--sample", action="store_true", help="time sd_norm_sample (one token per row) instead of sd_norm_probs")
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--k", type=int, default=-1, help="override the mode's top_k")
     ap.add_argument("--p", type=float, default=-1.0, help="override the mode's top_p")
@@ -76,17 +77,20 @@ def main():
         name, T, k, p = modes_all[a.mode]
         k = a.k if a.k >= 0 else k
         p = a.p if a.p >= 0 else p
-        ms, gbs = time_norm(a.rows, a.V, dt, T, k, p, iters=a.iters)
-        print(json.dumps(dict(kernel="norm", mode=name, rows=a.rows, V=a.V, dtype=a.dtype, ms=round(ms, 4), GBs=round(gbs, 1))))
+        ms, gbs = time_norm(a.rows, a.V, dt, T, k, p, iters=a.iters, sample=a.sample)
+        print(json.dumps(dict(kernel="norm_sample" if a.sample else "norm", mode=name, rows=a.rows, V=a.V, dtype=a.dtype, ms=round(ms, 4), GBs=round(gbs, 1))))
         if a.prof:
             from llmspeculativesampling_b200 import _cabi
             buf = torch.zeros(a.rows * 8 + 8192, 16, dtype=torch.int64, device="cuda")
             x = (torch.randn(a.rows, a.V, device="cuda") * SCALE).to(dt)
             out = torch.empty(a.rows, a.V, device="cuda")
-            ops.norm_probs(x, T, k, p, out=out, pipeline=PIPELINE)
+            uu = torch.rand(a.rows, device="cuda")
+            call = (lambda: ops.norm_sample(x, T, k, p, uu, probs_out=out, pipeline=PIPELINE)) if a.sample else \
+                   (lambda: ops.norm_probs(x, T, k, p, out=out, pipeline=PIPELINE))
+            call()
             torch.cuda.synchronize()
             _cabi.load().sd_debug_set_prof(buf.data_ptr())
-            ops.norm_probs(x, T, k, p, out=out, pipeline=PIPELINE)
+            call()
             torch.cuda.synchronize()
             _cabi.load().sd_debug_set_prof(None)
             b = buf.cpu()
