@@ -147,6 +147,34 @@ int sd_verify(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, 
               int64_t p_cmp_req_stride, const sd_compact_t* q_compact, int64_t q_cmp_req_stride, uint64_t* stats,
               int* err_flag, void* stream);
 
+/* Kernels 1 + 2 in ONE launch.  The arguments of sd_verify as a struct, then: sd_norm_sample over `rows` rows where
+ * request b owns the `rows_per_request` consecutive rows b * rows_per_request .. (rows = verify->B * rows_per_request);
+ * as soon as the last of them is normalised the request is verified exactly as sd_verify would (same arithmetic, same
+ * outputs) by the thread group that finished that row — the accept / resample step of
+ * sampling/speculative_sampling.py:1966-2027 no longer costs a second kernel launch and its drain / ramp.
+ * The verify arguments usually point into this call's own outputs (probs, tok_out, compact lists); rows of a request
+ * that are not part of this call (e.g. draft rows normalised earlier) must be complete before the launch.
+ *   request_counters  (verify->B,) int32 device scratch, zeroed once by the caller, left zeroed by every launch
+ * Needs compact lists on both sides and the persistent kernel (workspace given, 0 < top_k <= 128, aligned rows);
+ * otherwise the library runs sd_norm_sample followed by sd_verify on the same stream — the result is the same. */
+typedef struct sd_verify_args {
+  const float* p_probs; int64_t p_req_stride, p_row_stride;
+  const float* q_probs; int64_t q_req_stride, q_row_stride;
+  const int64_t* draft_tok; int64_t draft_stride;
+  const float* u_acc; int64_t u_acc_stride;
+  const float* u_final;
+  int32_t B, gamma; int64_t V; int32_t strict;
+  int32_t* n_accepted; int64_t* next_tok; float* ratios; int32_t* tie_count;
+  int64_t* tokens; int64_t tokens_stride; int32_t* seq_len; const int32_t* active;
+  const sd_compact_t* p_compact; int64_t p_cmp_req_stride;
+  const sd_compact_t* q_compact; int64_t q_cmp_req_stride;
+  uint64_t* stats;
+} sd_verify_args_t;
+int sd_norm_sample_verify(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
+                          int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                          const sd_compact_t* compact, const sd_verify_args_t* verify, int rows_per_request,
+                          int32_t* request_counters, int* err_flag, int flags, void* workspace, void* stream);
+
 /* max_fn — out = max(x,0) / (sum(max(x,0)) + 1e-6) per row.  Replaces sampling/utils.py:236-245. */
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream);
 

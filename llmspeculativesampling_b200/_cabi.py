@@ -22,6 +22,7 @@ SIGNATURES = {
     "sd_set_pdl": (None, [i32]),
     "sd_norm_probs": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, i32, vp, vp]),
     "sd_norm_sample": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp, i32, vp, vp]),
+    "sd_norm_sample_verify": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp]),
     "sd_sample": (i32, [vp, i64, i64, i64, vp, vp, vp, vp]),
     "sd_verify": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, vp, i32, i32, i64, i32,
                         vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
@@ -29,6 +30,18 @@ SIGNATURES = {
     "sd_kv_append": (i32, [vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sd_build_step": (i32, [vp, i64, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]),
 }
+
+class VerifyArgs(C.Structure):
+    """struct sd_verify_args (include/specdec_b200.h): the arguments of sd_verify, for sd_norm_sample_verify"""
+    _fields_ = [("p_probs", vp), ("p_req_stride", i64), ("p_row_stride", i64),
+                ("q_probs", vp), ("q_req_stride", i64), ("q_row_stride", i64),
+                ("draft_tok", vp), ("draft_stride", i64), ("u_acc", vp), ("u_acc_stride", i64), ("u_final", vp),
+                ("B", C.c_int32), ("gamma", C.c_int32), ("V", i64), ("strict", C.c_int32),
+                ("n_accepted", vp), ("next_tok", vp), ("ratios", vp), ("tie_count", vp),
+                ("tokens", vp), ("tokens_stride", i64), ("seq_len", vp), ("active", vp),
+                ("p_compact", vp), ("p_cmp_req_stride", i64), ("q_compact", vp), ("q_cmp_req_stride", i64),
+                ("stats", vp)]
+
 
 class Compact(C.Structure):
     """struct sd_compact (include/specdec_b200.h)"""

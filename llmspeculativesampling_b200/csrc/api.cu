@@ -45,17 +45,17 @@ static sd::Compact to_compact(const sd_compact_t* c) {
   return o;
 }
 
-static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
-                       int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
-                       const sd_compact_t* compact, int* err_flag, int flags, void* workspace, void* stream) {
-  if (rows == 0) return SD_OK;
+static int fill_norm(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
+                     int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                     const sd_compact_t* compact, int* err_flag, int flags, void* workspace, sd::NormParams& p) {
+  (void)dtype;
   if (logits == nullptr || err_flag == nullptr || rows < 0 || V <= 0 || ld_in < V) return fail(SD_EINVAL, "sd_norm: bad logits/shape");
   if (!(temperature > 0.f) || std::isinf(temperature)) return fail(SD_EINVAL, "sd_norm: temperature must be finite and > 0");
   if (probs != nullptr && ld_out < V) return fail(SD_EINVAL, "sd_norm: ld_out < V");
   if ((u == nullptr) != (tok_out == nullptr)) return fail(SD_EINVAL, "sd_norm: u and tok_out go together");
   if (probs == nullptr && u == nullptr) return fail(SD_EINVAL, "sd_norm: nothing to produce");
   if (V >= (1LL << 24) || rows >= (1LL << 28)) return fail(SD_EINVAL, "sd_norm: shape too large");
-  sd::NormParams p = {};
+  p = {};
   p.logits = logits; p.ld_in = ld_in; p.V = V;
   p.temperature = temperature; p.top_k = top_k < 0 ? 0 : top_k; p.top_p = top_p;
   p.probs = probs; p.ld_out = ld_out;
@@ -65,6 +65,17 @@ static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, i
   p.force_general = (flags & SD_NORM_FORCE_GENERAL) ? 1 : 0;
   p.no_pipeline = ((flags & SD_NORM_NO_PIPELINE) || workspace == nullptr) ? 1 : 0;
   p.sched = static_cast<unsigned int*>(workspace);
+  return SD_OK;
+}
+
+static int norm_common(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
+                       int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                       const sd_compact_t* compact, int* err_flag, int flags, void* workspace, void* stream) {
+  if (rows == 0) return SD_OK;
+  sd::NormParams p;
+  const int rc = fill_norm(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, compact,
+                           err_flag, flags, workspace, p);
+  if (rc != SD_OK) return rc;
   return done("sd_norm launch", sd::launch_norm(p, dtype, static_cast<int>(rows), static_cast<cudaStream_t>(stream)));
 }
 
@@ -96,6 +107,26 @@ int sd_sample(const float* probs, int64_t rows, int64_t V, int64_t ld, const flo
   return done("sd_sample launch", sd::launch_verify(p, static_cast<cudaStream_t>(stream)));
 }
 
+static int fill_verify(const sd_verify_args_t& a, int* err_flag, sd::VerifyParams& p) {
+  if (!a.p_probs || !a.q_probs || !a.draft_tok || !a.u_acc || !a.u_final || !a.n_accepted || !a.next_tok || !err_flag)
+    return fail(SD_EINVAL, "sd_verify: null argument");
+  if (a.B < 0 || a.gamma < 1 || a.gamma > 32 || a.V <= 0 || a.V >= (1LL << 24)) return fail(SD_EINVAL, "sd_verify: bad shape (1 <= gamma <= 32)");
+  if ((a.tokens == nullptr) != (a.seq_len == nullptr)) return fail(SD_EINVAL, "sd_verify: tokens and seq_len go together");
+  p = {};
+  p.p = a.p_probs; p.p_req_stride = a.p_req_stride; p.p_row_stride = a.p_row_stride;
+  p.q = a.q_probs; p.q_req_stride = a.q_req_stride; p.q_row_stride = a.q_row_stride;
+  p.draft = reinterpret_cast<const long long*>(a.draft_tok); p.draft_stride = a.draft_stride;
+  p.u_acc = a.u_acc; p.u_acc_stride = a.u_acc_stride; p.u_final = a.u_final;
+  p.B = a.B; p.gamma = a.gamma; p.V = a.V; p.strict = a.strict;
+  p.n_accepted = a.n_accepted; p.next_tok = reinterpret_cast<long long*>(a.next_tok); p.ratios = a.ratios;
+  p.tie_count = a.tie_count; p.err_flag = err_flag;
+  p.tokens = reinterpret_cast<long long*>(a.tokens); p.tokens_stride = a.tokens_stride; p.seq_len = a.seq_len; p.active = a.active;
+  p.stats = reinterpret_cast<unsigned long long*>(a.stats);
+  p.pc = to_compact(a.p_compact); p.qc = to_compact(a.q_compact);
+  p.pc_req_stride = a.p_cmp_req_stride * p.pc.row_stride; p.qc_req_stride = a.q_cmp_req_stride * p.qc.row_stride;
+  return SD_OK;
+}
+
 int sd_verify(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const float* q_probs,
               int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
               const float* u_acc, int64_t u_acc_stride, const float* u_final, int B, int gamma, int64_t V, int strict,
@@ -104,23 +135,33 @@ int sd_verify(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, 
               int64_t p_cmp_req_stride, const sd_compact_t* q_compact, int64_t q_cmp_req_stride, uint64_t* stats,
               int* err_flag, void* stream) {
   if (B == 0) return SD_OK;
-  if (!p_probs || !q_probs || !draft_tok || !u_acc || !u_final || !n_accepted || !next_tok || !err_flag)
-    return fail(SD_EINVAL, "sd_verify: null argument");
-  if (B < 0 || gamma < 1 || gamma > 32 || V <= 0 || V >= (1LL << 24)) return fail(SD_EINVAL, "sd_verify: bad shape (1 <= gamma <= 32)");
-  if ((tokens == nullptr) != (seq_len == nullptr)) return fail(SD_EINVAL, "sd_verify: tokens and seq_len go together");
-  sd::VerifyParams p = {};
-  p.p = p_probs; p.p_req_stride = p_req_stride; p.p_row_stride = p_row_stride;
-  p.q = q_probs; p.q_req_stride = q_req_stride; p.q_row_stride = q_row_stride;
-  p.draft = reinterpret_cast<const long long*>(draft_tok); p.draft_stride = draft_stride;
-  p.u_acc = u_acc; p.u_acc_stride = u_acc_stride; p.u_final = u_final;
-  p.B = B; p.gamma = gamma; p.V = V; p.strict = strict;
-  p.n_accepted = n_accepted; p.next_tok = reinterpret_cast<long long*>(next_tok); p.ratios = ratios;
-  p.tie_count = tie_count; p.err_flag = err_flag;
-  p.tokens = reinterpret_cast<long long*>(tokens); p.tokens_stride = tokens_stride; p.seq_len = seq_len; p.active = active;
-  p.stats = reinterpret_cast<unsigned long long*>(stats);
-  p.pc = to_compact(p_compact); p.qc = to_compact(q_compact);
-  p.pc_req_stride = p_cmp_req_stride * p.pc.row_stride; p.qc_req_stride = q_cmp_req_stride * p.qc.row_stride;
+  const sd_verify_args_t a = {p_probs, p_req_stride, p_row_stride, q_probs, q_req_stride, q_row_stride, draft_tok, draft_stride,
+                              u_acc, u_acc_stride, u_final, B, gamma, V, strict, n_accepted, next_tok, ratios, tie_count,
+                              tokens, tokens_stride, seq_len, active, p_compact, p_cmp_req_stride, q_compact,
+                              q_cmp_req_stride, stats};
+  sd::VerifyParams p;
+  const int rc = fill_verify(a, err_flag, p);
+  if (rc != SD_OK) return rc;
   return done("sd_verify launch", sd::launch_verify(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sd_norm_sample_verify(const void* logits, int dtype, int64_t rows, int64_t V, int64_t ld_in, float temperature,
+                          int top_k, float top_p, float* probs, int64_t ld_out, const float* u, int64_t* tok_out,
+                          const sd_compact_t* compact, const sd_verify_args_t* verify, int rows_per_request,
+                          int32_t* request_counters, int* err_flag, int flags, void* workspace, void* stream) {
+  if (verify == nullptr || request_counters == nullptr || rows_per_request < 1)
+    return fail(SD_EINVAL, "sd_norm_sample_verify: verify / request_counters / rows_per_request");
+  if (rows != static_cast<int64_t>(verify->B) * rows_per_request) return fail(SD_EINVAL, "sd_norm_sample_verify: rows != B * rows_per_request");
+  if (rows == 0) return SD_OK;
+  sd::NormParams p;
+  const int rc = fill_norm(logits, dtype, rows, V, ld_in, temperature, top_k, top_p, probs, ld_out, u, tok_out, compact,
+                           err_flag, flags, workspace, p);
+  if (rc != SD_OK) return rc;
+  const int rc2 = fill_verify(*verify, err_flag, p.fv);
+  if (rc2 != SD_OK) return rc2;
+  p.fv_rows = rows_per_request;
+  p.fv_cnt = request_counters;
+  return done("sd_norm_sample_verify launch", sd::launch_norm_verify(p, dtype, static_cast<int>(rows), static_cast<cudaStream_t>(stream)));
 }
 
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream) {

@@ -128,9 +128,23 @@ cudaError_t launch_norm(const NormParams& pin, int dtype, int rows, cudaStream_t
   NormParams p = pin;
   p.prof = g_prof;
   p.row_filter = nullptr;
+  p.fv_rows = 0;
   // persistent pipelined kernel where it applies (it falls back to the general path per row by itself)
   if (g_tune_threads == 0 && !p.no_pipeline && plan_pipe(p, dtype, rows, g_tune_cluster)) return launch_norm_pipe(p, dtype, rows, st);
   return launch_classic(p, dtype, rows, st);
+}
+
+cudaError_t launch_norm_verify(const NormParams& pin, int dtype, int rows, cudaStream_t st) {
+  NormParams p = pin;
+  p.prof = g_prof;
+  p.row_filter = nullptr;
+  // one launch: needs the pipelined kernel and compact lists on both sides (the in-kernel verify is the sparse one)
+  const bool lists = p.fv.q != nullptr && p.fv.pc.cnt != nullptr && p.fv.qc.cnt != nullptr && p.fv_cnt != nullptr && p.fv_rows > 0;
+  if (lists && g_tune_threads == 0 && !p.no_pipeline && plan_pipe(p, dtype, rows, g_tune_cluster)) return launch_norm_pipe(p, dtype, rows, st);
+  p.fv_rows = 0;
+  cudaError_t e = launch_norm(p, dtype, rows, st);
+  if (e != cudaSuccess) return e;
+  return launch_verify(pin.fv, st);
 }
 
 static cudaError_t launch_classic(const NormParams& p, int dtype, int rows, cudaStream_t st) {

@@ -20,6 +20,7 @@
 //
 // Replaces the same reference code as norm.cu: /root/reference/sampling/utils.py:152-210 (+213-233).
 #include "norm_row.cuh"
+#include "verify_sparse.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,7 @@ constexpr uint32_t kPipeTieUlps = 8;
 constexpr int kPipeWarpCap = 48;       // candidates one warp may collect per work item
 constexpr int kPipeMaxFail = 256;      // rows per cluster and round that may be deferred to the general path
 constexpr int kPipeFailSlack = 24;     // ... minus the items that can still be in flight when the leader stops taking rows
+constexpr int kPipeMaxPend = 64;       // requests per cluster and round whose fused verify needs the dense scan (served at the end)
 constexpr int kPipeRowRing = 32;       // row indices of the items in flight (the leader is < 16 items ahead of a peer)
 
 template <int CAP>
@@ -42,6 +44,7 @@ struct alignas(16) PipeGroupShared {
   uint2 w_pair[kPipeGroupWarps][kPipeWarpCap];       // candidates found by each warp (logit/T bits, index)
   int w_cnt[kPipeGroupWarps];
   int n_keep_p;
+  int fv_req;                                        // fused verify: request completed by this group's last item, or -1
   float tau;
   uint2 recv_cnt2[2][kMaxCluster];                   // [item parity][cluster rank].x = candidate count (-1: general path)
   uint2 r_pair[2][CAP];                         // receive regions (logit/T bits, index), double buffered by item parity
@@ -69,6 +72,8 @@ struct alignas(16) PipeShared {
   int n_fail;                         // rows deferred to the general path in this round ...
   int end_reason;                     // ... and why the round ended
   int fail_rows[kPipeMaxFail];
+  int n_pend, fv_req_cta, fv_na;      // fused verify: requests waiting for the dense scan; end-phase hand-over slots
+  int2 pend[kPipeMaxPend];            // (request, accepted tokens)
 };
 constexpr int kPipeEndDone = -1;       // every row has been handed out
 constexpr int kPipeEndPause = -2;      // the deferred-row list is nearly full: run the general path, then resume
@@ -107,8 +112,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t phase)
 }
 
 // debug timeline: prof[(cta * 32 + item) * 16 + slot] = clock64()   (items >= 32 are not recorded)
+#ifdef SD_DEBUG_HANG
+#define PIPE_PROF(item, slot, cond) do { } while (0)
+#define PIPE_DBG(slot, val, cond) do { if (p.prof != nullptr && (cond)) { \
+    *reinterpret_cast<volatile long long*>(p.prof + static_cast<long long>(blockIdx.x) * 16 + (slot)) = (val); __threadfence_system(); } } while (0)
+#else
+#define PIPE_DBG(slot, val, cond) do { } while (0)
 #define PIPE_PROF(item, slot, cond) do { if (p.prof != nullptr && (cond) && (item) < 32) \
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + (item)) * 16 + (slot)] = clock64(); } while (0)
+#endif
 
 // NG compute groups share NB slice buffers: work item i uses buffer i % NB and is processed by group i % NG.  A buffer
 // is only held from the TMA issue to the end of the re-scan (~40 % of an item's latency), so NG > NB groups keep the
@@ -157,6 +169,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     }
     for (int i = 0; i < kPipeRowRing; ++i) mbar_init(&sh.rowbar[i], 1);
     sh.n_fail = 0;
+    sh.n_pend = 0;
     sh.end_reason = kPipeEndDone;
     fence_barrier_init();
   }
@@ -232,6 +245,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
         // no more items: tell each group (its next NG item slots), in item order
         if (lane == 0) {
           sh.end_reason = row;
+          PIPE_DBG(0, it * 100 + 5, true);
           for (int j = 0; j < NG; ++j) {
             const int e = it + j;
             if (e >= NG) mbar_wait(&sh.taken[e % NG], (static_cast<uint32_t>(e / NG) - 1) & 1);
@@ -242,8 +256,11 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
         break;
       }
       PIPE_PROF(it, 0, lane == 0);
+      PIPE_DBG(0, it * 100 + 1, lane == 0);
       if (it >= NB) mbar_wait(&sh.empty[it % NB], (static_cast<uint32_t>(it / NB) - 1) & 1);   // the re-scan of item it - NB is done
+      PIPE_DBG(0, it * 100 + 2, lane == 0);
       if (it >= NG) mbar_wait(&sh.taken[it % NG], (static_cast<uint32_t>(it / NG) - 1) & 1);   // its group saw item it - NG
+      PIPE_DBG(0, it * 100 + 3, lane == 0);
       PIPE_PROF(it, 1, lane == 0);
       if (lane == 0) sh.item_row[slot] = make_uint2(static_cast<uint32_t>(row), 0u);          // (released by the arrive on full[g])
       issue_load(it, row);
@@ -255,7 +272,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
       const bool next_static = it + 1 < n_static;
       if (next_static) next = static_row(it + 1);
       else if (crank == 0 && lane == 0) {
-        if (sh.n_fail >= kPipeMaxFail - kPipeFailSlack) next = kPipeEndPause;
+        if (sh.n_fail >= kPipeMaxFail - kPipeFailSlack || sh.n_pend >= kPipeMaxPend - kPipeFailSlack) next = kPipeEndPause;
         else {
           next = static_cast<int>(atomicAdd(p.sched, 1u)) + static_rows;
           next = next < p.rows ? next : kPipeEndDone;
@@ -277,6 +294,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
         }
       }
       PIPE_PROF(it, 2, lane == 0);
+      PIPE_DBG(0, it * 100 + 4, lane == 0);
       row = next;
     }
   } else {
@@ -298,6 +316,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
 
     // ---- pass 1: thread maxima (NaN-propagating)
     PIPE_PROF(it, 3, gt == 0);
+    PIPE_DBG(1 + g, it * 100 + 1, gt == 0);
     mbar_wait(&sh.full[g], use & 1);
     const int row = static_cast<int>(*reinterpret_cast<volatile uint32_t*>(&sh.item_row[it % kPipeRowRing].x));
     if (row < 0) break;                                       // no more items (every group gets its own end marker)
@@ -454,6 +473,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     PIPE_PROF(it, 14, gt == 0);
     // the zero-fill of this item must be observed before the buffer is handed back (see header), then release it
     PIPE_PROF(it, 7, gt == 0);
+    PIPE_DBG(1 + g, it * 100 + 3, gt == 0);
     mbar_wait(&sh.zeroed[g], use & 1);
     __syncwarp();
     if (lane == 0) mbar_arrive_local(&sh.empty[buf]);
@@ -461,6 +481,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     if (gt == 0) mbar_arrive_local(&sh.taken[g]);              // every warp of the group has observed full + zeroed
 
     PIPE_PROF(it, 8, gt == 0);
+    PIPE_DBG(1 + g, it * 100 + 4, gt == 0);
     // ---- publish: push my candidates into every peer's receive region, then signal its mbarrier
     int wofs[GW + 1];
     bool w_over = false;
@@ -493,6 +514,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     named_bar(bar_id, GT);
 
     PIPE_PROF(it, 9, gt == 0);
+    PIPE_DBG(1 + g, it * 100 + 6, gt == 0);
     // ---- merge (identical in every CTA of the cluster): concatenate the C receive regions as 64-bit sort keys
     int n_tot = 0;
     bool ok = true;
@@ -663,14 +685,33 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     }
     named_bar(bar_id, GT);                   // group scratch is reused by the next item
     PIPE_PROF(it, 11, gt == 0);
+    PIPE_DBG(1 + g, it * 100 + 7, gt == 0);
+    // ---- fused verify: the group that finishes the last row of a request verifies it right away (one warp, from the
+    //      compact lists the rows' clusters just wrote; a request that needs the dense scan is left for the end)
+    if (p.fv_rows > 0 && crank == 0) {
+      if (gt == 0) {
+        __threadfence();                                       // this row's outputs (ordered by the barrier above) first
+        const int b = row / p.fv_rows;
+        int done_req = -1;
+        if (atomicAdd(p.fv_cnt + b, 1) == p.fv_rows - 1) { p.fv_cnt[b] = 0; __threadfence(); done_req = b; }
+        gs.fv_req = done_req;
+      }
+      named_bar(bar_id, GT);
+      const int b = gs.fv_req;
+      if (b >= 0 && gw == 0) {
+        const int na = sparse_verify_warp(p.fv, b, lane, reinterpret_cast<SparseVerifyScratch*>(gs.a_key));
+        if (na >= 0 && lane == 0) sh.pend[atomicAdd(&sh.n_pend, 1)] = make_int2(b, na);
+      }
+    }
   }
   }  // compute groups
 
   // =============================================================================== drained: general path for deferred rows
+  PIPE_DBG(5 + (warp == NG * GW ? 4 : warp / GW), 9, lane == 0 && (warp % GW == 0 || warp == NG * GW));
   if (!shook) { cluster.barrier_wait(); shook = true; }
   __syncthreads();
+  PIPE_DBG(10, 1, tid == 0);
   const int reason = sh.end_reason;
-  if (reason == kPipeEndDone) pdl_launch_dependents();   // the next kernel may start occupying freed SMs
   if (round == 0 && p.prof != nullptr && tid == 0) {
     unsigned long long gt1;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
@@ -678,6 +719,21 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + 3) * 16 + 15] = static_cast<long long>(gt1);
   }
   const int n_fail = sh.n_fail;                 // identical in every CTA of the cluster (same rows, same decisions) ...
+  if (n_fail > 0 || reason != kPipeEndDone) {
+    // the pipeline's mbarriers are retired before the general path re-purposes their memory (and before a later round
+    // initialises them again): nothing can touch them any more — every warp of this CTA is here, and a peer only signals
+    // barriers of items this CTA has finished
+    if (C > 1) cluster.sync();
+    if (tid == 0) {
+      for (int b = 0; b < NB; ++b) mbar_inval(&sh.empty[b]);
+      for (int g = 0; g < NG; ++g) {
+        mbar_inval(&sh.full[g]); mbar_inval(&sh.zeroed[g]); mbar_inval(&sh.taken[g]);
+        mbar_inval(&sh.xbar[g][0]); mbar_inval(&sh.xbar[g][1]);
+      }
+      for (int i = 0; i < kPipeRowRing; ++i) mbar_inval(&sh.rowbar[i]);
+    }
+    __syncthreads();
+  }
   if (n_fail > 0) {
     // ... but appended in racing order: sort, so that the CTAs of a cluster walk the rows in lock step
     int mine = 0, rank = 0;
@@ -687,19 +743,61 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     }
     __syncthreads();
     if (tid < n_fail) sh.fail_rows[rank] = mine;
-    __syncthreads();
-    if (C > 1) cluster.sync();                  // peers have drained too: their shared memory may be re-purposed
+    __syncthreads();                            // (peers have drained too — cluster.sync above — so shared memory may be re-purposed)
     NormParams p2 = p;
     p2.force_general = 1;
     p2.prof = nullptr;
+#ifdef SD_DEBUG_HANG
+    if (p.prof != nullptr) p2.prof = p.prof + 256 * 16;
+#endif
     for (int i = 0; i < n_fail; ++i) {
-      norm_row<T, 32 + NG * kPipeGroupThreads>(p2, sh.fail_rows[i]);
+      const int frow = sh.fail_rows[i];
+      PIPE_DBG(10, 1000 + i * 10 + 3, tid == 0);
+      PIPE_DBG(11, frow, tid == 0);
+      norm_row<T, 32 + NG * kPipeGroupThreads>(p2, frow);
+      __syncthreads();
+      PIPE_DBG(10, 1000 + i * 10 + 4, tid == 0);
+      if (p.fv_rows > 0 && crank == 0) {        // fused verify: count the row; the leader CTA verifies a completed request
+        constexpr int TH = 32 + NG * kPipeGroupThreads;
+        if (tid == 0) {
+          __threadfence();
+          const int b = frow / p.fv_rows;
+          int done_req = -1;
+          if (atomicAdd(p.fv_cnt + b, 1) == p.fv_rows - 1) { p.fv_cnt[b] = 0; __threadfence(); done_req = b; }
+          sh.fv_req_cta = done_req;
+        }
+        __syncthreads();
+        const int b = sh.fv_req_cta;
+        if (b >= 0) {
+          RowScratch<TH>* rs_cta = reinterpret_cast<RowScratch<TH>*>(smem_raw);
+          SparseVerifyScratch* sc_cta = reinterpret_cast<SparseVerifyScratch*>(smem_raw + ((sizeof(RowScratch<TH>) + 15) & ~size_t(15)));
+          if (warp == 0) {
+            const int na = sparse_verify_warp(p.fv, b, lane, sc_cta);
+            if (lane == 0) sh.fv_na = na;
+          }
+          __syncthreads();
+          if (sh.fv_na >= 0) dense_verify_cta<TH>(p.fv, b, sh.fv_na, rs_cta);
+          __syncthreads();
+        }
+      }
+    }
+  }
+  if (p.fv_rows > 0 && crank == 0 && sh.n_pend > 0) {       // requests whose lists were unavailable: dense scan by the CTA
+    constexpr int TH = 32 + NG * kPipeGroupThreads;
+    const int n_pend = sh.n_pend;
+    for (int i = 0; i < n_pend; ++i) {
+      dense_verify_cta<TH>(p.fv, sh.pend[i].x, sh.pend[i].y, reinterpret_cast<RowScratch<TH>*>(smem_raw));
       __syncthreads();
     }
   }
   if (reason == kPipeEndDone) break;
   }  // rounds
 
+  // Dependents are only triggered here, after ALL work of the CTA: an earlier griddepcontrol.launch_dependents (before
+  // the general-path phase) hung the kernel on B200 when that phase was long (measured; the trigger buys nothing anyway,
+  // the dependent's prologue overlaps the slowest CTA's tail either way).
+  PIPE_DBG(10, 6, tid == 0);
+  pdl_launch_dependents();
   // the last cluster to finish re-arms the row counter for the next launch that uses this scheduler block
   if (crank == 0 && tid == 0) {
     __threadfence();

@@ -59,7 +59,11 @@ __device__ __forceinline__ float div_fast(float l, float temp, float r_temp) {
   return (fabsf(q0) == INFINITY) ? q0 : x;
 }
 
+#ifdef SD_DEBUG_HANG
+#define SD_PROF(slot) do { if (p.prof != nullptr && tid == 0) { *reinterpret_cast<volatile long long*>(p.prof + static_cast<long long>(blockIdx.x) * 16 + (slot)) = clock64(); __threadfence_system(); } } while (0)
+#else
 #define SD_PROF(slot) do { if (p.prof != nullptr && tid == 0) p.prof[static_cast<long long>(blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
+#endif
 
 template <typename T, int THREADS>
 __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
@@ -139,6 +143,13 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
     }
   }
   if (tmax != tmax || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
+  if (p.use_tma) {
+    // Every thread is past its waits: retire the mbarriers.  The next row of this CTA initialises them again, and an
+    // mbarrier.init on a still-valid object is undefined (observed on B200: now and then the second row's TMA
+    // completion never showed up on the re-initialised barrier and the CTA hung).
+    __syncthreads();
+    if (tid == 0) for (int c = 0; c < n_chunks; ++c) mbar_inval(&sh.bar[c]);
+  }
   SD_PROF(3);
   bool done = false;
 

@@ -12,32 +12,6 @@ struct Compact {
   int cap; long long row_stride;
 };
 
-struct NormParams {
-  const void* logits; long long ld_in; long long V;
-  float temperature; int top_k; float top_p;
-  float* probs; long long ld_out;          // nullable: no dense write (sample only)
-  const float* u; long long* tok_out;      // nullable pair: per-row uniform -> sampled token
-  int* err_flag;
-  Compact cmp;                             // cmp.cnt == nullptr: disabled
-  // filled by the launcher
-  int cluster, slice_elems, slice_smem_bytes, use_tma, vec_out;
-  int force_general;                       // test knob: skip the fast top-k path
-  int no_pipeline;                         // use the one-cluster-per-row kernel even where the persistent one applies
-  long long* prof;                         // debug: per-CTA clock64 timestamps (16 slots per CTA), nullable
-  int rows;                                // number of logits rows
-  unsigned int* sched;                     // pipelined kernel: {next row ticket, finished clusters}; zero between launches
-  int pipe_groups;                         // persistent kernel: compute groups (= slice buffers) per CTA
-  int pipe_buffers, pipe_cap, pipe_clusters;             // ... merged-candidate capacity, clusters in the persistent grid
-  const int* row_filter;                   // norm_probs_kernel: process only rows with row_filter[row] != 0
-};
-cudaError_t launch_norm(const NormParams& p, int dtype, int rows, cudaStream_t st);
-void set_norm_tuning(int cluster, int threads);
-void set_norm_prof(long long* ptr);
-void set_pdl(int enable);
-int pdl_enabled();
-bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster);
-cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStream_t st);
-
 struct VerifyParams {
   const float* p; long long p_req_stride, p_row_stride;     // target probs  (B, gamma+1, V)
   const float* q; long long q_req_stride, q_row_stride;     // draft probs   (B, gamma,   V); null => plain sample of p row 0
@@ -55,6 +29,38 @@ struct VerifyParams {
   // filled by the launcher
   int cluster, slice_elems, use_tma;
 };
+struct NormParams {
+  const void* logits; long long ld_in; long long V;
+  float temperature; int top_k; float top_p;
+  float* probs; long long ld_out;          // nullable: no dense write (sample only)
+  const float* u; long long* tok_out;      // nullable pair: per-row uniform -> sampled token
+  int* err_flag;
+  Compact cmp;                             // cmp.cnt == nullptr: disabled
+  // filled by the launcher
+  int cluster, slice_elems, slice_smem_bytes, use_tma, vec_out;
+  int force_general;                       // test knob: skip the fast top-k path
+  int no_pipeline;                         // use the one-cluster-per-row kernel even where the persistent one applies
+  long long* prof;                         // debug: per-CTA clock64 timestamps (16 slots per CTA), nullable
+  int rows;                                // number of logits rows
+  unsigned int* sched;                     // pipelined kernel: {next row ticket, finished clusters}; zero between launches
+  int pipe_groups;                         // persistent kernel: compute groups (= slice buffers) per CTA
+  int pipe_buffers, pipe_cap, pipe_clusters;             // ... merged-candidate capacity, clusters in the persistent grid
+  const int* row_filter;                   // norm_probs_kernel: process only rows with row_filter[row] != 0
+  // pipelined kernel, optional: verify request b as soon as its fv_rows rows (b * fv_rows ..) are all normalised
+  int fv_rows;                             // 0: disabled
+  int* fv_cnt;                             // (B,) finished-row counters, zero between launches
+  VerifyParams fv;
+};
+cudaError_t launch_norm(const NormParams& p, int dtype, int rows, cudaStream_t st);
+// kernel 1 + kernel 2 in one launch where the pipelined kernel applies, else two launches
+cudaError_t launch_norm_verify(const NormParams& p, int dtype, int rows, cudaStream_t st);
+void set_norm_tuning(int cluster, int threads);
+void set_norm_prof(long long* ptr);
+void set_pdl(int enable);
+int pdl_enabled();
+bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster);
+cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStream_t st);
+
 cudaError_t launch_verify(const VerifyParams& p, cudaStream_t st);
 void set_verify_tuning(int cluster);
 

@@ -9,6 +9,7 @@
 // kernel is the drop-in for sampling/utils.py:213-233 (sample) on rows of p.
 #include "rowops.cuh"
 #include "specdec_internal.h"
+#include "verify_sparse.cuh"
 
 namespace sd {
 
@@ -172,18 +173,6 @@ __global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParam
 // Requests whose lists are unavailable (count -1: the row was served by the dense / general path) fall back, inside
 // this kernel, to a single-CTA dense scan straight from HBM/L2.
 constexpr int kSparseThreads = 128;
-constexpr int kSparseCap = 64;
-
-__device__ __forceinline__ void verify_commit(const VerifyParams& p, int b, int n_acc, long long out, int L_pre = -1) {
-  p.next_tok[b] = out;
-  if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc;
-  if (p.stats != nullptr) { atomicAdd(&p.stats[0], static_cast<unsigned long long>(n_acc)); atomicAdd(&p.stats[1], 1ull); }
-  if (p.tokens != nullptr) {
-    const int L = L_pre >= 0 ? L_pre : p.seq_len[b];
-    p.tokens[b * p.tokens_stride + L + n_acc] = out;
-    p.seq_len[b] = L + n_acc + 1;
-  }
-}
 
 __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const VerifyParams p) {
   __shared__ RowScratch<kSparseThreads> rs;
@@ -197,7 +186,6 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
   __shared__ unsigned long long e_w[kSparseCap];
   const int b = blockIdx.x;
   pdl_wait();
-  pdl_launch_dependents();                                    // the next kernel's prologue may overlap this (short) kernel
   if (p.active != nullptr && p.active[b] == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = static_cast<int>(p.V), gamma = p.gamma;
@@ -342,56 +330,7 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
   if (s_dense == 0) return;
 
   // ---- dense fallback for this request: one CTA scans p_n (and q_n) straight from global memory
-  RowCtx<kSparseThreads> cx(&rs, 1);
-  const int n_acc = s_n_acc;
-  bool use_q = n_acc < gamma;
-  const float* prow = p.p + b * p.p_req_stride + n_acc * p.p_row_stride;
-  const float* qrow = p.q + b * p.q_req_stride + n_acc * p.q_row_stride;
-  const int n_vec = (V + 3) / 4;
-  auto vecw = [&](int v, float (&w)[4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = v * 4 + j;
-      float a = i < V ? prow[i] : 0.f;
-      if (use_q && i < V) a = fmaxf(a - qrow[i], 0.f);
-      w[j] = a;
-    }
-  };
-  unsigned long long best = 0ull;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    unsigned long long mine = 0ull;
-    bool bad = false;
-    for (int v = tid; v < n_vec; v += kSparseThreads) {
-      float w[4];
-      vecw(v, w);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        bad |= !(w[j] >= 0.f) || isinf(w[j]);
-        if (w[j] > 0.f) {
-          const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(v * 4 + j));
-          mine = pk > mine ? pk : mine;
-        }
-      }
-    }
-    if (bad) atomicOr(p.err_flag, kErrEmptyRow);
-    best = cx.allreduce_max(mine);
-    if (best != 0ull || !use_q || p.strict) break;
-    use_q = false;
-  }
-  if (best == 0ull) {
-    if (tid == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.next_tok[b] = 0; if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc; }
-    return;
-  }
-  const float rmax = key2f(static_cast<uint32_t>(best >> 32));
-  const int argmax = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffu));
-  unsigned long long total = 0ull;
-  float psel = 1.f;
-  const int tok_d = cluster_icdf<4, kSparseThreads>(cx, n_vec, 0, rmax, p.u_final[b], vecw, &total, &psel);
-  if (tok_d >= 0) {
-    float guard_val = psel;
-    if (use_q) guard_val = __fdiv_rn(psel, ldexpf(__ull2float_rn(total), frexp_exp(rmax) - kScaleBits) + 1e-6f);
-    verify_commit(p, b, n_acc, guard_val < kProbGuard ? argmax : tok_d);
-  }
+  dense_verify_cta<kSparseThreads>(p, b, s_n_acc, &rs);
 }
 
 static int g_verify_cluster = 0;

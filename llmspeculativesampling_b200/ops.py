@@ -246,6 +246,49 @@ def verify(p_probs: torch.Tensor, q_probs: torch.Tensor, draft_tok: torch.Tensor
     return n_accepted, next_tok
 
 
+def norm_sample_verify(logits: torch.Tensor, temperature: float, top_k: int, top_p: float, u: torch.Tensor,
+                       probs_out: torch.Tensor, tok_out: torch.Tensor, compact, rows_per_request: int,
+                       request_counters: torch.Tensor, p_probs: torch.Tensor, q_probs: torch.Tensor,
+                       draft_tok: torch.Tensor, u_acc: torch.Tensor, u_final: torch.Tensor, n_accepted: torch.Tensor,
+                       next_tok: torch.Tensor, p_compact, p_cmp_req_stride: int, q_compact, q_cmp_req_stride: int,
+                       err: ErrFlag, strict: bool = False, ratios: Optional[torch.Tensor] = None,
+                       tie_count: Optional[torch.Tensor] = None, tokens: Optional[torch.Tensor] = None,
+                       seq_len: Optional[torch.Tensor] = None, active: Optional[torch.Tensor] = None,
+                       stats: Optional[torch.Tensor] = None, pipeline: bool = True) -> None:
+    """Kernels 1 + 2 in one launch (sd_norm_sample_verify): `norm_sample` over (B * rows_per_request, V) logits where
+    request b owns rows b * rows_per_request ..; each request is verified (arguments as `verify`) as soon as its last
+    row is normalised.  `request_counters`: (B,) int32 zeros, left zeroed.  Falls back to two launches inside the
+    library where the persistent kernel does not apply."""
+    _require_cuda(logits, "logits")
+    x = _rows2d(logits)
+    rows, V = x.shape
+    B, g1, _ = p_probs.shape
+    gamma = g1 - 1
+    assert rows == B * rows_per_request and request_counters.dtype == torch.int32 and request_counters.numel() >= B
+    assert u.is_cuda and u.dtype == torch.float32 and u.numel() == rows and u.is_contiguous()
+    assert tok_out.dtype == torch.int64 and tok_out.numel() == rows and tok_out.is_contiguous()
+    assert probs_out.dtype == torch.float32 and probs_out.shape == (rows, V) and probs_out.stride(1) == 1
+    assert q_probs.shape == (B, gamma, V) and p_probs.stride(2) == 1 and q_probs.stride(2) == 1
+    assert draft_tok.dtype == torch.int64 and draft_tok.shape == (B, gamma) and draft_tok.stride(1) == 1
+    assert u_acc.dtype == torch.float32 and u_acc.shape == (B, gamma) and u_acc.stride(1) == 1
+    assert u_final.dtype == torch.float32 and u_final.numel() == B and u_final.is_contiguous()
+    assert err is not None and not err.shared, "the fused launch needs an ErrFlag of its own (scheduler workspace)"
+    import ctypes
+    va = _cabi.VerifyArgs(
+        p_probs.data_ptr(), p_probs.stride(0), p_probs.stride(1), q_probs.data_ptr(), q_probs.stride(0), q_probs.stride(1),
+        draft_tok.data_ptr(), draft_tok.stride(0), u_acc.data_ptr(), u_acc.stride(0), u_final.data_ptr(),
+        B, gamma, V, 1 if strict else 0, n_accepted.data_ptr(), next_tok.data_ptr(), _ptr(ratios), _ptr(tie_count),
+        _ptr(tokens), tokens.stride(0) if tokens is not None else 0, _ptr(seq_len), _ptr(active),
+        ctypes.addressof(p_compact) if p_compact is not None else None, p_cmp_req_stride,
+        ctypes.addressof(q_compact) if q_compact is not None else None, q_cmp_req_stride, _ptr(stats))
+    flags = 0 if pipeline else NORM_NO_PIPELINE
+    rc = _cabi.load().sd_norm_sample_verify(
+        x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), int(top_k or 0), float(top_p or 0.0),
+        probs_out.data_ptr(), probs_out.stride(0), u.data_ptr(), tok_out.data_ptr(), _cref(compact), ctypes.byref(va),
+        int(rows_per_request), request_counters.data_ptr(), err.ptr(), flags, err.ws_ptr(), _stream())
+    _cabi.check(rc, "sd_norm_sample_verify")
+
+
 def kv_append(k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
               write_pos: torch.Tensor) -> None:
     """cache[b, h, write_pos[b] + j] = new[b, h, j] for K and V.  new: (B, H, q, D) any strides with a

@@ -198,6 +198,65 @@ def test_compact_lists_and_sparse_verify_equal_dense(cuda_lib, V, dtype, pipelin
         assert np.array_equal(ratios[b].cpu().numpy(), wr)
 
 
+@pytest.mark.parametrize("V,dtype,B", [(32000, torch.float32, 64), (50272, torch.bfloat16, 40), (32000, torch.bfloat16, 300),
+                                       (4096, torch.float32, 2000), (32000, torch.float32, 1200)])
+@pytest.mark.parametrize("strict", [False, True])
+def test_fused_norm_sample_verify_equals_two_launches(cuda_lib, V, dtype, B, strict):
+    """sd_norm_sample_verify (verify inside the persistent norm kernel, by the group that finishes a request's last row)
+    must return exactly what sd_norm_sample followed by sd_verify returns: probabilities, drafted tokens, accept counts,
+    next tokens, appended tokens / lengths, ratios, statistics — including requests with tied rows (deferred to the
+    general path at the end of the kernel) and requests whose residual row has no compact list (dense scan)."""
+    from llmspeculativesampling_b200 import ops
+    gamma, T, k, p = 4, 0.8, 20, 0.9
+    R = 2 * gamma + 1
+    g = torch.Generator().manual_seed(V + B)
+    z = torch.randn(B, gamma + 1, V, generator=g) * 3.0
+    tl = (z + 0.5 * torch.randn(B, gamma + 1, V, generator=g)).to(dtype)
+    dl = (z[:, :gamma] + 0.5 * torch.randn(B, gamma, V, generator=g)).to(dtype)
+    tl[5, 2] = 1.0                                            # all-ties target row: deferred row, no list, dense residual
+    dl[7, 0] = dl[7, 0].round()                               # heavy ties in a draft row
+    tl[B - 1, gamma] = 0.5                                    # the very last row of the launch is a deferred one
+    for b in range(11, B, 97):
+        tl[b, 1] = -2.0
+    logits = torch.cat([dl, tl], 1).contiguous().cuda()
+    u = torch.rand(B, 2 * gamma + 2, generator=g)
+    ur = torch.full((B, R), -1.0); ur[:, :gamma] = u[:, :gamma]
+    ur = ur.view(-1).cuda()
+    u_acc = u[:, gamma + 1:2 * gamma + 1].contiguous().cuda(); u_fin = u[:, 2 * gamma + 1].contiguous().cuda()
+    u_acc[5, :] = 0.0; u_acc[5, 2] = 1.0 - 2 ** -24           # request 5 rejects at its tied row
+    S = 16
+    res = []
+    for fused in (False, True):
+        probs = torch.empty(B, R, V, device="cuda")
+        tok = torch.zeros(B, R, dtype=torch.int64, device="cuda")
+        cmp_rows = ops.CompactRows(B * R, "cuda")
+        n_acc = torch.full((B,), -7, dtype=torch.int32, device="cuda"); nxt = torch.full((B,), -7, dtype=torch.int64, device="cuda")
+        ratios = torch.zeros(B, gamma, device="cuda"); stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+        tokens = torch.zeros(B, S, dtype=torch.int64, device="cuda"); seq_len = torch.full((B,), 3, dtype=torch.int32, device="cuda")
+        err = ops.ErrFlag("cuda")
+        kw = dict(p_compact=cmp_rows.view(gamma, 1), p_cmp_req_stride=R, q_compact=cmp_rows.view(0, 1), q_cmp_req_stride=R)
+        for rep in range(2 if fused else 1):                   # twice: the counters must be left re-armed
+            if fused:
+                cnt = torch.zeros(B, dtype=torch.int32, device="cuda") if rep == 0 else cnt
+                seq_len.fill_(3); stats.zero_(); n_acc.fill_(-7); probs.fill_(-1.0)
+                ops.norm_sample_verify(logits.view(B * R, V), T, k, p, ur, probs.view(B * R, V), tok.view(-1), cmp_rows.view(), R, cnt,
+                                       probs[:, gamma:], probs[:, :gamma], tok[:, :gamma], u_acc, u_fin, n_acc, nxt, err=err,
+                                       strict=strict, ratios=ratios, tokens=tokens, seq_len=seq_len, stats=stats, **kw)
+                assert int(cnt.abs().sum()) == 0
+            else:
+                ops.norm_sample(logits.view(B * R, V), T, k, p, ur, probs_out=probs.view(B * R, V), tok_out=tok.view(-1), err=err,
+                                compact=cmp_rows.view())
+                ops.verify(probs[:, gamma:], probs[:, :gamma], tok[:, :gamma], u_acc, u_fin, strict=strict, n_accepted=n_acc,
+                           next_tok=nxt, ratios=ratios, tokens=tokens, seq_len=seq_len, err=err, stats=stats, **kw)
+        torch.cuda.synchronize()
+        err.check()
+        res.append((probs, tok, n_acc, nxt, ratios, tokens, seq_len, stats))
+    names = ["probs", "tok", "n_acc", "next", "ratios", "tokens", "seq_len", "stats"]
+    for nm, a, b_ in zip(names, res[0], res[1]):
+        assert torch.equal(a, b_), f"{nm} differs between the fused launch and norm + verify"
+    assert int(res[1][7][1]) == B and int(res[1][2][5]) == 2
+
+
 def test_distribution_preservation_chi_square(cuda_lib):
     """The reference authors' manual two-token check (kvcache_model.py:73-76, speculative_sampling.py:227-229: force
     p = {1: .4, 12: .6}, q = {1: .6, 12: .4} and count emitted tokens) as a statistical test of the whole step:
