@@ -237,6 +237,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="config2", choices=["config2", "config1"],
                     help="config2 = headline synthetic verify microbench; config1 = side report on the reference's CPU-runnable case")
+    ap.add_argument("--fused", type=int, default=0,
+                    help="0: sd_norm_sample + sd_verify (two launches per step, the faster arrangement at B = 64); "
+                         "1: sd_norm_sample_verify (one launch per step, requests verified inside the norm kernel)")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("SD_PDL", "1")), help="programmatic dependent launch on/off")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -282,7 +285,17 @@ def main():
     acc_total = torch.zeros(2, dtype=torch.int64, device=dev)     # [accepted tokens, requests verified], updated by kernel 2
     err = ops.ErrFlag(dev)
 
+    req_cnt = torch.zeros(B, dtype=torch.int32, device=dev)       # fused launch: finished-row counters (left zeroed)
+
     def step(i: int, count: bool = True):
+        if args.fused:
+            # ONE launch: kernel 1 over the B*(2*gamma+1) rows; each request is verified inside it as soon as its last
+            # row is normalised (sd_norm_sample_verify)
+            ops.norm_sample_verify(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs[i].view(B * R, V),
+                                   tok_rows.view(-1), c_all, R, req_cnt, probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g],
+                                   u_acc[i], u_fin[i], n_acc, next_tok, c_p, R, c_q, R, err,
+                                   stats=acc_total if count else None)
+            return
         ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
                         tok_out=tok_rows.view(-1), err=err, compact=c_all)
         ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
@@ -396,10 +409,15 @@ def main():
         hl, hu = host_sets[i]
         l_dev.copy_(hl, non_blocking=True); u_dev.copy_(hu, non_blocking=True)
         ur_dev.copy_(u_dev[:, :R].reshape(-1)); ua_dev.copy_(u_dev[:, R:R + g]); uf_dev.copy_(u_dev[:, R + g])
-        ops.norm_sample(l_dev.view(B * R, V), TEMP, TOP_K, TOP_P, ur_dev, probs_out=pr_dev.view(B * R, V),
-                        tok_out=tok_rows.view(-1), err=err, compact=c_all)
-        ops.verify(pr_dev[:, g:], pr_dev[:, :g], tok_rows[:, :g], ua_dev, uf_dev, n_accepted=n_acc, next_tok=next_tok, err=err,
-                   p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
+        if args.fused:
+            ops.norm_sample_verify(l_dev.view(B * R, V), TEMP, TOP_K, TOP_P, ur_dev, pr_dev.view(B * R, V), tok_rows.view(-1),
+                                   c_all, R, req_cnt, pr_dev[:, g:], pr_dev[:, :g], tok_rows[:, :g], ua_dev, uf_dev, n_acc,
+                                   next_tok, c_p, R, c_q, R, err)
+        else:
+            ops.norm_sample(l_dev.view(B * R, V), TEMP, TOP_K, TOP_P, ur_dev, probs_out=pr_dev.view(B * R, V),
+                            tok_out=tok_rows.view(-1), err=err, compact=c_all)
+            ops.verify(pr_dev[:, g:], pr_dev[:, :g], tok_rows[:, :g], ua_dev, uf_dev, n_accepted=n_acc, next_tok=next_tok, err=err,
+                       p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
         h_acc.copy_(n_acc, non_blocking=True); h_tok.copy_(next_tok, non_blocking=True)
         torch.cuda.synchronize()                            # the caller needs the tokens before the next step
         return int(h_acc.sum())
@@ -447,17 +465,20 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2_policy": f"inputs and outputs rotate over {n_sets} sets "
                    f"({n_sets * norm_bytes / 1e6:.0f} MB > 2 x 126 MB L2)", "cuda_graph": True,
-                   "kernels_per_step": ["sd_norm_sample (B*(2*gamma+1) rows, one launch; dense probs + compact lists)",
-                                        "sd_verify (sparse path on the compact lists)"]},
+                   "kernels_per_step": (["sd_norm_sample_verify (ONE launch: kernel 1 over the B*(2*gamma+1) rows — dense probs + "
+                                         "compact lists — and kernel 2's verify of each request inside it, by the thread group "
+                                         "that finishes the request's last row)"] if args.fused else
+                                        ["sd_norm_sample (B*(2*gamma+1) rows, one launch; dense probs + compact lists)",
+                                         "sd_verify (sparse path on the compact lists)"])},
         "emitted_tokens_per_s": (accepted + iters_total) / secs,
         "mean_accepted_per_iteration": accepted / iters_total,
         "request_iterations_per_s": iters_total / secs,
         "clocks": clock_info,
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": (1 if args.fused else 2) * args.steps,
         "e2e": {"value": e2e_acc / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "norm_topk_pipe_kernel<float,3> (1 launch per step, 576 rows)",
+                     "traffic": traffic, "kernel": "norm_topk_pipe_kernel<float,4,3,128> (1 launch per step, 576 rows; timed without the in-kernel verify)",
                      "algorithmic_bytes_per_step": norm_bytes, "ms_per_step": norm_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                      "frac_of_nominal_8TBs": achieved / 8000.0,

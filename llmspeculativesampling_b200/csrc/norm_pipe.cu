@@ -698,7 +698,11 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
       }
       named_bar(bar_id, GT);
       const int b = gs.fv_req;
+#ifdef SD_FV_NOVERIFY
+      if (false) {
+#else
       if (b >= 0 && gw == 0) {
+#endif
         const int na = sparse_verify_warp(p.fv, b, lane, reinterpret_cast<SparseVerifyScratch*>(gs.a_key));
         if (na >= 0 && lane == 0) sh.pend[atomicAdd(&sh.n_pend, 1)] = make_int2(b, na);
       }

@@ -89,30 +89,60 @@ struct SparseVerifyScratch {
 // The whole verify step of request b by ONE warp, from the compact lists in global memory (read through L2 with
 // ld.cg: inside the norm kernel they were just written by other SMs).  Same arithmetic as verify_sparse_kernel.
 // Returns -1 when the request is done, otherwise n_acc of a request that needs dense_verify_cta (a list is missing).
-__device__ inline int sparse_verify_warp(const VerifyParams& p, int b, int lane, SparseVerifyScratch* sc) {
+__device__ __forceinline__ int sparse_verify_warp(const VerifyParams& p, int b, int lane, SparseVerifyScratch* sc) {
   const int V = static_cast<int>(p.V), gamma = p.gamma;
   if (p.active != nullptr && __ldcg(p.active + b) == 0) return -1;
   int L_pre = -1;
   if (p.tokens != nullptr) L_pre = __ldcg(p.seq_len + b);
   const float u_f = __ldcg(p.u_final + b);
+  // accept scan: lane i owns drafted token i.  Its p / q values come from the compact lists of row i, which the WHOLE
+  // warp fetches (two entries per lane and list, four rows per round, every load of a round issued before the first
+  // use) — a per-lane walk over a list would be a chain of ~2 x cnt dependent L2 round trips.
+  long long tok = 0;
+  float u_a = 0.f, pv = 0.f, qv = 0.f;
+  int cpl = -1, cql = -1;
+  if (lane < gamma) {
+    tok = __ldcg(p.draft + b * p.draft_stride + lane);
+    u_a = __ldcg(p.u_acc + b * p.u_acc_stride + lane);
+    cpl = __ldcg(p.pc.cnt + b * p.pc_req_stride + lane * p.pc.row_stride);
+    cql = __ldcg(p.qc.cnt + b * p.qc_req_stride + lane * p.qc.row_stride);
+    if (tok < 0 || tok >= V) { atomicOr(p.err_flag, kErrBadToken); tok = 0; }
+    if (!(cpl >= 0 && cpl <= kSparseCap && cpl <= p.pc.cap)) { cpl = -1; pv = __ldcg(p.p + b * p.p_req_stride + lane * p.p_row_stride + tok); }
+    if (!(cql >= 0 && cql <= kSparseCap && cql <= p.qc.cap)) { cql = -1; qv = __ldcg(p.q + b * p.q_req_stride + lane * p.q_row_stride + tok); }
+  }
+  for (int i0 = 0; i0 < gamma; i0 += 4) {
+    // eight lanes per row, four rows per round: lane sub = lane % 8 walks entries sub, sub + 8, ... of both lists
+    const int i = i0 + (lane >> 3), sub = lane & 7, ic = min(i, gamma - 1);
+    const long long tok_i = __shfl_sync(0xffffffffu, tok, ic);
+    const int cp_i = i < gamma ? __shfl_sync(0xffffffffu, cpl, ic) : (__shfl_sync(0xffffffffu, cpl, ic), -1);
+    const int cq_i = i < gamma ? __shfl_sync(0xffffffffu, cql, ic) : (__shfl_sync(0xffffffffu, cql, ic), -1);
+    const long long pcr = (b * p.pc_req_stride + ic * p.pc.row_stride) * p.pc.cap, qcr = (b * p.qc_req_stride + ic * p.qc.row_stride) * p.qc.cap;
+    float fp = 0.f, fq = 0.f;                                 // listed probabilities are > 0 and indices are unique: max = lookup
+#pragma unroll 4
+    for (int j = sub; j < cp_i; j += 8) {
+      const int id = __ldcg(p.pc.idx + pcr + j);
+      const float v = __ldcg(p.pc.val + pcr + j);
+      fp = id == tok_i ? v : fp;
+    }
+#pragma unroll 4
+    for (int j = sub; j < cq_i; j += 8) {
+      const int id = __ldcg(p.qc.idx + qcr + j);
+      const float v = __ldcg(p.qc.val + qcr + j);
+      fq = id == tok_i ? v : fq;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      fp = fmaxf(fp, __shfl_xor_sync(0xffffffffu, fp, o));
+      fq = fmaxf(fq, __shfl_xor_sync(0xffffffffu, fq, o));
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float a = __shfl_sync(0xffffffffu, fp, 8 * r), c = __shfl_sync(0xffffffffu, fq, 8 * r);
+      if (lane == i0 + r) { if (cpl >= 0) pv = a; if (cql >= 0) qv = c; }
+    }
+  }
   bool acc = true, tie = false;
   if (lane < gamma) {
-    long long tok = __ldcg(p.draft + b * p.draft_stride + lane);
-    const float u_a = __ldcg(p.u_acc + b * p.u_acc_stride + lane);
-    if (tok < 0 || tok >= V) { atomicOr(p.err_flag, kErrBadToken); tok = 0; }
-    const long long pcr = b * p.pc_req_stride + lane * p.pc.row_stride, qcr = b * p.qc_req_stride + lane * p.qc.row_stride;
-    const int cpl = __ldcg(p.pc.cnt + pcr), cql = __ldcg(p.qc.cnt + qcr);
-    float pv = 0.f, qv = 0.f;
-    if (cpl >= 0 && cpl <= kSparseCap && cpl <= p.pc.cap) {
-      for (int t = 0; t < cpl; ++t) pv = __ldcg(p.pc.idx + pcr * p.pc.cap + t) == tok ? __ldcg(p.pc.val + pcr * p.pc.cap + t) : pv;
-    } else {
-      pv = __ldcg(p.p + b * p.p_req_stride + lane * p.p_row_stride + tok);
-    }
-    if (cql >= 0 && cql <= kSparseCap && cql <= p.qc.cap) {
-      for (int t = 0; t < cql; ++t) qv = __ldcg(p.qc.idx + qcr * p.qc.cap + t) == tok ? __ldcg(p.qc.val + qcr * p.qc.cap + t) : qv;
-    } else {
-      qv = __ldcg(p.q + b * p.q_req_stride + lane * p.q_row_stride + tok);
-    }
     if (qv == 0.f) atomicOr(p.err_flag, kErrZeroQ);
     const float ratio = __fdiv_rn(pv, qv);
     const float thr = p.strict ? fminf(1.0f, ratio) : ratio;
@@ -135,12 +165,12 @@ __device__ inline int sparse_verify_warp(const VerifyParams& p, int b, int lane,
     sc->q_idx[t] = __ldcg(p.qc.idx + qcr * p.qc.cap + t);
     sc->q_val[t] = __ldcg(p.qc.val + qcr * p.qc.cap + t);
   }
-  int id[2]; float pv[2], r[2];
+  int id[2]; float pn[2], r[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int j = lane + 32 * h;
-    if (j < cp) { id[h] = __ldcg(p.pc.idx + pcr * p.pc.cap + j); pv[h] = __ldcg(p.pc.val + pcr * p.pc.cap + j); }
-    else { id[h] = 0x7fffffff; pv[h] = 0.f; }
+    if (j < cp) { id[h] = __ldcg(p.pc.idx + pcr * p.pc.cap + j); pn[h] = __ldcg(p.pc.val + pcr * p.pc.cap + j); }
+    else { id[h] = 0x7fffffff; pn[h] = 0.f; }
   }
   __syncwarp();
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -149,7 +179,7 @@ __device__ inline int sparse_verify_warp(const VerifyParams& p, int b, int lane,
     for (int h = 0; h < 2; ++h) {
       float qv = 0.f;
       if (use_q) for (int t = 0; t < cq; ++t) qv = (sc->q_idx[t] == id[h]) ? sc->q_val[t] : qv;
-      r[h] = use_q ? fmaxf(pv[h] - qv, 0.f) : pv[h];
+      r[h] = use_q ? fmaxf(pn[h] - qv, 0.f) : pn[h];
       if (r[h] > 0.f) {
         const unsigned long long pk = (static_cast<unsigned long long>(f2key(r[h])) << 32) | (0xffffffffu - static_cast<uint32_t>(id[h]));
         best = pk > best ? pk : best;
