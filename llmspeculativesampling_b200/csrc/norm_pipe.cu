@@ -698,12 +698,13 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
       }
       named_bar(bar_id, GT);
       const int b = gs.fv_req;
-#ifdef SD_FV_NOVERIFY
-      if (false) {
-#else
       if (b >= 0 && gw == 0) {
-#endif
+        const long long t_v0 = clock64();
         const int na = sparse_verify_warp(p.fv, b, lane, reinterpret_cast<SparseVerifyScratch*>(gs.a_key));
+        if (p.prof != nullptr && lane == 0) {                  // debug timeline: duration and end time of the in-kernel verify
+          p.prof[(static_cast<long long>(blockIdx.x) * 32 + 31) * 16 + g] = clock64() - t_v0;
+          p.prof[(static_cast<long long>(blockIdx.x) * 32 + 31) * 16 + 4 + g] = clock64();
+        }
         if (na >= 0 && lane == 0) sh.pend[atomicAdd(&sh.n_pend, 1)] = make_int2(b, na);
       }
     }

@@ -37,6 +37,23 @@ def step(i, mode):
             ops.verify(pr[:, g:], pr[:, :g], tok[:, :g], ua, uf, n_accepted=n_acc, next_tok=nxt, err=err, p_compact=c_p,
                        p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
 
+if os.environ.get("PROF"):
+    from llmspeculativesampling_b200 import _cabi
+    buf = torch.zeros(148 * 32 + 64, 16, dtype=torch.int64, device="cuda")
+    step(0, "fused"); step(1, "fused"); torch.cuda.synchronize()
+    _cabi.load().sd_debug_set_prof(buf.data_ptr())
+    step(2, "fused"); torch.cuda.synchronize()
+    _cabi.load().sd_debug_set_prof(None)
+    t = buf.cpu()[:148 * 32].view(148, 32, 16)
+    dur = t[:, 31, 0:4].flatten(); dur = dur[dur != 0].double()
+    ent = t[:, 0, 15]; ext = t[:, 1, 15]
+    vend = t[:, 31, 4:8].max(dim=1).values
+    last_item = t[:, :31, 11].max(dim=1).values
+    print(f"in-kernel verifies: {dur.numel()}, duration mean {dur.mean() / 1000:.1f} kcyc, max {dur.max() / 1000:.1f}; "
+          f"CTA lifetime mean {(ext - ent).double().mean() / 1000:.1f} kcyc, max {(ext - ent).double().max() / 1000:.1f}; "
+          f"last item done -> exit: max {((ext - last_item).double() / 1000).max():.1f} kcyc; "
+          f"verify end -> exit: min {((ext - vend)[vend != 0].double() / 1000).min():.1f} kcyc")
+    sys.exit(0)
 for mode in sys.argv[1:] or ["norm", "two", "fused"]:
     for i in range(n_sets):
         step(i, mode)
