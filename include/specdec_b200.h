@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SD_VERSION 100
+#define SD_VERSION 110
 #define SD_OK 0
 #define SD_EINVAL (-1)
 

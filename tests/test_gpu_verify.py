@@ -226,7 +226,7 @@ def test_fused_norm_sample_verify_equals_two_launches(cuda_lib, V, dtype, B, str
     u_acc[5, :] = 0.0; u_acc[5, 2] = 1.0 - 2 ** -24           # request 5 rejects at its tied row
     S = 16
     res = []
-    for fused in (False, True):
+    for fused in (False, True, "two-launch fallback"):     # the last: no persistent kernel -> the library launches norm + verify itself
         probs = torch.empty(B, R, V, device="cuda")
         tok = torch.zeros(B, R, dtype=torch.int64, device="cuda")
         cmp_rows = ops.CompactRows(B * R, "cuda")
@@ -241,7 +241,8 @@ def test_fused_norm_sample_verify_equals_two_launches(cuda_lib, V, dtype, B, str
                 seq_len.fill_(3); stats.zero_(); n_acc.fill_(-7); probs.fill_(-1.0)
                 ops.norm_sample_verify(logits.view(B * R, V), T, k, p, ur, probs.view(B * R, V), tok.view(-1), cmp_rows.view(), R, cnt,
                                        probs[:, gamma:], probs[:, :gamma], tok[:, :gamma], u_acc, u_fin, n_acc, nxt, err=err,
-                                       strict=strict, ratios=ratios, tokens=tokens, seq_len=seq_len, stats=stats, **kw)
+                                       strict=strict, ratios=ratios, tokens=tokens, seq_len=seq_len, stats=stats,
+                                       pipeline=fused is True, **kw)
                 assert int(cnt.abs().sum()) == 0
             else:
                 ops.norm_sample(logits.view(B * R, V), T, k, p, ur, probs_out=probs.view(B * R, V), tok_out=tok.view(-1), err=err,
@@ -252,8 +253,9 @@ def test_fused_norm_sample_verify_equals_two_launches(cuda_lib, V, dtype, B, str
         err.check()
         res.append((probs, tok, n_acc, nxt, ratios, tokens, seq_len, stats))
     names = ["probs", "tok", "n_acc", "next", "ratios", "tokens", "seq_len", "stats"]
-    for nm, a, b_ in zip(names, res[0], res[1]):
-        assert torch.equal(a, b_), f"{nm} differs between the fused launch and norm + verify"
+    for other in (1, 2):
+        for nm, a, b_ in zip(names, res[0], res[other]):
+            assert torch.equal(a, b_), f"{nm} differs between the fused entry point (arm {other}) and norm + verify"
     assert int(res[1][7][1]) == B and int(res[1][2][5]) == 2
 
 
