@@ -5,6 +5,7 @@
 Fixtures (all produced by code under /root/reference, imported in place by oracle/ref_loader.py):
   norm_logits.npz   (logits, T, k, p) -> probs  by reference sampling/utils.py:norm_logits
   max_fn.npz        x -> max_fn(x)              by reference sampling/utils.py:max_fn
+  bild_runs.json    end-to-end sampling.speculative_sampling.BiLD_sampling on the replay models
   spec_runs.json    end-to-end sampling.speculative_sampling on the replay models with the
                     uniform tape: emitted token ids, acc_len per iteration, acc_rate
 """
@@ -35,6 +36,30 @@ def _logits(V, rows, scale, seed, dtype):
     x = torch.randn(rows, V, generator=g) * scale
     dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[dtype]
     return x.to(dt)
+
+
+BILD_CASES = [   # V, top_k, top_p, T, gamma, max_len, seed, noise, fallback_thres, rollback_thres
+    (1000, 20, 0.9, 1.0, 4, 40, 31, 0.5, 0.6, 3.0), (32000, 20, 0.9, 0.8, 4, 32, 32, 0.5, 0.5, 2.0),
+    (500, 0, 0.0, 1.0, 4, 40, 33, 0.5, 0.3, 2.0), (777, 0, 0.9, 1.3, 3, 32, 34, 0.3, 0.4, 4.0),
+    (900, 5, 0.0, 0.7, 5, 40, 35, 0.8, 0.9, 1.0), (1000, 20, 0.9, 1.0, 8, 40, 36, 0.0, 0.2, 5.0),
+]
+
+
+def write_bild():
+    """bild_runs.json: the reference's BiLD_sampling (speculative_sampling.py:1718-1873) on the replay models."""
+    runs = []
+    for (V, k, p, T, gamma, max_len, seed, noise, fb, rb) in BILD_CASES:
+        d, t = replay_model.make_pair(V, seed=seed, noise=noise)
+        prefix = torch.randint(3, V, (1, 7), generator=torch.Generator().manual_seed(seed))
+        tp = tape.make_tape(seed, max_len + 1, gamma)
+        out, det = ref_loader.run_reference_bild(prefix, d, t, max_len, gamma, fb, rb, T, k, p, tape=tp)
+        runs.append(dict(V=V, top_k=k, top_p=p, temperature=T, gamma=gamma, max_len=max_len, seed=seed, noise=noise,
+                         fallback_thres=fb, rollback_thres=rb, prefix=prefix[0].tolist(), tokens=out[0].tolist(),
+                         acc_len=[int(a) for a in det["acc_len"]], target_call_times=int(det["target_call_times"]),
+                         approx_call_times=int(det["approx_call_times"])))
+        print("bild", V, k, p, T, gamma, fb, rb, "checks", det["target_call_times"], "draft tokens", det["approx_call_times"])
+    with open(os.path.join(OUT, "bild_runs.json"), "w") as f:
+        json.dump(runs, f)
 
 
 def main():
@@ -73,6 +98,7 @@ def main():
         print("run", V, k, p, T, gamma, "mean acc", np.mean(det["acc_len"]))
     with open(os.path.join(OUT, "spec_runs.json"), "w") as f:
         json.dump(runs, f)
+    write_bild()
     print("wrote", os.listdir(OUT))
 
 

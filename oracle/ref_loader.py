@@ -164,3 +164,74 @@ def run_reference(prefix, approx_model, target_model, max_len, gamma, temperatur
         out, d = pkg.speculative_sampling(prefix, a, t, eos_token_id, None, max_len, gamma=gamma,
                                           temperature=temperature, top_k=top_k, top_p=top_p, details=True)
     return out, d
+
+
+class BiLDTapeRNG:
+    """Feeds the ``sample`` calls of the reference's BiLD_sampling from a (cycles, 2*gamma+2) tape: draft tokens of a
+    check cycle use u_draft[0..], the sample that ``target.generate(x, 1)`` throws away uses u_discard (recognised
+    because the target's forward ran just before it), the target's own token uses u_final and closes the cycle."""
+
+    def __init__(self, tape: torch.Tensor, gamma: int):
+        self.tape, self.gamma = tape, gamma
+        self.cycle = 0
+        self.n_draft = 0
+        self.discard_pending = False
+
+    def target_called(self):
+        self.discard_pending = True
+
+    def _tok(self, probs, u):
+        tok = ref_ops.icdf_sample(probs.reshape(-1), float(u))
+        return torch.tensor([[tok]], dtype=torch.long, device=probs.device)
+
+    def kv_sample(self, probs: torch.Tensor, num_samples: int = 1):
+        if self.discard_pending:
+            self.discard_pending = False
+            return self._tok(probs, self.tape[self.cycle, self.gamma])
+        u = self.tape[self.cycle, self.n_draft]
+        self.n_draft += 1
+        return self._tok(probs, u)
+
+    def final_sample(self, probs: torch.Tensor, num_samples: int = 1):
+        u = self.tape[self.cycle, 2 * self.gamma + 1]
+        self.cycle += 1
+        self.n_draft = 0
+        return self._tok(probs, u)
+
+
+class _NotifyForward(torch.nn.Module):
+    """Transparent wrapper that tells the tape when the target model runs."""
+
+    def __init__(self, inner, callback):
+        super().__init__()
+        self.inner, self.callback = inner, callback
+        self.config = inner.config
+
+    @property
+    def device(self):
+        return self.inner.device
+
+    def forward(self, *args, **kwargs):
+        self.callback()
+        return self.inner(*args, **kwargs)
+
+
+def run_reference_bild(prefix, approx_model, target_model, max_len, gamma, fallback_thres, rollback_thres, temperature,
+                       top_k, top_p, tape=None, seed=0, eos_token_id=-1, legacy_models=True):
+    """Run the real ``sampling.speculative_sampling.BiLD_sampling`` (speculative_sampling.py:1718-1873) on the tape."""
+    if tape is None:
+        tape = tape_mod.make_tape(seed, max_len + 1, gamma)
+    rng = BiLDTapeRNG(tape, gamma)
+    a = approx_model if legacy_models else LegacyCacheAdapter(approx_model)
+    t = target_model if legacy_models else LegacyCacheAdapter(target_model)
+    t = _NotifyForward(t, rng.target_called)
+    pkg = load_package()
+    kv, ss = sys.modules["sampling.kvcache_model"], sys.modules["sampling.speculative_sampling"]
+    saved = (kv.sample, ss.sample)
+    try:
+        kv.sample, ss.sample = rng.kv_sample, rng.final_sample
+        out, d = ss.BiLD_sampling(prefix, a, t, gamma, eos_token_id, None, fallback_thres, rollback_thres, max_len,
+                                  temperature=temperature, top_k=top_k, top_p=top_p, details=True)
+    finally:
+        kv.sample, ss.sample = saved
+    return out, d

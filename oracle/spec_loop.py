@@ -7,6 +7,7 @@
 * ``speculative_sampling``    -> /root/reference/sampling/speculative_sampling.py:1934-2043
 * ``speculative_sampling_v2`` -> /root/reference/sampling/speculative_sampling.py:2118-2185
 * ``autoregressive_sampling`` -> /root/reference/sampling/autoregressive_sampling.py:9-61
+* ``bild_sampling``           -> /root/reference/sampling/speculative_sampling.py:1718-1873 (BiLD_sampling, decoder-only)
 
 Randomness comes from a uniform tape (oracle/tape.py) instead of torch's global RNG.
 Works with ``oracle.replay_model.ReplayLM`` (legacy tuple cache) and with stock Hugging Face
@@ -183,3 +184,69 @@ def autoregressive_sampling(x: torch.Tensor, model, N: int, eos_token_id: Option
         if eos_token_id is not None and tok == eos_token_id:
             break
     return x
+
+
+@torch.no_grad()
+def bild_sampling(prefix: torch.Tensor, approx_model, target_model, max_len: int, gamma: int, fallback_thres: float,
+                  rollback_thres: float, temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0,
+                  eos_token_id: Optional[int] = None, tape: Optional[torch.Tensor] = None, seed: int = 0):
+    """Big-Little decoding, speculative_sampling.py:1718-1873 (decoder-only branch): the draft model emits one token at
+    a time; the target only looks when the draft is unsure (max q < fallback_thres, :1784) or gamma tokens are unchecked;
+    it keeps tokens while -log p[token] <= rollback_thres (:1800), then ALWAYS samples its own next token (:1812).
+    One tape row per check cycle: u_draft[i] for the i-th draft token of the cycle, u_discard for the sample that
+    target.generate(x, 1) throws away (:1788), u_final for the target's token (:1812).
+    Returns (tokens (1, n), details)."""
+    assert prefix.shape[0] == 1, "input batch size must be 1"               # :1729
+    seq_len = prefix.shape[1]
+    T = seq_len + max_len
+    if tape is None:
+        tape = tape_mod.make_tape(seed, max_len + 1, gamma)
+    ori_eos = int((prefix == eos_token_id).sum()) if eos_token_id is not None else 0
+    approx = OracleStepper(approx_model, temperature, top_k, top_p)
+    target = OracleStepper(target_model, temperature, top_k, top_p)
+    acc_len: List[int] = []
+    last_check = seq_len - 1                                                # :1759
+    cycle, n_draft = 0, 0
+    approx_calls = target_calls = 0
+    out = prefix
+    while prefix.shape[1] < T:                                              # :1764
+        u_draft, u_discard, _, u_final = tape_mod.split(tape[cycle], gamma)
+        x = approx.generate(prefix, 1, [u_draft[n_draft]])                  # :1772
+        n_draft += 1
+        approx_calls += 1
+        q_last = approx.hist[-1]                                            # :1778 (q[:, -1, :])
+        if float(q_last.max()) < fallback_thres or x.shape[1] - last_check - 1 >= gamma:   # :1784
+            _ = target.generate(x, 1, [u_discard])                          # :1788
+            target_calls += 1
+            p = target.hist
+            n = x.shape[1] - 1
+            l = 0
+            for i in range(last_check, x.shape[1] - 1):                     # :1797-1803
+                j = int(x[0, i + 1])
+                if float(-p[i, j].log()) > rollback_thres:
+                    n = i
+                    break
+                l += 1
+            acc_len.append(l)
+            prefix = x[:, :n + 1]                                           # :1806
+            approx.rollback(n + 1)                                          # :1811
+            tok = ref_ops.icdf_sample(p[n], float(u_final))                 # :1812
+            target.rollback(n + 1)                                          # :1813
+            last_check = n + 1
+            prefix = torch.cat([prefix, torch.tensor([[tok]], dtype=prefix.dtype)], dim=1)   # :1817
+            cycle += 1
+            n_draft = 0
+        else:
+            prefix = x                                                      # :1826
+        out = prefix
+        if eos_token_id is not None:                                        # :1833-1841
+            mask = out == eos_token_id
+            if int(mask.sum()) > ori_eos:
+                keep = torch.cumsum(mask.float(), dim=1) < ori_eos + 1
+                end = int(keep.sum())
+                if end < keep.shape[1]:
+                    keep[:, end] = True
+                out = out[keep][None, :]
+                break
+    details = dict(acc_len=acc_len, target_call_times=target_calls, approx_call_times=approx_calls, cycles=cycle)
+    return out, details

@@ -18,6 +18,33 @@ def _pair(V, seed, noise, device="cuda", dtype=torch.float32):
     return replay_model.make_pair(V, seed=seed, noise=noise, device=device, dtype=dtype)
 
 
+def test_bild_drop_in_matches_reference_golden_runs(cuda_lib):
+    """BiLD_sampling on the GPU building blocks vs golden runs of the UNMODIFIED reference
+    (tests/golden/bild_runs.json): same tokens, accepted run lengths and draft / target call counts."""
+    from llmspeculativesampling_b200.sampling import BiLD_sampling
+    runs = json.load(open(os.path.join(GOLD, "bild_runs.json")))
+    for r in runs:
+        d, t = _pair(r["V"], r["seed"], r["noise"])
+        prefix = torch.tensor([r["prefix"]], device="cuda")
+        tp = tape.make_tape(r["seed"], r["max_len"] + 1, r["gamma"])
+        out, det = BiLD_sampling(prefix, d, t, r["gamma"], None, None, r["fallback_thres"], r["rollback_thres"], r["max_len"],
+                                 r["temperature"], r["top_k"], r["top_p"], details=True, uniforms=tp)
+        assert out[0].tolist() == r["tokens"], f"V={r['V']} k={r['top_k']} p={r['top_p']} gamma={r['gamma']}"
+        assert det["acc_len"] == r["acc_len"]
+        assert (det["target_call_times"], det["approx_call_times"]) == (r["target_call_times"], r["approx_call_times"])
+    # EOS cut (:1833-1841): the output ends at the first new EOS
+    r = runs[0]
+    d, t = _pair(r["V"], r["seed"], r["noise"])
+    eos = r["tokens"][len(r["prefix"]) + 5]
+    tp = tape.make_tape(r["seed"], r["max_len"] + 1, r["gamma"])
+    out = BiLD_sampling(torch.tensor([r["prefix"]], device="cuda"), d, t, r["gamma"], eos, None, r["fallback_thres"],
+                        r["rollback_thres"], r["max_len"], r["temperature"], r["top_k"], r["top_p"], uniforms=tp)
+    want, _ = spec_loop.bild_sampling(torch.tensor([r["prefix"]]), *replay_model.make_pair(r["V"], seed=r["seed"], noise=r["noise"]),
+                                      r["max_len"], r["gamma"], r["fallback_thres"], r["rollback_thres"], r["temperature"],
+                                      r["top_k"], r["top_p"], eos_token_id=eos, tape=tp)
+    assert out[0].tolist() == want[0].tolist() and out[0, -1].item() == eos
+
+
 def test_drop_in_matches_reference_golden_runs(cuda_lib):
     from llmspeculativesampling_b200.sampling import speculative_sampling
     runs = json.load(open(os.path.join(GOLD, "spec_runs.json")))

@@ -53,6 +53,35 @@ def test_spec_loop_restatement_matches_reference_runs(residual):
         assert abs(det["acc_rate"] - r["acc_rate"]) < 1e-6
 
 
+def test_bild_restatement_matches_reference_runs():
+    """The reference's BiLD_sampling (speculative_sampling.py:1718-1873, tape-driven, unmodified code) vs the oracle's
+    restatement: tokens, accepted run lengths and the number of draft / target calls."""
+    runs = json.load(open(os.path.join(GOLD, "bild_runs.json")))
+    torch.set_num_threads(1)
+    for r in runs:
+        if r["V"] > 4096:
+            continue                                    # keep the CPU suite short (covered on the GPU side)
+        d, t = replay_model.make_pair(r["V"], seed=r["seed"], noise=r["noise"])
+        tp = tape.make_tape(r["seed"], r["max_len"] + 1, r["gamma"])
+        out, det = spec_loop.bild_sampling(torch.tensor([r["prefix"]]), d, t, r["max_len"], r["gamma"], r["fallback_thres"],
+                                           r["rollback_thres"], r["temperature"], r["top_k"], r["top_p"], tape=tp)
+        assert out[0].tolist() == r["tokens"], r
+        assert det["acc_len"] == r["acc_len"]
+        assert (det["target_call_times"], det["approx_call_times"]) == (r["target_call_times"], r["approx_call_times"])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the dev container")
+def test_bild_oracle_matches_live_reference():
+    torch.set_num_threads(1)
+    d, t = replay_model.make_pair(640, seed=44, noise=0.6)
+    prefix = torch.randint(3, 640, (1, 6), generator=torch.Generator().manual_seed(44))
+    for (fb, rb, k, p) in [(0.5, 2.5, 20, 0.9), (0.25, 3.0, 0, 0.0)]:
+        tp = tape.make_tape(44, 31, 4)
+        a, da = ref_loader.run_reference_bild(prefix, d, t, 30, 4, fb, rb, 1.0, k, p, tape=tp)
+        b, db = spec_loop.bild_sampling(prefix, d, t, 30, 4, fb, rb, 1.0, k, p, tape=tp)
+        assert torch.equal(a, b) and [int(x) for x in da["acc_len"]] == db["acc_len"]
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the dev container")
 def test_oracle_matches_live_reference():
     torch.set_num_threads(1)
