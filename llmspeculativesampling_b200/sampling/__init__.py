@@ -1,10 +1,12 @@
 """Drop-in surface of the reference's `sampling` package (/root/reference/sampling/__init__.py:1-7)
-for the draft-and-verify hot path, plus `BiLD_sampling`.  The multi-draft / beam research
-variants of the reference are out of scope and raise NotImplementedError if called."""
+for the draft-and-verify hot path, plus `multi_speculative_sampling(strategy='iid')` and `BiLD_sampling`
+(SURVEY.md §8f rows N2, N3).  The beam / tree research variants of the reference are out of scope (SURVEY.md §2 rows
+7-11) and raise NotImplementedError if called."""
 from .speculative_sampling import speculative_sampling, speculative_sampling_v2
 from .autoregressive_sampling import autoregressive_sampling
 from .kvcache_model import KVCacheModel
 from .bild import BiLD_sampling
+from .multi import multi_speculative_sampling
 from .utils import norm_logits, top_k_top_p_filter, sample, max_fn
 
 
@@ -15,7 +17,6 @@ def _out_of_scope(name):
     return f
 
 
-multi_speculative_sampling = _out_of_scope("multi_speculative_sampling")
 beam_speculative_sampling = _out_of_scope("beam_speculative_sampling")
 beam_speculative_sampling_v2 = _out_of_scope("beam_speculative_sampling_v2")
 mjsd_speculative_sampling = _out_of_scope("mjsd_speculative_sampling")

@@ -110,9 +110,16 @@ class KVCacheModel:
         return self._prob_buf[:, cur - 1]
 
     @torch.no_grad()
-    def generate(self, input: torch.Tensor, gamma: int, uniforms: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """gamma x (forward, sample, append) — kvcache_model.py:279-293.  uniforms: (gamma, B) or None."""
+    def generate(self, input: torch.Tensor, gamma: int, uniforms: Optional[torch.Tensor] = None, multi: int = 1,
+                 strategy: str = "beam") -> torch.Tensor:
+        """gamma x (forward, sample, append) — kvcache_model.py:279-293.  uniforms: (gamma, B) or None.
+        `multi=W, strategy='iid'` (kvcache_model.py:272-276): the single prefix is drafted W times independently."""
         x = input
+        if multi > 1:
+            if strategy != "iid":
+                raise NotImplementedError("only strategy='iid' of the multi-draft path is built (beam needs HF 4.35 beam APIs)")
+            if x.shape[0] == 1:
+                x = x.repeat(multi, 1)
         for i in range(gamma):
             q = self._forward_with_kvcache(x)
             u = uniforms[i].reshape(-1) if uniforms is not None else torch.rand(x.shape[0], device=x.device)
@@ -122,10 +129,14 @@ class KVCacheModel:
         return x
 
     @torch.no_grad()
-    def rollback(self, end_pos: int, choice=None) -> None:
-        """kvcache_model.py:360-431 with choice=None: crop cache and probability history to end_pos.
-        On static buffers this is a counter update; stale rows are overwritten by the next forward."""
-        if choice is not None:
-            raise NotImplementedError("rollback(choice=...) belongs to multi_speculative_sampling (out of scope)")
+    def rollback(self, end_pos: int, choice: Optional[int] = None) -> None:
+        """kvcache_model.py:360-436: crop cache and probability history to end_pos.  On static buffers this is a counter
+        update; stale rows are overwritten by the next forward.  With `choice` (:390-396, :433-436: keep draft `choice`
+        only — the next forward expands it to all rows again, :180-200) the kept positions of that row's KV cache are
+        copied to every row of the static buffers."""
         assert self._stepper is not None and self._n > 0                   # reference: assert self._past_key_values
         self._n = min(self._n, int(end_pos))
+        if choice is not None and self._stepper.B > 1:
+            c, n = int(choice), self._n
+            for t in self._stepper.cache.k + self._stepper.cache.v:
+                t[:, :, :n].copy_(t[c:c + 1, :, :n].expand(t.shape[0], -1, -1, -1).clone())

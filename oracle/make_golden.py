@@ -5,6 +5,7 @@
 Fixtures (all produced by code under /root/reference, imported in place by oracle/ref_loader.py):
   norm_logits.npz   (logits, T, k, p) -> probs  by reference sampling/utils.py:norm_logits
   max_fn.npz        x -> max_fn(x)              by reference sampling/utils.py:max_fn
+  multi_runs.json   end-to-end sampling.speculative_sampling.multi_speculative_sampling(strategy='iid')
   bild_runs.json    end-to-end sampling.speculative_sampling.BiLD_sampling on the replay models
   spec_runs.json    end-to-end sampling.speculative_sampling on the replay models with the
                     uniform tape: emitted token ids, acc_len per iteration, acc_rate
@@ -62,6 +63,32 @@ def write_bild():
         json.dump(runs, f)
 
 
+MULTI_CASES = [   # V, top_k, top_p, T, gamma, width, max_len, seed, noise
+    (1000, 20, 0.9, 1.0, 4, 3, 32, 41, 0.5), (32000, 20, 0.9, 0.8, 4, 4, 24, 42, 0.5), (500, 0, 0.0, 1.0, 4, 4, 32, 43, 0.8),
+    (777, 0, 0.9, 1.3, 3, 2, 32, 44, 0.3), (900, 5, 0.0, 0.7, 5, 3, 32, 45, 1.5), (1000, 20, 0.9, 1.0, 2, 8, 24, 46, 2.0),
+]
+
+
+def multi_tape(seed: int, iterations: int, gamma: int, width: int) -> torch.Tensor:
+    return torch.rand(iterations, ref_loader.multi_block(gamma, width), generator=torch.Generator().manual_seed(seed))
+
+
+def write_multi():
+    """multi_runs.json: the reference's multi_speculative_sampling(strategy='iid') (speculative_sampling.py:1379-1716)."""
+    runs = []
+    for (V, k, p, T, gamma, width, max_len, seed, noise) in MULTI_CASES:
+        d, t = replay_model.make_pair(V, seed=seed, noise=noise)
+        prefix = torch.randint(3, V, (1, 7), generator=torch.Generator().manual_seed(seed))
+        tp = multi_tape(seed, max_len + 1, gamma, width)
+        out, det = ref_loader.run_reference_multi(prefix, d, t, max_len, gamma, width, T, k, p, tp)
+        runs.append(dict(V=V, top_k=k, top_p=p, temperature=T, gamma=gamma, width=width, max_len=max_len, seed=seed,
+                         noise=noise, prefix=prefix[0].tolist(), tokens=out[0].tolist(),
+                         acc_len=[int(a) for a in det["acc_len"]], acc_rate=float(det["acc_rate"])))
+        print("multi", V, k, p, T, gamma, width, "mean acc len", np.mean(det["acc_len"]))
+    with open(os.path.join(OUT, "multi_runs.json"), "w") as f:
+        json.dump(runs, f)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -99,6 +126,7 @@ def main():
     with open(os.path.join(OUT, "spec_runs.json"), "w") as f:
         json.dump(runs, f)
     write_bild()
+    write_multi()
     print("wrote", os.listdir(OUT))
 
 

@@ -235,3 +235,70 @@ def run_reference_bild(prefix, approx_model, target_model, max_len, gamma, fallb
     finally:
         kv.sample, ss.sample = saved
     return out, d
+
+
+def multi_block(gamma: int, width: int) -> int:
+    """Uniforms one iteration of multi_speculative_sampling(strategy='iid') can consume."""
+    return 2 * width * gamma + width + 1
+
+
+class MultiTapeRNG:
+    """Feeds the reference's multi_speculative_sampling (iid): per iteration a block of 2*W*gamma + W + 1 uniforms —
+    [gamma draft calls x W rows | W discarded target samples | the accept tests IN THE ORDER THE REFERENCE DRAWS THEM
+    (draft 0 position 0, 1, .. until its first reject, then draft 1, ..; speculative_sampling.py:1616-1634) | final]."""
+
+    def __init__(self, tape: torch.Tensor, gamma: int, width: int):
+        self.tape, self.gamma, self.width = tape, gamma, width
+        self.it = 0
+        self.n_kv = 0
+        self.n_rand = 0
+
+    def _rows(self, probs, us):
+        toks = [ref_ops.icdf_sample(probs[w], float(us[w])) for w in range(probs.shape[0])]
+        return torch.tensor(toks, dtype=torch.long, device=probs.device).view(-1, 1)
+
+    def kv_sample(self, probs: torch.Tensor, num_samples: int = 1):
+        W = self.width
+        assert probs.shape[0] == W
+        us = self.tape[self.it, self.n_kv * W:(self.n_kv + 1) * W]          # calls 0..gamma-1: drafts, call gamma: discarded
+        self.n_kv += 1
+        return self._rows(probs, us)
+
+    def final_sample(self, probs: torch.Tensor, num_samples: int = 1):
+        u = self.tape[self.it, multi_block(self.gamma, self.width) - 1]
+        tok = self._rows(probs.reshape(1, -1), [u])            # raises on an empty row: the reference then retries with p
+        self.it += 1
+        self.n_kv = 0
+        self.n_rand = 0
+        return tok
+
+    def rand(self, *size, **kw):
+        W, g = self.width, self.gamma
+        u = self.tape[self.it, g * W + W + self.n_rand]
+        self.n_rand += 1
+        return u.reshape(1).clone().to(kw.get("device", "cpu"))
+
+
+def run_reference_multi(prefix, approx_model, target_model, max_len, gamma, width, temperature, top_k, top_p, tape,
+                        eos_token_id=-1, legacy_models=True):
+    """Run the real ``multi_speculative_sampling(strategy='iid')`` (speculative_sampling.py:1379-1716) on the tape."""
+    rng = MultiTapeRNG(tape, gamma, width)
+    a = approx_model if legacy_models else LegacyCacheAdapter(approx_model)
+    t = target_model if legacy_models else LegacyCacheAdapter(target_model)
+    load_package()
+    kv, ss = sys.modules["sampling.kvcache_model"], sys.modules["sampling.speculative_sampling"]
+    saved = (kv.sample, ss.sample, ss.torch)
+    real_torch = ss.torch
+
+    class _TorchProxy:
+        def __getattr__(self, name):
+            return rng.rand if name == "rand" else getattr(real_torch, name)
+
+    try:
+        kv.sample, ss.sample, ss.torch = rng.kv_sample, rng.final_sample, _TorchProxy()
+        out, d = ss.multi_speculative_sampling(prefix, a, t, eos_token_id, None, max_len, gamma=gamma, width=width,
+                                               strategy="iid", temperature=temperature, top_k=top_k, top_p=top_p,
+                                               details=True)
+    finally:
+        kv.sample, ss.sample, ss.torch = saved
+    return out, d

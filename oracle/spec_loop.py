@@ -7,6 +7,8 @@
 * ``speculative_sampling``    -> /root/reference/sampling/speculative_sampling.py:1934-2043
 * ``speculative_sampling_v2`` -> /root/reference/sampling/speculative_sampling.py:2118-2185
 * ``autoregressive_sampling`` -> /root/reference/sampling/autoregressive_sampling.py:9-61
+* ``multi_speculative_sampling`` -> /root/reference/sampling/speculative_sampling.py:1379-1716 (strategy='iid'),
+                                 with kvcache_model.py:180-200,272-276 (multi) and :390-396,433-436 (rollback choice)
 * ``bild_sampling``           -> /root/reference/sampling/speculative_sampling.py:1718-1873 (BiLD_sampling, decoder-only)
 
 Randomness comes from a uniform tape (oracle/tape.py) instead of torch's global RNG.
@@ -249,4 +251,139 @@ def bild_sampling(prefix: torch.Tensor, approx_model, target_model, max_len: int
                 out = out[keep][None, :]
                 break
     details = dict(acc_len=acc_len, target_call_times=target_calls, approx_call_times=approx_calls, cycles=cycle)
+    return out, details
+
+
+class MultiStepper:
+    """KVCacheModel with a batch of W drafts (legacy tuple caches): kvcache_model.py:141-252 incl. the cache / history
+    expansion to W rows (:180-200, :240-245) and rollback(end_pos, choice) (:390-396, :433-436)."""
+
+    def __init__(self, model, temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0):
+        self.model = model
+        self.kv = None
+        self.hist: Optional[torch.Tensor] = None                            # (B, seq, V)
+        self.temperature, self.top_k, self.top_p = temperature, top_k, top_p
+
+    def _norm(self, logits: torch.Tensor) -> torch.Tensor:                  # (B, n, V) -> probabilities, one row per call
+        B, n, _ = logits.shape
+        return torch.stack([torch.cat([ref_ops.norm_probs(logits[b, i:i + 1].float(), self.temperature, self.top_k, self.top_p)
+                                       for i in range(n)], 0) for b in range(B)], 0)
+
+    @torch.no_grad()
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        B = ids.shape[0]
+        if self.kv is None:
+            out = self.model(ids, use_cache=True)
+            self.hist = self._norm(out.logits)
+        else:
+            if self.kv[0][0].shape[0] < B:                                  # :180-190
+                self.kv = tuple((k.repeat(B, 1, 1, 1), v.repeat(B, 1, 1, 1)) for k, v in self.kv)
+            out = self.model(ids[:, _cached_len(self.kv):], past_key_values=self.kv, use_cache=True)
+            new = self._norm(out.logits)
+            if self.hist.shape[0] < B:                                      # :240-244
+                self.hist = self.hist.repeat(B // self.hist.shape[0], 1, 1)
+            self.hist = torch.cat([self.hist, new], dim=1)
+        self.kv = out.past_key_values
+        return self.hist[:, -1]
+
+    def generate(self, ids: torch.Tensor, gamma: int, uniforms) -> torch.Tensor:
+        """uniforms[i][b]: the uniform of row b's i-th token."""
+        x = ids
+        for i in range(gamma):
+            q = self.forward(x)
+            toks = [ref_ops.icdf_sample(q[b], float(uniforms[i][b])) for b in range(x.shape[0])]
+            x = torch.cat([x, torch.tensor(toks, dtype=x.dtype).view(-1, 1)], dim=1)
+        return x
+
+    def rollback(self, end_pos: int, choice: int) -> None:
+        self.kv = tuple((k[choice:choice + 1, :, :end_pos, :], v[choice:choice + 1, :, :end_pos, :]) for k, v in self.kv)
+        self.hist = self.hist[choice:choice + 1, :end_pos]
+
+
+def multi_block(gamma: int, width: int) -> int:
+    return 2 * width * gamma + width + 1
+
+
+@torch.no_grad()
+def multi_speculative_sampling(prefix: torch.Tensor, approx_model, target_model, max_len: int, gamma: int, width: int,
+                               temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0,
+                               eos_token_id: Optional[int] = None, tape: Optional[torch.Tensor] = None):
+    """W independent drafts per iteration, one target pass over all of them, the first draft with the longest accepted
+    run wins (speculative_sampling.py:1612-1640, accept iff r < min(1, p/q)).  One tape row of multi_block(gamma, W)
+    uniforms per iteration: [gamma x W draft | W discarded target samples | accept tests in the order the reference
+    draws them | final].  Returns (tokens (1, n), details)."""
+    assert prefix.shape[0] == 1, "input batch size must be 1"
+    W, g = width, gamma
+    T = prefix.shape[1] + max_len
+    ori_eos = int((prefix == eos_token_id).sum()) if eos_token_id is not None else 0
+    approx = MultiStepper(approx_model, temperature, top_k, top_p)
+    target = MultiStepper(target_model, temperature, top_k, top_p)
+    acc_len: List[int] = []
+    acc_rate: List[float] = []
+    choices: List[int] = []
+    out = prefix
+    it = 0
+    while out.shape[1] < T:                                                 # :1441
+        blk = tape[it]
+        L = out.shape[1]
+        x = approx.generate(out.repeat(W, 1), g, blk[:g * W].view(g, W))    # :1531-1534
+        q = approx.hist[:, L - 1:, :]                                       # :1542
+        _ = target.generate(x, 1, blk[g * W:g * W + W].view(1, W))          # :1558 (W samples discarded)
+        p = target.hist
+        for w in range(W):                                                  # :1600-1609
+            for i in range(g):
+                j = int(x[w, L + i])
+                qv = float(q[w, i, j])
+                r = float((p[w, L + i - 1, j] / q[w, i, j])) if qv != 0 else 0.0
+                acc_rate.append(0.0 if qv == 0 else min(r, 1.0))
+        n_rand = 0
+        is_all_accept = False
+        max_n, max_l, choice = L - 1, 0, 0
+        for w in range(W):                                                  # :1616-1640
+            cur_n, cur_l, cur_all = L - 1, 0, True
+            for i in range(g):
+                r = blk[g * W + W + n_rand]
+                n_rand += 1
+                j = int(x[w, L + i])
+                thr = torch.min(torch.tensor([1.0]), p[w, L + i - 1, j] / q[w, i, j])
+                if bool(r < thr):
+                    cur_l += 1
+                    cur_n += 1
+                else:
+                    cur_all = False
+                    break
+            if cur_l > max_l:
+                max_n, max_l, choice = cur_n, cur_l, w
+                if cur_all:
+                    is_all_accept = True
+                    break
+        acc_len.append(max_l)
+        choices.append(choice)
+        n = max_n
+        out = x[choice:choice + 1, :n + 1]                                  # :1644
+        approx.rollback(n + 1, choice)                                      # :1646
+        u_final = float(blk[multi_block(g, W) - 1])
+        if is_all_accept:
+            tok = ref_ops.icdf_sample(p[choice, -1], u_final)               # :1649
+            target.rollback(n + 2, choice)
+        else:
+            new_p = ref_ops.max_fn(p[choice:choice + 1, n, :] - q[choice:choice + 1, max_l, :])   # :1657
+            try:
+                tok = ref_ops.icdf_sample(new_p[0], u_final)
+            except Exception:                                               # :1661-1663 (empty residual)
+                tok = ref_ops.icdf_sample(p[choice, n], u_final)
+            target.rollback(n + 1, choice)
+        out = torch.cat([out, torch.tensor([[tok]], dtype=out.dtype)], dim=1)   # :1677
+        it += 1
+        if eos_token_id is not None:                                        # :1681-1689
+            mask = out == eos_token_id
+            if int(mask.sum()) > ori_eos:
+                keep = torch.cumsum(mask.float(), dim=1) < ori_eos + 1
+                end = int(keep.sum())
+                if end < keep.shape[1]:
+                    keep[:, end] = True
+                out = out[keep][None, :]
+                break
+    details = dict(acc_len=acc_len, acc_rate=float(np.mean(acc_rate)) if acc_rate else 0.0, choices=choices,
+                   target_call_times=it, approx_call_times=it)
     return out, details

@@ -18,6 +18,25 @@ def _pair(V, seed, noise, device="cuda", dtype=torch.float32):
     return replay_model.make_pair(V, seed=seed, noise=noise, device=device, dtype=dtype)
 
 
+def test_multi_draft_drop_in_matches_reference_golden_runs(cuda_lib):
+    """multi_speculative_sampling(strategy='iid') on the GPU building blocks vs golden runs of the
+    UNMODIFIED reference (tests/golden/multi_runs.json): same tokens and longest accepted runs."""
+    from oracle import make_golden
+    from llmspeculativesampling_b200.sampling import multi_speculative_sampling
+    runs = json.load(open(os.path.join(GOLD, "multi_runs.json")))
+    for r in runs:
+        d, t = _pair(r["V"], r["seed"], r["noise"])
+        prefix = torch.tensor([r["prefix"]], device="cuda")
+        tp = make_golden.multi_tape(r["seed"], r["max_len"] + 1, r["gamma"], r["width"])
+        out, det = multi_speculative_sampling(prefix, d, t, None, None, r["max_len"], r["gamma"], r["width"], None, "iid",
+                                              None, 0.4, r["temperature"], r["top_k"], r["top_p"], details=True, uniforms=tp)
+        assert out[0].tolist() == r["tokens"], f"V={r['V']} k={r['top_k']} p={r['top_p']} gamma={r['gamma']} W={r['width']}"
+        assert det["acc_len"] == r["acc_len"]
+        assert abs(det["acc_rate"] - r["acc_rate"]) < 1e-5
+    with pytest.raises(NotImplementedError):
+        multi_speculative_sampling(prefix, d, t, None, None, 8, strategy="beam")
+
+
 def test_bild_drop_in_matches_reference_golden_runs(cuda_lib):
     """BiLD_sampling on the GPU building blocks vs golden runs of the UNMODIFIED reference
     (tests/golden/bild_runs.json): same tokens, accepted run lengths and draft / target call counts."""

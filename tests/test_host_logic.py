@@ -87,7 +87,7 @@ def test_drop_in_signatures_follow_the_reference():
     assert kv[:5] == ["self", "model", "temperature", "top_k", "top_p"]                          # reference kvcache_model.py:24
     ar = list(inspect.signature(sampling.autoregressive_sampling).parameters)
     assert ar[:8] == ["x", "model", "N", "eos_token_id", "temperature", "top_k", "top_p", "pad_token_id"]
-    for name in ["multi_speculative_sampling", "mjsd_speculative_sampling", "beam_speculative_sampling"]:
+    for name in ["random_width_beam_sampling", "mjsd_speculative_sampling", "beam_speculative_sampling"]:
         with pytest.raises(NotImplementedError):
             getattr(sampling, name)()
 

@@ -53,6 +53,24 @@ def test_spec_loop_restatement_matches_reference_runs(residual):
         assert abs(det["acc_rate"] - r["acc_rate"]) < 1e-6
 
 
+def test_multi_draft_restatement_matches_reference_runs():
+    """The reference's multi_speculative_sampling(strategy='iid') (speculative_sampling.py:1379-1716, tape-driven,
+    unmodified code) vs the oracle's restatement: tokens, longest accepted run per iteration, mean acceptance."""
+    from oracle import make_golden
+    runs = json.load(open(os.path.join(GOLD, "multi_runs.json")))
+    torch.set_num_threads(1)
+    for r in runs:
+        if r["V"] > 4096:
+            continue                                    # keep the CPU suite short (covered on the GPU side)
+        d, t = replay_model.make_pair(r["V"], seed=r["seed"], noise=r["noise"])
+        tp = make_golden.multi_tape(r["seed"], r["max_len"] + 1, r["gamma"], r["width"])
+        out, det = spec_loop.multi_speculative_sampling(torch.tensor([r["prefix"]]), d, t, r["max_len"], r["gamma"], r["width"],
+                                                        r["temperature"], r["top_k"], r["top_p"], tape=tp)
+        assert out[0].tolist() == r["tokens"], r
+        assert det["acc_len"] == r["acc_len"]
+        assert abs(det["acc_rate"] - r["acc_rate"]) < 1e-6
+
+
 def test_bild_restatement_matches_reference_runs():
     """The reference's BiLD_sampling (speculative_sampling.py:1718-1873, tape-driven, unmodified code) vs the oracle's
     restatement: tokens, accepted run lengths and the number of draft / target calls."""
