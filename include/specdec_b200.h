@@ -175,6 +175,22 @@ int sd_norm_sample_verify(const void* logits, int dtype, int64_t rows, int64_t V
                           const sd_compact_t* compact, const sd_verify_args_t* verify, int rows_per_request,
                           int32_t* request_counters, int* err_flag, int flags, void* workspace, void* stream);
 
+/* Kernel 2, multi-draft variant.  Replaces the accept loop and resample of multi_speculative_sampling(strategy='iid'),
+ * sampling/speculative_sampling.py:1612-1667: `width` drafts of gamma tokens per request.
+ *   p_probs   draft w, row i of request b at p_probs + b*p_req_stride + w*p_draft_stride + i*p_row_stride (i = 0..gamma)
+ *   q_probs   likewise, rows i = 0..gamma-1;   draft_tok (B, width, gamma) int64 with the two strides given
+ *   u_acc     per request the accept uniforms IN DRAWING ORDER (row stride u_acc_stride >= width*gamma): the reference
+ *             draws lazily — draft 0 one per tested token until its first reject, then draft 1, ... (:1616-1634)
+ *   accept iff u < min(1, p/q) (a NaN ratio rejects); the first draft with the longest accepted run wins (:1636-1640),
+ *   an all-accepted draft ends the scan; then the residual max(0, p_n - q_n) of the winning draft (empty: p_n) or its
+ *   bonus row is sampled with u_final as in sd_verify.
+ *   choice (B,) int32 winning draft, n_accepted (B,) its accepted run, next_tok (B,), ratios optional (B, width, gamma). */
+int sd_verify_multi(const float* p_probs, int64_t p_req_stride, int64_t p_draft_stride, int64_t p_row_stride,
+                    const float* q_probs, int64_t q_req_stride, int64_t q_draft_stride, int64_t q_row_stride,
+                    const int64_t* draft_tok, int64_t draft_req_stride, int64_t draft_draft_stride, const float* u_acc,
+                    int64_t u_acc_stride, const float* u_final, int B, int width, int gamma, int64_t V, int32_t* choice,
+                    int32_t* n_accepted, int64_t* next_tok, float* ratios, int* err_flag, void* stream);
+
 /* max_fn — out = max(x,0) / (sum(max(x,0)) + 1e-6) per row.  Replaces sampling/utils.py:236-245. */
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream);
 

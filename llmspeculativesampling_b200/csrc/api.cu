@@ -164,6 +164,23 @@ int sd_norm_sample_verify(const void* logits, int dtype, int64_t rows, int64_t V
   return done("sd_norm_sample_verify launch", sd::launch_norm_verify(p, dtype, static_cast<int>(rows), static_cast<cudaStream_t>(stream)));
 }
 
+int sd_verify_multi(const float* p_probs, int64_t p_req_stride, int64_t p_draft_stride, int64_t p_row_stride,
+                    const float* q_probs, int64_t q_req_stride, int64_t q_draft_stride, int64_t q_row_stride,
+                    const int64_t* draft_tok, int64_t draft_req_stride, int64_t draft_draft_stride, const float* u_acc,
+                    int64_t u_acc_stride, const float* u_final, int B, int width, int gamma, int64_t V, int32_t* choice,
+                    int32_t* n_accepted, int64_t* next_tok, float* ratios, int* err_flag, void* stream) {
+  if (B == 0) return SD_OK;
+  if (width < 1 || u_acc_stride < static_cast<int64_t>(width) * gamma) return fail(SD_EINVAL, "sd_verify_multi: width / u_acc_stride");
+  const sd_verify_args_t a = {p_probs, p_req_stride, p_row_stride, q_probs, q_req_stride, q_row_stride, draft_tok,
+                              draft_req_stride, u_acc, u_acc_stride, u_final, B, gamma, V, 1, n_accepted, next_tok, ratios,
+                              nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr};
+  sd::VerifyParams p;
+  const int rc = fill_verify(a, err_flag, p);
+  if (rc != SD_OK) return rc;
+  return done("sd_verify_multi launch", sd::launch_verify_multi(p, p_draft_stride, q_draft_stride, draft_draft_stride, width,
+                                                                choice, static_cast<cudaStream_t>(stream)));
+}
+
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream) {
   if (rows == 0) return SD_OK;
   if (!x || !out || V <= 0 || ld < V || ld_out < V) return fail(SD_EINVAL, "sd_max_fn: bad argument");

@@ -333,6 +333,79 @@ __global__ void __launch_bounds__(kSparseThreads) verify_sparse_kernel(const Ver
   dense_verify_cta<kSparseThreads>(p, b, s_n_acc, &rs);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-draft verify (reference multi_speculative_sampling(strategy='iid'), speculative_sampling.py:1612-1667): W drafts
+// of gamma tokens per request.  Warp 0 walks the drafts in order — lane i tests token i of draft w with the uniform at
+// the request's running offset (the reference draws its uniforms lazily: a draft consumes one per tested token and
+// stops at its first reject, :1616-1634) — and keeps the first draft with the longest accepted run; an all-accepted
+// draft ends the scan.  The whole CTA then samples the residual max(0, p_n - q_n) of the winning draft (or its bonus
+// row) exactly like the dense path of kernel 2.
+constexpr int kMultiThreads = 256;
+
+struct VerifyMultiParams {
+  VerifyParams v;                       // p/q/draft describe draft 0 of every request; *_req_stride spans all W drafts
+  long long p_draft_stride, q_draft_stride, draft_draft_stride;
+  int width;
+  int* choice;
+};
+
+__global__ void __launch_bounds__(kMultiThreads) verify_multi_kernel(const VerifyMultiParams mp) {
+  __shared__ RowScratch<kMultiThreads> rs;
+  __shared__ int s_choice, s_n_acc;
+  const VerifyParams& p = mp.v;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = static_cast<int>(p.V), gamma = p.gamma, W = mp.width;
+  if (p.active != nullptr && p.active[b] == 0) return;
+  if (p.ratios != nullptr) {                                               // statistics: p/q of EVERY drafted token (:1600-1609)
+    for (int idx = tid; idx < W * gamma; idx += kMultiThreads) {
+      const int w = idx / gamma, i = idx - w * gamma;
+      long long tok = p.draft[b * p.draft_stride + w * mp.draft_draft_stride + i];
+      if (tok < 0 || tok >= V) tok = 0;
+      p.ratios[static_cast<long long>(b) * W * gamma + idx] =
+          __fdiv_rn(p.p[b * p.p_req_stride + w * mp.p_draft_stride + i * p.p_row_stride + tok],
+                    p.q[b * p.q_req_stride + w * mp.q_draft_stride + i * p.q_row_stride + tok]);
+    }
+  }
+  if (warp == 0) {
+    int off = 0, max_l = 0, choice = 0;
+    for (int w = 0; w < W; ++w) {
+      bool acc = true;
+      if (lane < gamma) {
+        long long tok = p.draft[b * p.draft_stride + w * mp.draft_draft_stride + lane];
+        if (tok < 0 || tok >= V) { atomicOr(p.err_flag, kErrBadToken); tok = 0; }
+        const float pv = p.p[b * p.p_req_stride + w * mp.p_draft_stride + lane * p.p_row_stride + tok];
+        const float qv = p.q[b * p.q_req_stride + w * mp.q_draft_stride + lane * p.q_row_stride + tok];
+        const float ratio = __fdiv_rn(pv, qv);
+        const float r = p.u_acc[b * p.u_acc_stride + off + lane];        // (only read where the reference would draw it)
+        acc = (ratio == ratio) && (r < fminf(1.0f, ratio));               // torch.min(1, NaN) is NaN: rejects
+      }
+      const unsigned rej = __ballot_sync(0xffffffffu, !acc);
+      const int cur_l = rej ? (__ffs(rej) - 1) : gamma;
+      off += rej ? cur_l + 1 : gamma;
+      if (cur_l > max_l) {
+        max_l = cur_l;
+        choice = w;
+        if (!rej) break;                                                   // warp-uniform
+      }
+    }
+    if (lane == 0) { s_choice = choice; s_n_acc = max_l; if (mp.choice != nullptr) mp.choice[b] = choice; }
+  }
+  __syncthreads();
+  VerifyParams vp = p;                                                     // the winning draft's rows, non-strict residual rule
+  vp.p = p.p + s_choice * mp.p_draft_stride;
+  vp.q = p.q + s_choice * mp.q_draft_stride;
+  vp.strict = 0;
+  dense_verify_cta<kMultiThreads>(vp, b, s_n_acc, &rs);
+}
+
+cudaError_t launch_verify_multi(const VerifyParams& v, long long p_draft_stride, long long q_draft_stride,
+                                long long draft_draft_stride, int width, int* choice, cudaStream_t st) {
+  if (v.gamma < 1 || v.gamma > 32 || width < 1) return cudaErrorInvalidValue;
+  VerifyMultiParams mp = {v, p_draft_stride, q_draft_stride, draft_draft_stride, width, choice};
+  verify_multi_kernel<<<static_cast<unsigned>(v.B), kMultiThreads, 0, st>>>(mp);
+  return cudaGetLastError();
+}
+
 static int g_verify_cluster = 0;
 void set_verify_tuning(int cluster) { g_verify_cluster = cluster; }
 

@@ -246,6 +246,33 @@ def verify(p_probs: torch.Tensor, q_probs: torch.Tensor, draft_tok: torch.Tensor
     return n_accepted, next_tok
 
 
+def verify_multi(p_probs: torch.Tensor, q_probs: torch.Tensor, draft_tok: torch.Tensor, u_acc: torch.Tensor,
+                 u_final: torch.Tensor, ratios: Optional[torch.Tensor] = None, err: Optional[ErrFlag] = None):
+    """Kernel 2, multi-draft variant (sd_verify_multi).  p_probs (B, W, gamma+1, V), q_probs (B, W, gamma, V) fp32,
+    draft_tok (B, W, gamma) int64, u_acc (B, >= W*gamma) accept uniforms in the reference's drawing order, u_final (B,).
+    Returns (choice, n_accepted, next_tok)."""
+    _require_cuda(p_probs, "p_probs")
+    B, W, g1, V = p_probs.shape
+    gamma = g1 - 1
+    assert q_probs.shape == (B, W, gamma, V) and p_probs.dtype == q_probs.dtype == torch.float32
+    assert p_probs.stride(3) == 1 and q_probs.stride(3) == 1
+    assert draft_tok.dtype == torch.int64 and draft_tok.shape == (B, W, gamma) and draft_tok.stride(2) == 1
+    assert u_acc.dtype == torch.float32 and u_acc.dim() == 2 and u_acc.shape[0] == B and u_acc.shape[1] >= W * gamma and u_acc.stride(1) == 1
+    assert u_final.dtype == torch.float32 and u_final.numel() == B and u_final.is_contiguous()
+    dev = p_probs.device
+    choice = torch.empty(B, dtype=torch.int32, device=dev)
+    n_acc = torch.empty(B, dtype=torch.int32, device=dev)
+    nxt = torch.empty(B, dtype=torch.int64, device=dev)
+    err = err or default_flag(dev)
+    rc = _cabi.load().sd_verify_multi(
+        p_probs.data_ptr(), p_probs.stride(0), p_probs.stride(1), p_probs.stride(2),
+        q_probs.data_ptr(), q_probs.stride(0), q_probs.stride(1), q_probs.stride(2),
+        draft_tok.data_ptr(), draft_tok.stride(0), draft_tok.stride(1), u_acc.data_ptr(), u_acc.stride(0), u_final.data_ptr(),
+        B, W, gamma, V, choice.data_ptr(), n_acc.data_ptr(), nxt.data_ptr(), _ptr(ratios), err.ptr(), _stream())
+    _cabi.check(rc, "sd_verify_multi")
+    return choice, n_acc, nxt
+
+
 def norm_sample_verify(logits: torch.Tensor, temperature: float, top_k: int, top_p: float, u: torch.Tensor,
                        probs_out: torch.Tensor, tok_out: torch.Tensor, compact, rows_per_request: int,
                        request_counters: torch.Tensor, p_probs: torch.Tensor, q_probs: torch.Tensor,

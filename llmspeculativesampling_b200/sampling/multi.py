@@ -4,9 +4,9 @@ strategy='iid', decoder-only path).
 SURVEY.md §8f row N2, first version: W independent drafts per iteration (`KVCacheModel.generate(multi=W)`), ONE target
 pass over all of them, the first draft with the longest accepted run wins (:1612-1640), `rollback(end_pos, choice)`
 keeps that draft's KV cache (:1646-1667).  Everything per row runs on the hot-path kernels (fused filter + softmax,
-inverse-CDF sampling, max_fn); the accept tests of an iteration are ONE gather of p[token] / q[token] for all W x gamma
-drafted tokens and a scan on the host in the reference's order (it draws its uniforms lazily, draft by draft, and stops a
-draft at its first reject — :1616-1634).  Batch 1 as in the reference (:1413).  `strategy='beam'` depends on the beam
+inverse-CDF sampling); the accept tests and the resample of an iteration are ONE launch of the multi-draft variant of
+kernel 2 (`sd_verify_multi`: the reference draws its accept uniforms lazily, draft by draft, stopping a draft at its first
+reject — :1616-1634 — and the kernel consumes the tape in exactly that order).  Batch 1 as in the reference (:1413).  `strategy='beam'` depends on the beam
 search APIs removed from transformers 5.x and stays out of scope.
 """
 from __future__ import annotations
@@ -55,57 +55,29 @@ def multi_speculative_sampling(prefix: torch.Tensor, approx_model: torch.nn.Modu
     acc_len, acc_rate = [], []
     out = prefix
     it = 0
-    rows = torch.arange(W, device=dev).view(W, 1)
     while out.shape[1] < T:                                                 # :1441
         blk_h, blk_d = tape_h[min(it, tape_h.shape[0] - 1)], tape_d[min(it, tape_d.shape[0] - 1)]
         L = out.shape[1]
         x = approx.generate(out, g, uniforms=blk_d[:g * W].view(g, W), multi=W, strategy="iid")   # :1531 -> (W, L + g)
         _ = target.generate(x, 1, uniforms=blk_d[g * W:g * W + W].view(1, W))                     # :1558 (W samples discarded)
         q_hist, p_hist = approx._prob_history, target._prob_history
-        toks = x[:, L:L + g]                                                # (W, g) drafted tokens
-        pos = torch.arange(L - 1, L - 1 + g, device=dev).view(1, g)
-        p_at = p_hist[rows, pos, toks]                                      # p[w, L+i-1, x[w, L+i]]
-        q_at = q_hist[rows, pos, toks]                                      # q[w, i, ...] (history rows start at L-1)
-        ratio = (p_at / q_at).cpu()                                         # fp32 divide, :1626
-        q_h = q_at.cpu()
-        for w in range(W):                                                  # :1600-1609
+        # kernel 2, multi-draft variant: accept scan over the W drafts (uniforms consumed in the reference's drawing
+        # order), first longest run wins, residual / bonus sample — one launch, one small read-back
+        ratios = torch.empty(1, W, g, dtype=torch.float32, device=dev)
+        ch, na, nt = ops.verify_multi(p_hist[:, L - 1:L + g].unsqueeze(0), q_hist[:, L - 1:L - 1 + g].unsqueeze(0),
+                                      x[:, L:L + g].unsqueeze(0), blk_d[g * W + W:g * W + W + W * g].view(1, W * g),
+                                      blk_d[nblk - 1].view(1).contiguous(), ratios=ratios)
+        choice, max_l, t = int(ch[0]), int(na[0]), nt
+        r_h = ratios[0].cpu()
+        for w in range(W):                                                  # :1600-1609 (statistics over ALL drafted tokens)
             for i in range(g):
-                acc_rate.append(0.0 if float(q_h[w, i]) == 0 else min(float(ratio[w, i]), 1.0))
-        thr = torch.minimum(torch.ones(()), ratio)                          # min(1, p/q)
-        n_rand = 0
-        is_all_accept = False
-        max_n, max_l, choice = L - 1, 0, 0
-        for w in range(W):                                                  # :1612-1640
-            cur_l, cur_all = 0, True
-            for i in range(g):
-                r = blk_h[g * W + W + n_rand]
-                n_rand += 1
-                if bool(r < thr[w, i]):
-                    cur_l += 1
-                else:
-                    cur_all = False
-                    break
-            if cur_l > max_l:
-                max_n, max_l, choice = L - 1 + cur_l, cur_l, w
-                if cur_all:
-                    is_all_accept = True
-                    break
+                rv = float(r_h[w, i])
+                acc_rate.append(0.0 if (rv != rv or rv == float("inf")) else min(rv, 1.0))
         acc_len.append(max_l)
-        n = max_n
+        n = L - 1 + max_l
         out = x[choice:choice + 1, :n + 1]                                  # :1644
-        u_final = blk_d[nblk - 1].view(1).contiguous()
-        if is_all_accept:
-            t = ops.sample_rows(p_hist[choice:choice + 1, L + g - 1].contiguous(), u_final)          # :1649
-            approx.rollback(n + 1, choice)
-            target.rollback(n + 2, choice)
-        else:
-            new_p = ops.max_fn((p_hist[choice:choice + 1, n] - q_hist[choice:choice + 1, n]).contiguous())   # :1657 (q row max_l = position n)
-            err = ops.ErrFlag(dev)
-            t = ops.sample_rows(new_p, u_final, err=err)
-            if int(err.t.item()) != 0:                                      # empty residual: sample(p) instead, :1661-1663
-                t = ops.sample_rows(p_hist[choice:choice + 1, n].contiguous(), u_final)
-            approx.rollback(n + 1, choice)
-            target.rollback(n + 1, choice)
+        approx.rollback(n + 1, choice)                                      # :1646
+        target.rollback(n + 2 if max_l == g else n + 1, choice)             # :1650 / :1667
         out = torch.cat((out, t.view(1, 1)), dim=1)                         # :1677
         it += 1
         if eos_token_id is not None:                                        # :1681-1689

@@ -259,6 +259,35 @@ def test_fused_norm_sample_verify_equals_two_launches(cuda_lib, V, dtype, B, str
     assert int(res[1][7][1]) == B and int(res[1][2][5]) == 2
 
 
+@pytest.mark.parametrize("B,W,gamma,V,k,p,noise", [(6, 3, 4, 32000, 20, 0.9, 0.5), (5, 8, 2, 1000, 0, 0.0, 1.0), (4, 2, 5, 4099, 5, 0.0, 0.2),
+                                                   (3, 4, 4, 2048, 20, 0.9, 3.0)])
+def test_verify_multi_bit_exact(cuda_lib, B, W, gamma, V, k, p, noise):
+    """sd_verify_multi (W drafts per request, lazily drawn accept uniforms, first longest run wins) vs the oracle's
+    restatement of speculative_sampling.py:1612-1667: winning draft, accepted run, next token and ratios."""
+    from llmspeculativesampling_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + W)
+    z = torch.randn(B, 1, gamma + 1, V, generator=g) * 3.0
+    tl = z + noise * torch.randn(B, W, gamma + 1, V, generator=g)
+    dl = z[:, :, :gamma] + noise * torch.randn(B, W, gamma, V, generator=g)
+    pp = oracle_probs(tl.reshape(-1, V), 0.9, k, p).reshape(B, W, gamma + 1, V)
+    qq = oracle_probs(dl.reshape(-1, V), 0.9, k, p).reshape(B, W, gamma, V)
+    u_d = torch.rand(B, W, gamma, generator=g)
+    draft = torch.tensor([[[ref_ops.icdf_sample(qq[b, w, i], float(u_d[b, w, i])) for i in range(gamma)] for w in range(W)]
+                          for b in range(B)])
+    u_seq = torch.rand(B, W * gamma + 3, generator=g)
+    u_seq[0, :] = 0.0                                          # request 0: every token with p > 0 is accepted (bonus row)
+    if B > 1:
+        u_seq[1, :] = 1.0 - 2 ** -24                           # request 1: only ratios >= 1 are accepted
+    u_fin = torch.rand(B, generator=g)
+    ratios = torch.zeros(B, W, gamma, device="cuda")
+    ch, na, nt = ops.verify_multi(pp.cuda(), qq.cuda(), draft.cuda(), u_seq.cuda(), u_fin.cuda(), ratios=ratios)
+    ops.default_flag("cuda").check()
+    for b in range(B):
+        wc, wn, wt, wr = ref_ops.verify_multi_request(pp[b], qq[b], draft[b], u_seq[b].numpy(), float(u_fin[b]))
+        assert (int(ch[b]), int(na[b]), int(nt[b])) == (wc, wn, wt), f"request {b}"
+        assert np.array_equal(ratios[b].cpu().numpy(), wr, equal_nan=True)
+
+
 def test_distribution_preservation_chi_square(cuda_lib):
     """The reference authors' manual two-token check (kvcache_model.py:73-76, speculative_sampling.py:227-229: force
     p = {1: .4, 12: .6}, q = {1: .6, 12: .4} and count emitted tokens) as a statistical test of the whole step:
