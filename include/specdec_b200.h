@@ -191,6 +191,15 @@ int sd_verify_multi(const float* p_probs, int64_t p_req_stride, int64_t p_draft_
                     int64_t u_acc_stride, const float* u_final, int B, int width, int gamma, int64_t V, int32_t* choice,
                     int32_t* n_accepted, int64_t* next_tok, float* ratios, int* err_flag, void* stream);
 
+/* Kernel 2, BiLD variant.  Replaces the target's check of BiLD_sampling, sampling/speculative_sampling.py:1793-1813:
+ * request b has n_check[b] (<= max_check; NULL: max_check) unchecked draft tokens draft_tok[b, i] whose target
+ * distributions are rows i of p_probs; the target keeps tokens while -log p[i][token] <= rollback_thres (:1800), then
+ * always samples its own token from row n = number of kept tokens (:1812) with u_final (row max_check must exist).
+ *   n_accepted (B,) kept tokens, next_tok (B,), nll optional (B, max_check) the tested -log p values. */
+int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const int64_t* draft_tok,
+                   int64_t draft_stride, const int32_t* n_check, int max_check, float rollback_thres, const float* u_final,
+                   int B, int64_t V, int32_t* n_accepted, int64_t* next_tok, float* nll, int* err_flag, void* stream);
+
 /* max_fn — out = max(x,0) / (sum(max(x,0)) + 1e-6) per row.  Replaces sampling/utils.py:236-245. */
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream);
 

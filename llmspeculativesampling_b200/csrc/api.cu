@@ -181,6 +181,20 @@ int sd_verify_multi(const float* p_probs, int64_t p_req_stride, int64_t p_draft_
                                                                 choice, static_cast<cudaStream_t>(stream)));
 }
 
+int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const int64_t* draft_tok,
+                   int64_t draft_stride, const int32_t* n_check, int max_check, float rollback_thres, const float* u_final,
+                   int B, int64_t V, int32_t* n_accepted, int64_t* next_tok, float* nll, int* err_flag, void* stream) {
+  if (B == 0) return SD_OK;
+  if (!p_probs || !draft_tok || !u_final || !n_accepted || !next_tok || !err_flag) return fail(SD_EINVAL, "sd_verify_bild: null argument");
+  if (B < 0 || max_check < 1 || max_check > 32 || V <= 0 || V >= (1LL << 24)) return fail(SD_EINVAL, "sd_verify_bild: bad shape (1 <= max_check <= 32)");
+  sd::VerifyParams p = {};
+  p.p = p_probs; p.p_req_stride = p_req_stride; p.p_row_stride = p_row_stride;
+  p.draft = reinterpret_cast<const long long*>(draft_tok); p.draft_stride = draft_stride;
+  p.u_final = u_final; p.B = B; p.gamma = max_check; p.V = V;
+  p.n_accepted = n_accepted; p.next_tok = reinterpret_cast<long long*>(next_tok); p.ratios = nll; p.err_flag = err_flag;
+  return done("sd_verify_bild launch", sd::launch_verify_bild(p, n_check, rollback_thres, static_cast<cudaStream_t>(stream)));
+}
+
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream) {
   if (rows == 0) return SD_OK;
   if (!x || !out || V <= 0 || ld < V || ld_out < V) return fail(SD_EINVAL, "sd_max_fn: bad argument");

@@ -406,6 +406,42 @@ cudaError_t launch_verify_multi(const VerifyParams& v, long long p_draft_stride,
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// BiLD check (reference BiLD_sampling, speculative_sampling.py:1793-1813): the target keeps unchecked draft tokens while
+// -log p[token] <= rollback_thres, then ALWAYS samples its own next token from its distribution at the first
+// position it did not keep (plain sample of a p row — there is no residual in BiLD).
+__global__ void __launch_bounds__(kMultiThreads) verify_bild_kernel(const VerifyParams p, const int* n_check, const float rollback_thres) {
+  __shared__ RowScratch<kMultiThreads> rs;
+  __shared__ int s_n;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int V = static_cast<int>(p.V);
+  if (p.active != nullptr && p.active[b] == 0) return;
+  const int nc = n_check != nullptr ? min(n_check[b], p.gamma) : p.gamma;
+  if (tid < 32) {
+    bool fail = false;
+    if (lane < nc) {
+      long long tok = p.draft[b * p.draft_stride + lane];
+      if (tok < 0 || tok >= V) { atomicOr(p.err_flag, kErrBadToken); tok = 0; }
+      const float nll = -logf(p.p[b * p.p_req_stride + lane * p.p_row_stride + tok]);
+      fail = nll > rollback_thres;                                         // (-log 0 = inf fails; NaN keeps, as in the reference)
+      if (p.ratios != nullptr) p.ratios[b * p.gamma + lane] = nll;
+    }
+    const unsigned bad = __ballot_sync(0xffffffffu, fail);
+    if (lane == 0) s_n = bad ? (__ffs(bad) - 1) : nc;
+  }
+  __syncthreads();
+  VerifyParams vp = p;
+  vp.gamma = 0;                                                            // never a residual: plain sample of p row n
+  vp.strict = 0;
+  dense_verify_cta<kMultiThreads>(vp, b, s_n, &rs);
+}
+
+cudaError_t launch_verify_bild(const VerifyParams& v, const int* n_check, float rollback_thres, cudaStream_t st) {
+  if (v.gamma < 1 || v.gamma > 32) return cudaErrorInvalidValue;
+  verify_bild_kernel<<<static_cast<unsigned>(v.B), kMultiThreads, 0, st>>>(v, n_check, rollback_thres);
+  return cudaGetLastError();
+}
+
 static int g_verify_cluster = 0;
 void set_verify_tuning(int cluster) { g_verify_cluster = cluster; }
 

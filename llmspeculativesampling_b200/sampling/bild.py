@@ -4,7 +4,8 @@ SURVEY.md §8f row N3, first version: the reference's own loop (one draft token 
 draft is unsure or gamma tokens are unchecked) on the GPU building blocks of the hot path — `KVCacheModel` (static KV
 cache, fused filter + softmax rows, inverse-CDF sampling from a uniform tape) — so tokens are reproducible and equal to
 the reference's on the same uniforms.  The two policy quantities are read from the probability rows the kernels already
-wrote: max q of the newest draft row (:1784) and -log p[token] of the unchecked tokens (:1800, one gather per check).
+wrote: max q of the newest draft row (:1784), and the target's check (-log p[token] of the unchecked tokens, first failure,
+the target's own token, :1797-1812) is one launch of the BiLD variant of kernel 2 (`sd_verify_bild`).
 Batch 1 as in the reference (:1729); the batched / CUDA-graph engine serves `speculative_sampling` only.
 """
 from __future__ import annotations
@@ -53,16 +54,16 @@ def BiLD_sampling(prefix: torch.Tensor, approx_model: torch.nn.Module, target_mo
         if q_max < fallback_thres or x.shape[1] - last_check - 1 >= gamma:
             _ = target.generate(x, 1, uniforms=row[gamma].view(1, 1))       # :1788 (sample discarded)
             target_call_times += 1
-            p = target._prob_history[0]                                     # (len, V)
-            pos = torch.arange(last_check, x.shape[1] - 1, device=dev)
-            nll = -p[pos, x[0, pos + 1]].log()                              # :1800, every unchecked token in one gather
-            fail = (nll > rollback_thres).nonzero()
-            l = int(fail[0]) if fail.numel() else int(pos.numel())          # :1797-1803
+            # kernel 2, BiLD variant: -log p[token] of every unchecked token, first failure, the target's own token
+            p = target._prob_history                                        # (1, len, V)
+            c = x.shape[1] - 1 - last_check                                 # unchecked tokens (<= gamma)
+            kept, t = ops.verify_bild(p[:, last_check:last_check + c + 1], x[:, last_check + 1:last_check + 1 + c],
+                                      rollback_thres, row[2 * gamma + 1].view(1).contiguous())   # :1797-1812
+            l = int(kept[0])
             n = last_check + l
             acc_len.append(l)
             prefix = x[:, :n + 1]                                           # :1806
             approx.rollback(n + 1)                                          # :1811
-            t = ops.sample_rows(p[n:n + 1], row[2 * gamma + 1].view(1).contiguous())    # :1812
             target.rollback(n + 1)                                          # :1813
             last_check = n + 1
             prefix = torch.cat((prefix, t.view(1, 1)), dim=1)               # :1817

@@ -288,6 +288,33 @@ def test_verify_multi_bit_exact(cuda_lib, B, W, gamma, V, k, p, noise):
         assert np.array_equal(ratios[b].cpu().numpy(), wr, equal_nan=True)
 
 
+@pytest.mark.parametrize("B,C,V,k,p", [(16, 4, 32000, 20, 0.9), (9, 7, 1000, 0, 0.0), (5, 1, 4099, 5, 0.0)])
+def test_verify_bild_bit_exact(cuda_lib, B, C, V, k, p):
+    """sd_verify_bild (keep tokens while -log p[token] <= rollback_thres, then sample the target's own token) vs the
+    reference rule of speculative_sampling.py:1797-1812 restated with torch on the CPU."""
+    from llmspeculativesampling_b200 import ops
+    g = torch.Generator().manual_seed(B + C)
+    pp = oracle_probs(torch.randn(B * (C + 1), V, generator=g) * 2.0, 1.0, k, p).reshape(B, C + 1, V)
+    draft = torch.stack([torch.stack([torch.multinomial(pp[b, i] + 1e-4 / V, 1, generator=g)[0] for i in range(C)]) for b in range(B)])
+    draft[0, 0] = int((pp[0, 0] == 0).nonzero()[0]) if bool((pp[0, 0] == 0).any()) else draft[0, 0]   # p = 0: -log = inf fails
+    n_check = torch.randint(1, C + 1, (B,), generator=g, dtype=torch.int32)
+    u_fin = torch.rand(B, generator=g)
+    thr = 3.0
+    nll = torch.zeros(B, C, device="cuda")
+    kept, nxt = ops.verify_bild(pp.cuda(), draft.cuda(), thr, u_fin.cuda(), n_check=n_check.cuda(), nll=nll)
+    ops.default_flag("cuda").check()
+    for b in range(B):
+        n = int(n_check[b])
+        for i in range(int(n_check[b])):
+            if float(-pp[b, i, draft[b, i]].log()) > thr:
+                n = i
+                break
+        assert int(kept[b]) == n, f"request {b}"
+        assert int(nxt[b]) == ref_ops.icdf_sample(pp[b, n], float(u_fin[b]))
+        want = (-pp[b, torch.arange(int(n_check[b])), draft[b, :int(n_check[b])]].log()).numpy()
+        assert np.allclose(nll[b, :int(n_check[b])].cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+
+
 def test_distribution_preservation_chi_square(cuda_lib):
     """The reference authors' manual two-token check (kvcache_model.py:73-76, speculative_sampling.py:227-229: force
     p = {1: .4, 12: .6}, q = {1: .6, 12: .4} and count emitted tokens) as a statistical test of the whole step:
