@@ -37,6 +37,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -227,6 +228,71 @@ def run_config1(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------- next rows (side report)
+def run_variants(args):
+    """SURVEY 8f rows N2 / N3 on the config-1 models (llama-68m-shape draft + target, fp32, batch 1, 64 new tokens):
+    multi_speculative_sampling(strategy='iid', width=4) and BiLD_sampling — the oracle port of the reference's loop timed
+    on one host core next to the drop-in on cuda:0, same weights, prompt and uniform tape; leading tokens compared."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from llmspeculativesampling_b200 import build, uniform_tape
+    from llmspeculativesampling_b200.sampling import multi_speculative_sampling, BiLD_sampling
+    from oracle import spec_loop, ref_loader
+    build.build()
+    cfg = LlamaConfig(vocab_size=32000, hidden_size=768, intermediate_size=3072, num_hidden_layers=2,
+                      num_attention_heads=12, num_key_value_heads=12, max_position_embeddings=2048)
+    prompt = torch.randint(3, 32000, (1, 16), generator=torch.Generator().manual_seed(7))
+    N, W, k, p = 64, 4, 20, 0.9
+    out = []
+    torch.manual_seed(0); draft = LlamaForCausalLM(cfg).eval()
+    torch.manual_seed(0); target = LlamaForCausalLM(cfg).eval()          # identical weights: non-trivial acceptance
+    torch.set_num_threads(1)
+
+    def agree(a, b):
+        n = min(a.shape[1], b.shape[1]) - 16
+        return int((a[0, 16:16 + n] == b[0, 16:16 + n].cpu()).long().cumprod(0).sum()), n
+
+    # ---- N2: multi-draft, iid
+    tape = torch.rand(N + 1, spec_loop.multi_block(GAMMA, W), generator=torch.Generator().manual_seed(3))
+    da, ta = ref_loader.LegacyCacheAdapter(draft), ref_loader.LegacyCacheAdapter(target)
+    t0 = time.perf_counter()
+    ref_tok, ref_d = spec_loop.multi_speculative_sampling(prompt, da, ta, N, GAMMA, W, 1.0, k, p, tape=tape)
+    cpu_s = time.perf_counter() - t0
+    dg, tg = draft.cuda(), target.cuda()
+    multi_speculative_sampling(prompt.cuda(), dg, tg, None, None, N, GAMMA, W, None, "iid", None, 0.4, 1.0, k, p, uniforms=tape)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    tok, d = multi_speculative_sampling(prompt.cuda(), dg, tg, None, None, N, GAMMA, W, None, "iid", None, 0.4, 1.0, k, p,
+                                        uniforms=tape, details=True)
+    torch.cuda.synchronize(); gpu_s = time.perf_counter() - t0
+    a, n = agree(ref_tok, tok)
+    out.append({"row": "N2 multi_speculative_sampling(strategy='iid')", "width": W, "gamma": GAMMA, "top_k": k, "top_p": p,
+                "cpu_oracle": {"seconds": cpu_s, "emitted_tokens_per_s": (ref_tok.shape[1] - 16) / cpu_s, "mean_accepted": float(np.mean(ref_d["acc_len"])), "threads": 1},
+                "b200": {"seconds": gpu_s, "emitted_tokens_per_s": (tok.shape[1] - 16) / gpu_s, "mean_accepted": float(np.mean(d["acc_len"]))},
+                "leading_tokens_identical_to_cpu_run": a, "of": n})
+    draft.cpu(); target.cpu()
+    # ---- N3: BiLD
+    fb, rb = 0.08, 3.0
+    tape = uniform_tape.make_tape(5, N + 1, GAMMA)
+    t0 = time.perf_counter()
+    ref_tok, ref_d = spec_loop.bild_sampling(prompt, draft, target, N, GAMMA, fb, rb, 1.0, k, p, tape=tape)
+    cpu_s = time.perf_counter() - t0
+    dg, tg = draft.cuda(), target.cuda()
+    BiLD_sampling(prompt.cuda(), dg, tg, GAMMA, None, None, fb, rb, N, 1.0, k, p, uniforms=tape)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    tok, d = BiLD_sampling(prompt.cuda(), dg, tg, GAMMA, None, None, fb, rb, N, 1.0, k, p, uniforms=tape, details=True)
+    torch.cuda.synchronize(); gpu_s = time.perf_counter() - t0
+    a, n = agree(ref_tok, tok)
+    out.append({"row": "N3 BiLD_sampling", "gamma": GAMMA, "fallback_thres": fb, "rollback_thres": rb, "top_k": k, "top_p": p,
+                "cpu_oracle": {"seconds": cpu_s, "emitted_tokens_per_s": (ref_tok.shape[1] - 16) / cpu_s, "target_calls": ref_d["target_call_times"],
+                               "draft_tokens": ref_d["approx_call_times"], "threads": 1},
+                "b200": {"seconds": gpu_s, "emitted_tokens_per_s": (tok.shape[1] - 16) / gpu_s, "target_calls": d["target_call_times"],
+                         "draft_tokens": d["approx_call_times"]},
+                "leading_tokens_identical_to_cpu_run": a, "of": n})
+    print(json.dumps({"workload": "SURVEY 8f next rows on the config-1 models (llama-68m shapes, identical weights, fp32, batch 1, 64 new tokens)",
+                      "note": "first versions: the reference's host loop on the GPU building blocks (not the batched CUDA-graph engine)",
+                      "results": out}))
+    return 0
+
+
 # ------------------------------------------------------------------------------------------- B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -235,7 +301,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config1"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config1", "variants"],
                     help="config2 = headline synthetic verify microbench; config1 = side report on the reference's CPU-runnable case")
     ap.add_argument("--fused", type=int, default=0,
                     help="0: sd_norm_sample + sd_verify (two launches per step, the faster arrangement at B = 64); "
@@ -247,6 +313,8 @@ def main():
         return run_reference(args)
     if args.workload == "config1":
         return run_config1(args)
+    if args.workload == "variants":
+        return run_variants(args)
 
     import torch.distributed as dist
     from llmspeculativesampling_b200 import build, ops
