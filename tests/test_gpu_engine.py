@@ -18,6 +18,27 @@ def _pair(V, seed, noise, device="cuda", dtype=torch.float32):
     return replay_model.make_pair(V, seed=seed, noise=noise, device=device, dtype=dtype)
 
 
+def test_serving_front_end_batches_requests(cuda_lib):
+    """serving.Server / BatchingQueue: requests submitted concurrently are decoded together and every
+    caller gets the tokens a one-request call with the same request id would give (per-request tapes)."""
+    from llmspeculativesampling_b200.serving import Server, BatchingQueue
+    from llmspeculativesampling_b200.sampling import speculative_sampling
+    d, t = _pair(1000, 5, 0.5)
+    srv = Server(d, t, num_tokens=24, top_k=10, top_p=0.9, random_seed=11)
+    g = torch.Generator().manual_seed(2)
+    reqs = [{"prompt_ids": torch.randint(3, 1000, (int(n),), generator=g).tolist()} for n in (5, 9, 7, 12, 6)]
+    q = BatchingQueue(srv.process_batch, max_batch=8, max_wait_s=0.5)
+    futs = [q.submit(r) for r in reqs]
+    outs = [f.result(timeout=120) for f in futs]
+    q.close()
+    assert sum(q.batches) == len(reqs) and len(q.batches) <= 2
+    for i, (r, o) in enumerate(zip(reqs, outs)):
+        assert o[:len(r["prompt_ids"])] == r["prompt_ids"] and len(o) >= len(r["prompt_ids"]) + 24
+        solo = speculative_sampling(torch.tensor([r["prompt_ids"]], device="cuda"), d, t, None, None, 24, gamma=4, temperature=1.0,
+                                    top_k=10, top_p=0.9, random_seed=11, request_ids=[i])
+        assert solo[0].tolist()[:len(o)] == o[:solo.shape[1]]
+
+
 def test_multi_draft_drop_in_matches_reference_golden_runs(cuda_lib):
     """multi_speculative_sampling(strategy='iid') on the GPU building blocks vs golden runs of the
     UNMODIFIED reference (tests/golden/multi_runs.json): same tokens and longest accepted runs."""

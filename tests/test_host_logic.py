@@ -115,3 +115,36 @@ def test_sharded_stats_reduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_batching_queue_groups_concurrent_requests():
+    """serving front-end: concurrent submits are served in batches, results go back to their callers,
+    a failing batch fails its waiters only."""
+    import threading
+    from llmspeculativesampling_b200.serving import BatchingQueue
+    calls = []
+
+    def handler(reqs):
+        calls.append(len(reqs))
+        if any(r.get("boom") for r in reqs):
+            raise ValueError("bad batch")
+        return [r["x"] * 2 for r in reqs]
+
+    q = BatchingQueue(handler, max_batch=4, max_wait_s=0.2)
+    futs = [None] * 10
+
+    def client(i):
+        futs[i] = q.submit({"x": i})
+
+    ts = [threading.Thread(target=client, args=(i,)) for i in range(10)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert [f.result(timeout=10) for f in futs] == [2 * i for i in range(10)]
+    assert sum(calls) == 10 and max(calls) <= 4 and len(calls) <= 5
+    bad = q.submit({"x": 1, "boom": True})
+    with pytest.raises(ValueError):
+        bad.result(timeout=10)
+    assert q.submit({"x": 21}).result(timeout=10) == 42
+    q.close()
+    with pytest.raises(RuntimeError):
+        q.submit({"x": 0})
