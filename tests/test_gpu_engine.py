@@ -215,3 +215,42 @@ def test_tiny_hf_llama_pair_runs_and_preserves_distribution(cuda_lib):
         want, _ = spec_loop.speculative_sampling(prompts[b].unsqueeze(0), dcpu, tcpu, max_len, gamma, 1.0, 0, 0.0, tape=tp[:, b])
         same += int(o1[b][0].tolist() == want[0].tolist())
     assert same >= B - 1
+
+
+def test_tiny_hf_llama_multi_draft_and_bild(cuda_lib):
+    """multi_speculative_sampling(iid) and BiLD_sampling with stock Hugging Face modules (static KV caches with W rows,
+    rollback(choice) as a KV row copy).  GEMM rounding differs between CPU and GPU, so the CPU oracle is compared on the
+    leading tokens (the runs may diverge once a uniform lands on a rounding-sensitive threshold) and the structural
+    invariants are checked exactly."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from llmspeculativesampling_b200.sampling import multi_speculative_sampling, BiLD_sampling
+    from llmspeculativesampling_b200 import uniform_tape
+    from oracle import ref_loader
+    cfg = LlamaConfig(vocab_size=1024, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256)
+    torch.manual_seed(0)
+    target = LlamaForCausalLM(cfg).eval()
+    torch.manual_seed(0)
+    draft = LlamaForCausalLM(cfg).eval()
+    with torch.no_grad():
+        for pd in draft.parameters():
+            pd.add_(0.02 * torch.randn_like(pd))
+    prompt = torch.randint(3, 1024, (1, 7), generator=torch.Generator().manual_seed(5))
+    gamma, W, N = 3, 3, 20
+    tape_m = torch.rand(N + 1, spec_loop.multi_block(gamma, W), generator=torch.Generator().manual_seed(8))
+    tape_b = uniform_tape.make_tape(9, N + 1, gamma)
+    torch.set_num_threads(1)
+    want_m, dm = spec_loop.multi_speculative_sampling(prompt, ref_loader.LegacyCacheAdapter(draft), ref_loader.LegacyCacheAdapter(target),
+                                                      N, gamma, W, 1.0, 0, 0.0, tape=tape_m)
+    want_b, db = spec_loop.bild_sampling(prompt, draft, target, N, gamma, 0.01, 6.0, 1.0, 0, 0.0, tape=tape_b)
+    dg, tg = draft.cuda(), target.cuda()
+    got_m, gm = multi_speculative_sampling(prompt.cuda(), dg, tg, None, None, N, gamma, W, None, "iid", None, 0.4, 1.0, 0, 0.0,
+                                           details=True, uniforms=tape_m)
+    got_b, gb = BiLD_sampling(prompt.cuda(), dg, tg, gamma, None, None, 0.01, 6.0, N, 1.0, 0, 0.0, details=True, uniforms=tape_b)
+    for got, want in ((got_m, want_m), (got_b, want_b)):
+        assert got.shape[0] == 1 and got.shape[1] >= 7 + N and got[0, :7].tolist() == prompt[0].tolist()
+        lead = int((got[0, :min(got.shape[1], want.shape[1])].cpu() == want[0, :min(got.shape[1], want.shape[1])]).long().cumprod(0).sum())
+        assert lead >= 7 + N // 2, f"only {lead - 7} leading tokens agree with the CPU oracle"
+    assert all(0 <= a <= gamma for a in gm["acc_len"]) and gm["target_call_times"] == len(gm["acc_len"])
+    assert sum(a + 1 for a in gm["acc_len"]) == got_m.shape[1] - 7
+    assert all(0 <= a <= gamma for a in gb["acc_len"]) and gb["approx_call_times"] >= gb["target_call_times"]
