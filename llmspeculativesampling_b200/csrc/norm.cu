@@ -55,7 +55,10 @@ void set_norm_tuning(int cluster, int threads) { g_tune_cluster = cluster; g_tun
 template <typename T, int THREADS, int MINB>
 static cudaError_t launch_cfg(const NormParams& p, size_t smem, int rows, cudaStream_t st) {
   auto kern = norm_probs_kernel<T, THREADS, MINB>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};            // per device: the attribute belongs to the device's copy of the kernel
+  int dev_id = 0;
+  (void)cudaGetDevice(&dev_id);
+  bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;

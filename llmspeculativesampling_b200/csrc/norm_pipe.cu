@@ -24,6 +24,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 namespace sd {
 
@@ -838,7 +839,10 @@ static bool pipe_fits(const PipeVariant& v, size_t slice_bytes, int C, int kcap)
 template <typename T, int NG, int NB, int CAP>
 static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStream_t st, int* query_max_clusters) {
   auto kern = norm_topk_pipe_kernel<T, NG, NB, CAP>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};            // per device: the attribute belongs to the device's copy of the kernel
+  int dev_id = 0;
+  (void)cudaGetDevice(&dev_id);
+  bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
@@ -889,6 +893,7 @@ static cudaError_t pipe_dispatch_dtype(const NormParams& p, int dtype, int rows,
 struct PipePlan { long long V; int dtype, kcap, cluster, groups, buffers, cap, max_clusters; };
 static PipePlan g_plans[32];
 static int g_n_plans = 0;
+static std::mutex g_plan_mutex;          // the library may be called from several host threads (one stream each)
 
 bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
   if (p.sched == nullptr) return false;
@@ -898,6 +903,7 @@ bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster) {
   const bool aligned_in = (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) && ((p.ld_in * es) % 16 == 0) && (row_bytes % 16 == 0);
   if (!aligned_in) return false;
   const int kcap = p.top_k + 8;                              // per-rank receive region must hold k + slack
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
   const PipePlan* plan = nullptr;
   for (int i = 0; i < g_n_plans; ++i)
     if (g_plans[i].V == p.V && g_plans[i].dtype == dtype && g_plans[i].kcap == kcap && tune_cluster == 0) plan = &g_plans[i];

@@ -477,7 +477,10 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(slice) * 4 + sizeof(VerifyShared<THREADS>);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   auto kern = verify_kernel<THREADS, 3>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};            // per device: the attribute belongs to the device's copy of the kernel
+  int dev_id = 0;
+  (void)cudaGetDevice(&dev_id);
+  bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
