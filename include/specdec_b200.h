@@ -212,6 +212,21 @@ int sd_kv_append(const void* k_new, const void* v_new, int64_t stride_b, int64_t
                  void* k_cache, void* v_cache, const int32_t* write_pos, int B, int H, int q, int D, int S,
                  int elem_size, void* stream);
 
+/* Kernel 3a', multi-draft rollback — replaces rollback(end_pos, choice) of sampling/kvcache_model.py:390-396 (keep draft
+ * `choice`; the next forward expands it to all rows again, :180-200) on static caches that hold W rows per request
+ * (row b*W + w): positions start[b*start_stride] .. + count[b] - 1 of row choice[b] are copied over the request's other
+ * rows (everything before is the shared prefix).  max_count bounds count; requests with active[b*active_stride] == 0 are
+ * skipped (active may be NULL). */
+int sd_kv_select(void* k_cache, void* v_cache, int B, int W, int H, int S, int D, int elem_size, int max_count,
+                 const int32_t* choice, const int32_t* start, int start_stride, const int32_t* count, const int32_t* active,
+                 int active_stride, void* stream);
+
+/* Token append of the multi-draft loop (sampling/speculative_sampling.py:1644, :1677): every row b*W + w of request b
+ * becomes prefix + the winning draft's n_acc[b] accepted tokens + next_tok[b]; seq_len of all W rows advances by
+ * n_acc[b] + 1.  tokens (B*W, >= S) int64, seq_len (B*W,) int32, active optional (B*W,). */
+int sd_multi_commit(int64_t* tokens, int64_t tokens_stride, int32_t* seq_len, int B, int W, const int32_t* choice,
+                    const int32_t* n_acc, const int64_t* next_tok, const int32_t* active, int S, void* stream);
+
 /* Kernel 3b — per-step input builder for the graph-captured draft/target steps.  For request b the step
  * consumes the q tokens at positions start..start+q-1, start = seq_len[b] + offset; prev_tok (optional)
  * is stored at the last of them first (token append of sampling/kvcache_model.py:293).  Emits input_ids

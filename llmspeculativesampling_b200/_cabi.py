@@ -30,6 +30,8 @@ SIGNATURES = {
                         vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
     "sd_max_fn": (i32, [vp, i64, i64, i64, vp, i64, vp]),
     "sd_kv_append": (i32, [vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "sd_kv_select": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]),
+    "sd_multi_commit": (i32, [vp, i64, vp, i32, i32, vp, vp, vp, vp, i32, vp]),
     "sd_build_step": (i32, [vp, i64, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]),
 }
 

@@ -213,6 +213,22 @@ int sd_kv_append(const void* k_new, const void* v_new, int64_t stride_b, int64_t
                                    S, elem_size, static_cast<cudaStream_t>(stream)));
 }
 
+int sd_kv_select(void* k_cache, void* v_cache, int B, int W, int H, int S, int D, int elem_size, int max_count,
+                 const int32_t* choice, const int32_t* start, int start_stride, const int32_t* count, const int32_t* active,
+                 int active_stride, void* stream) {
+  if (!k_cache || !v_cache || !choice || !start || !count) return fail(SD_EINVAL, "sd_kv_select: null argument");
+  return done("sd_kv_select launch", sd::launch_kv_select(k_cache, v_cache, B, W, H, S, D, elem_size, max_count, choice, start,
+                                                          start_stride, count, active, active_stride, static_cast<cudaStream_t>(stream)));
+}
+
+int sd_multi_commit(int64_t* tokens, int64_t tokens_stride, int32_t* seq_len, int B, int W, const int32_t* choice,
+                    const int32_t* n_acc, const int64_t* next_tok, const int32_t* active, int S, void* stream) {
+  if (!tokens || !seq_len || !choice || !n_acc || !next_tok) return fail(SD_EINVAL, "sd_multi_commit: null argument");
+  return done("sd_multi_commit launch", sd::launch_multi_commit(reinterpret_cast<long long*>(tokens), tokens_stride, seq_len, B, W,
+                                                                choice, n_acc, reinterpret_cast<const long long*>(next_tok), active, S,
+                                                                static_cast<cudaStream_t>(stream)));
+}
+
 int sd_build_step(int64_t* tokens, int64_t tokens_stride, const int32_t* seq_len, int offset, int q,
                   const int64_t* prev_tok, int B, int S, int64_t* input_ids, int64_t* position_ids, int32_t* write_pos,
                   uint8_t* mask, void* stream) {

@@ -73,6 +73,77 @@ cudaError_t launch_kv_append(const void* k_new, const void* v_new, long long sb,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-draft rollback (reference kvcache_model.py:390-396: rollback(end_pos, choice) keeps draft `choice` only; the next
+// forward expands it to all rows again, :180-200).  On static caches with W rows per request: the kept positions
+// [start, start + count) of the winning row are copied over the other W - 1 rows (everything before `start` is the
+// shared prefix and identical already).  One warp per (request, draft != choice, head, position).
+__global__ void kv_select_kernel(unsigned char* __restrict__ kc, unsigned char* __restrict__ vc, int B, int W, int H, int S,
+                                 int row_bytes, int max_count, const int* __restrict__ choice, const int* __restrict__ start,
+                                 int start_stride, const int* __restrict__ count, const int* __restrict__ active, int active_stride) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long r = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  if (r >= static_cast<long long>(B) * W * H * max_count) return;
+  const int j = static_cast<int>(r % max_count);
+  const int h = static_cast<int>((r / max_count) % H);
+  const int w = static_cast<int>((r / (static_cast<long long>(max_count) * H)) % W);
+  const int b = static_cast<int>(r / (static_cast<long long>(max_count) * H * W));
+  if (active != nullptr && active[b * active_stride] == 0) return;
+  const int c = choice[b];
+  if (w == c || j >= count[b]) return;
+  const int pos = start[b * start_stride] + j;
+  if (pos < 0 || pos >= S) return;
+  const long long src = ((static_cast<long long>(b * W + c) * H + h) * S + pos) * row_bytes;
+  const long long dst = ((static_cast<long long>(b * W + w) * H + h) * S + pos) * row_bytes;
+  for (int o = (threadIdx.x & 31) * 16; o < row_bytes; o += 32 * 16) {
+    *reinterpret_cast<uint4*>(kc + dst + o) = *reinterpret_cast<const uint4*>(kc + src + o);
+    *reinterpret_cast<uint4*>(vc + dst + o) = *reinterpret_cast<const uint4*>(vc + src + o);
+  }
+}
+
+cudaError_t launch_kv_select(void* k_cache, void* v_cache, int B, int W, int H, int S, int D, int elem_size, int max_count,
+                             const int* choice, const int* start, int start_stride, const int* count, const int* active,
+                             int active_stride, cudaStream_t st) {
+  const int row_bytes = D * elem_size;
+  if (row_bytes % 16 != 0 || max_count < 1) return cudaErrorInvalidValue;
+  const long long rows = static_cast<long long>(B) * W * H * max_count;
+  if (rows <= 0) return cudaSuccess;
+  const int wpb = 8;
+  kv_select_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+      static_cast<unsigned char*>(k_cache), static_cast<unsigned char*>(v_cache), B, W, H, S, row_bytes, max_count, choice,
+      start, start_stride, count, active, active_stride);
+  return cudaGetLastError();
+}
+
+// Token append of the multi-draft loop (reference speculative_sampling.py:1644, :1677): every row of request b becomes
+// prefix + the winning draft's accepted tokens + the target's token, and all W lengths advance together.
+__global__ void multi_commit_kernel(long long* __restrict__ tokens, long long tokens_stride, int* __restrict__ seq_len, int W,
+                                    const int* __restrict__ choice, const int* __restrict__ n_acc,
+                                    const long long* __restrict__ next_tok, const int* __restrict__ active, int S) {
+  const int b = blockIdx.x;
+  if (active != nullptr && active[b * W] == 0) return;
+  const int c = choice[b], n = n_acc[b];
+  const int L = seq_len[b * W];
+  const long long* src = tokens + static_cast<long long>(b * W + c) * tokens_stride;
+  for (int i = threadIdx.x; i < W * (n + 1); i += blockDim.x) {
+    const int w = i / (n + 1), j = i - w * (n + 1);
+    if (L + j >= S) continue;
+    long long* dst = tokens + static_cast<long long>(b * W + w) * tokens_stride;
+    if (j == n) dst[L + j] = next_tok[b];
+    else if (w != c) dst[L + j] = src[L + j];
+  }
+  __syncthreads();
+  if (threadIdx.x < W) seq_len[b * W + threadIdx.x] = L + n + 1;
+}
+
+cudaError_t launch_multi_commit(long long* tokens, long long tokens_stride, int* seq_len, int B, int W, const int* choice,
+                                const int* n_acc, const long long* next_tok, const int* active, int S, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  if (W < 1 || W > 128) return cudaErrorInvalidValue;
+  multi_commit_kernel<<<static_cast<unsigned>(B), 128, 0, st>>>(tokens, tokens_stride, seq_len, W, choice, n_acc, next_tok, active, S);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Step builder.  For request b with current length L = seq_len[b] the step consumes the q tokens at
 // positions start .. start+q-1, start = L + offset.  If prev_tok is given it is first stored at the
 // last of these positions (the token the previous draft step sampled).  Emits input ids, position

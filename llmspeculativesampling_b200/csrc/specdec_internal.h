@@ -72,6 +72,11 @@ cudaError_t launch_max_fn(const float* x, long long rows, long long V, long long
 cudaError_t launch_kv_append(const void* k_new, const void* v_new, long long sb, long long sh, long long sq,
                              void* k_cache, void* v_cache, const int* pos, int B, int H, int q, int D, int S,
                              int elem_size, cudaStream_t st);
+cudaError_t launch_kv_select(void* k_cache, void* v_cache, int B, int W, int H, int S, int D, int elem_size, int max_count,
+                             const int* choice, const int* start, int start_stride, const int* count, const int* active,
+                             int active_stride, cudaStream_t st);
+cudaError_t launch_multi_commit(long long* tokens, long long tokens_stride, int* seq_len, int B, int W, const int* choice,
+                                const int* n_acc, const long long* next_tok, const int* active, int S, cudaStream_t st);
 cudaError_t launch_build_step(long long* tokens, long long tokens_stride, const int* seq_len, int offset, int q,
                               const long long* prev_tok, int B, int S, long long* input_ids, long long* position_ids,
                               int* write_pos, unsigned char* mask, cudaStream_t st);

@@ -355,6 +355,28 @@ def kv_append(k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor, v
     _cabi.check(rc, "sd_kv_append")
 
 
+def kv_select(k_cache: torch.Tensor, v_cache: torch.Tensor, W: int, choice: torch.Tensor, start: torch.Tensor,
+              start_stride: int, count: torch.Tensor, max_count: int, active: Optional[torch.Tensor] = None,
+              active_stride: int = 1) -> None:
+    """Multi-draft rollback on static caches (B*W, H, S, D): copy positions start .. start+count-1 of every request's
+    winning row over its other rows (sd_kv_select)."""
+    R, H, S, D = k_cache.shape
+    assert R % W == 0 and k_cache.is_contiguous() and v_cache.is_contiguous()
+    rc = _cabi.load().sd_kv_select(k_cache.data_ptr(), v_cache.data_ptr(), R // W, W, H, S, D, k_cache.element_size(),
+                                   int(max_count), choice.data_ptr(), start.data_ptr(), int(start_stride), count.data_ptr(),
+                                   _ptr(active), int(active_stride), _stream())
+    _cabi.check(rc, "sd_kv_select")
+
+
+def multi_commit(tokens: torch.Tensor, seq_len: torch.Tensor, W: int, choice: torch.Tensor, n_acc: torch.Tensor,
+                 next_tok: torch.Tensor, active: Optional[torch.Tensor] = None) -> None:
+    """Token append of the multi-draft loop for all W rows of every request (sd_multi_commit)."""
+    R, S = tokens.shape
+    rc = _cabi.load().sd_multi_commit(tokens.data_ptr(), tokens.stride(0), seq_len.data_ptr(), R // W, W, choice.data_ptr(),
+                                      n_acc.data_ptr(), next_tok.data_ptr(), _ptr(active), S, _stream())
+    _cabi.check(rc, "sd_multi_commit")
+
+
 def build_step(tokens: torch.Tensor, seq_len: torch.Tensor, offset: int, q: int, prev_tok: Optional[torch.Tensor],
                S: int, input_ids: torch.Tensor, position_ids: torch.Tensor, write_pos: torch.Tensor,
                mask: Optional[torch.Tensor]) -> None:

@@ -254,3 +254,30 @@ def test_tiny_hf_llama_multi_draft_and_bild(cuda_lib):
     assert all(0 <= a <= gamma for a in gm["acc_len"]) and gm["target_call_times"] == len(gm["acc_len"])
     assert sum(a + 1 for a in gm["acc_len"]) == got_m.shape[1] - 7
     assert all(0 <= a <= gamma for a in gb["acc_len"]) and gb["approx_call_times"] >= gb["target_call_times"]
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_multi_draft_engine_matches_oracle_per_request(cuda_lib, use_graph):
+    """Batched multi-draft engine (B ragged requests x W drafts, one CUDA graph per iteration, rollback(choice) as a KV row
+    copy inside the graph): every request must emit exactly the tokens / accepted runs / winning drafts of the oracle's
+    batch-1 restatement of the reference loop run on that request's tape."""
+    from llmspeculativesampling_b200.multi_engine import MultiDraftEngine, multi_block
+    V, gamma, W, N = 1000, 4, 3, 20
+    d, t = _pair(V, 17, 0.6)
+    dc, tc = replay_model.make_pair(V, seed=17, noise=0.6)
+    g = torch.Generator().manual_seed(4)
+    prompts = [torch.randint(3, V, (n,), generator=g) for n in (6, 9, 4, 7)]
+    B = len(prompts)
+    tape = torch.rand(N + 1, B, multi_block(gamma, W), generator=g)
+    eng = MultiDraftEngine(d, t, B, W, max(len(p) for p in prompts) + N, gamma, 1.0, 20, 0.9, "cuda", use_cuda_graph=use_graph)
+    eng.load_prompts([p.cuda() for p in prompts], N)
+    iters = eng.run(tape.cuda())
+    assert eng.graph_captured == use_graph
+    outs = eng.results()
+    acc = eng.acc_hist_m[:iters].cpu()
+    cho = eng.choice_hist[:iters].cpu()
+    for b in range(B):
+        want, det = spec_loop.multi_speculative_sampling(prompts[b].unsqueeze(0), dc, tc, N, gamma, W, 1.0, 20, 0.9, tape=tape[:, b])
+        assert outs[b][0].tolist() == want[0].tolist(), f"request {b}"
+        n_it = len(det["acc_len"])
+        assert [int(a) for a in acc[:n_it, b]] == det["acc_len"] and [int(c) for c in cho[:n_it, b]] == det["choices"]
