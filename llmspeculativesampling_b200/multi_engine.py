@@ -41,6 +41,7 @@ class MultiDraftEngine(SpecDecEngine):
         self.ratios_m = torch.zeros(batch, W, g, dtype=torch.float32, device=dev)
         self.acc_hist_m = torch.full((self.max_iterations, batch), -1, dtype=torch.int32, device=dev)
         self.choice_hist = torch.zeros(self.max_iterations, batch, dtype=torch.int32, device=dev)
+        self.ratio_hist_m = torch.zeros(self.max_iterations, batch, W, g, dtype=torch.float32, device=dev)
 
     def load_prompts(self, prompts: Sequence[torch.Tensor], max_new_tokens, eos_token_id: Optional[int] = None) -> None:
         assert len(prompts) == self.n_req
@@ -81,6 +82,7 @@ class MultiDraftEngine(SpecDecEngine):
         act_req = self.active.view(B, W)[:, 0]
         self.acc_hist_m.index_copy_(0, it, torch.where(act_req > 0, self.n_acc_m, torch.full_like(self.n_acc_m, -1)).unsqueeze(0))
         self.choice_hist.index_copy_(0, it, self.choice.unsqueeze(0))
+        self.ratio_hist_m.index_copy_(0, it, self.ratios_m.unsqueeze(0))
         it.add_(1)
         gen = (self._cols >= self.prompt_len.unsqueeze(1)) & (self._cols < self.seq_len.unsqueeze(1))
         hit_eos = ((self.tokens == self.eos) & gen).any(dim=1)

@@ -281,3 +281,26 @@ def test_multi_draft_engine_matches_oracle_per_request(cuda_lib, use_graph):
         assert outs[b][0].tolist() == want[0].tolist(), f"request {b}"
         n_it = len(det["acc_len"])
         assert [int(a) for a in acc[:n_it, b]] == det["acc_len"] and [int(c) for c in cho[:n_it, b]] == det["choices"]
+
+
+def test_kvcache_model_multi_draft_generate_and_rollback_choice(cuda_lib):
+    """KVCacheModel.generate(multi=W, strategy='iid') and rollback(end_pos, choice) (kvcache_model.py:272-276, :390-396)
+    against the oracle's MultiStepper: drafted tokens and probability rows, also after keeping one draft."""
+    from llmspeculativesampling_b200.sampling import KVCacheModel
+    V, gamma, W = 1000, 3, 4
+    d, _ = _pair(V, 23, 0.5)
+    dc, _ = replay_model.make_pair(V, seed=23, noise=0.5)
+    prefix = torch.randint(3, V, (1, 6), generator=torch.Generator().manual_seed(1))
+    u = torch.rand(2, gamma, W, generator=torch.Generator().manual_seed(2))
+    m = KVCacheModel(d, 1.0, 20, 0.9, max_len=64)
+    o = spec_loop.MultiStepper(dc, 1.0, 20, 0.9)
+    x = m.generate(prefix.cuda(), gamma, uniforms=u[0].cuda(), multi=W, strategy="iid")
+    xo = o.generate(prefix.repeat(W, 1), gamma, u[0])
+    assert x.cpu().tolist() == xo.tolist()
+    assert torch.allclose(m._prob_history[:, 5:].cpu(), o.hist[:, 5:], rtol=1e-5, atol=2.0 ** -40)
+    keep, choice = 8, 2
+    m.rollback(keep, choice)
+    o.rollback(keep, choice)
+    x2 = m.generate(x[choice:choice + 1, :keep + 1], gamma, uniforms=u[1].cuda(), multi=W, strategy="iid")
+    xo2 = o.generate(xo[choice:choice + 1, :keep + 1].repeat(W, 1), gamma, u[1])
+    assert x2.cpu().tolist() == xo2.tolist()
