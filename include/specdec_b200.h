@@ -195,10 +195,19 @@ int sd_verify_multi(const float* p_probs, int64_t p_req_stride, int64_t p_draft_
  * request b has n_check[b] (<= max_check; NULL: max_check) unchecked draft tokens draft_tok[b, i] whose target
  * distributions are rows i of p_probs; the target keeps tokens while -log p[i][token] <= rollback_thres (:1800), then
  * always samples its own token from row n = number of kept tokens (:1812) with u_final (row max_check must exist).
- *   n_accepted (B,) kept tokens, next_tok (B,), nll optional (B, max_check) the tested -log p values. */
-int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const int64_t* draft_tok,
-                   int64_t draft_stride, const int32_t* n_check, int max_check, float rollback_thres, const float* u_final,
-                   int B, int64_t V, int32_t* n_accepted, int64_t* next_tok, float* nll, int* err_flag, void* stream);
+ *   n_accepted (B,) kept tokens, next_tok (B,), nll optional (B, max_check) the tested -log p values.
+ * Engine mode (q_probs != NULL, max_check tokens drafted up front in a fixed-shape graph): the number of tokens the
+ * reference would have drafted is derived first — it stops at the first token whose distribution is unsure,
+ * max q[i] < fallback_thres (:1784) — and written to n_drafted[b]; tokens / seq_len (optional, together) get the fused
+ * append tokens[b, seq_len + n] = next_tok, seq_len += n + 1; with limit[b] (optional total-length limit) a request with
+ * less room than drafted tokens ends like the reference's loop (:1764): the drafted tokens stay unchecked, no target
+ * token, n_accepted = -1 - kept tokens, next_tok = -1.  active optional (B,). */
+int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const float* q_probs,
+                   int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
+                   const int32_t* n_check, int max_check, float fallback_thres, float rollback_thres, const float* u_final,
+                   int B, int64_t V, int32_t* n_accepted, int64_t* next_tok, float* nll, int32_t* n_drafted, int64_t* tokens,
+                   int64_t tokens_stride, int32_t* seq_len, const int32_t* limit, const int32_t* active, int* err_flag,
+                   void* stream);
 
 /* max_fn — out = max(x,0) / (sum(max(x,0)) + 1e-6) per row.  Replaces sampling/utils.py:236-245. */
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream);

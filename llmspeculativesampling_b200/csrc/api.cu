@@ -181,18 +181,25 @@ int sd_verify_multi(const float* p_probs, int64_t p_req_stride, int64_t p_draft_
                                                                 choice, static_cast<cudaStream_t>(stream)));
 }
 
-int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const int64_t* draft_tok,
-                   int64_t draft_stride, const int32_t* n_check, int max_check, float rollback_thres, const float* u_final,
-                   int B, int64_t V, int32_t* n_accepted, int64_t* next_tok, float* nll, int* err_flag, void* stream) {
+int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const float* q_probs,
+                   int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
+                   const int32_t* n_check, int max_check, float fallback_thres, float rollback_thres, const float* u_final,
+                   int B, int64_t V, int32_t* n_accepted, int64_t* next_tok, float* nll, int32_t* n_drafted, int64_t* tokens,
+                   int64_t tokens_stride, int32_t* seq_len, const int32_t* limit, const int32_t* active, int* err_flag,
+                   void* stream) {
   if (B == 0) return SD_OK;
   if (!p_probs || !draft_tok || !u_final || !n_accepted || !next_tok || !err_flag) return fail(SD_EINVAL, "sd_verify_bild: null argument");
   if (B < 0 || max_check < 1 || max_check > 32 || V <= 0 || V >= (1LL << 24)) return fail(SD_EINVAL, "sd_verify_bild: bad shape (1 <= max_check <= 32)");
+  if ((tokens == nullptr) != (seq_len == nullptr)) return fail(SD_EINVAL, "sd_verify_bild: tokens and seq_len go together");
   sd::VerifyParams p = {};
   p.p = p_probs; p.p_req_stride = p_req_stride; p.p_row_stride = p_row_stride;
+  p.q = q_probs; p.q_req_stride = q_req_stride; p.q_row_stride = q_row_stride;
   p.draft = reinterpret_cast<const long long*>(draft_tok); p.draft_stride = draft_stride;
   p.u_final = u_final; p.B = B; p.gamma = max_check; p.V = V;
   p.n_accepted = n_accepted; p.next_tok = reinterpret_cast<long long*>(next_tok); p.ratios = nll; p.err_flag = err_flag;
-  return done("sd_verify_bild launch", sd::launch_verify_bild(p, n_check, rollback_thres, static_cast<cudaStream_t>(stream)));
+  p.tokens = reinterpret_cast<long long*>(tokens); p.tokens_stride = tokens_stride; p.seq_len = seq_len; p.active = active;
+  return done("sd_verify_bild launch", sd::launch_verify_bild(p, n_check, fallback_thres, rollback_thres, limit, n_drafted,
+                                                              static_cast<cudaStream_t>(stream)));
 }
 
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream) {

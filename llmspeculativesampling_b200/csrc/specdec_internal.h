@@ -62,7 +62,8 @@ bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster);
 cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStream_t st);
 
 cudaError_t launch_verify(const VerifyParams& p, cudaStream_t st);
-cudaError_t launch_verify_bild(const VerifyParams& v, const int* n_check, float rollback_thres, cudaStream_t st);
+cudaError_t launch_verify_bild(const VerifyParams& v, const int* n_check, float fallback_thres, float rollback_thres,
+                               const int* limit, int* n_drafted, cudaStream_t st);
 cudaError_t launch_verify_multi(const VerifyParams& v, long long p_draft_stride, long long q_draft_stride,
                                 long long draft_draft_stride, int width, int* choice, cudaStream_t st);
 void set_verify_tuning(int cluster);

@@ -410,13 +410,43 @@ cudaError_t launch_verify_multi(const VerifyParams& v, long long p_draft_stride,
 // BiLD check (reference BiLD_sampling, speculative_sampling.py:1793-1813): the target keeps unchecked draft tokens while
 // -log p[token] <= rollback_thres, then ALWAYS samples its own next token from its distribution at the first
 // position it did not keep (plain sample of a p row — there is no residual in BiLD).
-__global__ void __launch_bounds__(kMultiThreads) verify_bild_kernel(const VerifyParams p, const int* n_check, const float rollback_thres) {
+__global__ void __launch_bounds__(kMultiThreads) verify_bild_kernel(const VerifyParams p, const int* n_check, const float fallback_thres,
+                                                                    const float rollback_thres, const int* limit, int* n_drafted) {
   __shared__ RowScratch<kMultiThreads> rs;
   __shared__ int s_n;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int V = static_cast<int>(p.V);
   if (p.active != nullptr && p.active[b] == 0) return;
-  const int nc = n_check != nullptr ? min(n_check[b], p.gamma) : p.gamma;
+  int nc = n_check != nullptr ? min(n_check[b], p.gamma) : p.gamma;
+  if (p.q != nullptr) {
+    // engine mode: gamma tokens were drafted up front; the reference would have stopped drafting at the first token whose
+    // distribution was unsure (max q < fallback_thres, speculative_sampling.py:1784) — tokens after it do not exist for it
+    RowCtx<kMultiThreads> cx(&rs, 1);
+    nc = p.gamma;
+    for (int i = 0; i < p.gamma; ++i) {
+      const float* qrow = p.q + b * p.q_req_stride + i * p.q_row_stride;
+      float m = 0.f;
+      for (int j = tid; j < V; j += kMultiThreads) m = fmaxf(m, qrow[j]);
+      m = cx.allreduce_max(m);
+      if (m < fallback_thres) { nc = i + 1; break; }                       // block-uniform
+    }
+  }
+  if (n_drafted != nullptr && tid == 0) n_drafted[b] = nc;
+  if (limit != nullptr && p.seq_len != nullptr) {
+    // the reference tests its length limit before every draft token (:1764): with fewer than nc tokens of room it leaves
+    // the loop with the drafted tokens unchecked and no target token
+    const int room = limit[b] - p.seq_len[b];
+    if (room < nc) {
+      if (tid == 0) {
+        const int keep = max(room, 0);
+        p.n_accepted[b] = -1 - keep;                                       // (< 0: no check happened; -1 - kept tokens)
+        p.next_tok[b] = -1;
+        p.seq_len[b] += keep;
+        if (n_drafted != nullptr) n_drafted[b] = keep;
+      }
+      return;
+    }
+  }
   if (tid < 32) {
     bool fail = false;
     if (lane < nc) {
@@ -433,12 +463,14 @@ __global__ void __launch_bounds__(kMultiThreads) verify_bild_kernel(const Verify
   VerifyParams vp = p;
   vp.gamma = 0;                                                            // never a residual: plain sample of p row n
   vp.strict = 0;
+  vp.q = nullptr;
   dense_verify_cta<kMultiThreads>(vp, b, s_n, &rs);
 }
 
-cudaError_t launch_verify_bild(const VerifyParams& v, const int* n_check, float rollback_thres, cudaStream_t st) {
+cudaError_t launch_verify_bild(const VerifyParams& v, const int* n_check, float fallback_thres, float rollback_thres,
+                               const int* limit, int* n_drafted, cudaStream_t st) {
   if (v.gamma < 1 || v.gamma > 32) return cudaErrorInvalidValue;
-  verify_bild_kernel<<<static_cast<unsigned>(v.B), kMultiThreads, 0, st>>>(v, n_check, rollback_thres);
+  verify_bild_kernel<<<static_cast<unsigned>(v.B), kMultiThreads, 0, st>>>(v, n_check, fallback_thres, rollback_thres, limit, n_drafted);
   return cudaGetLastError();
 }
 

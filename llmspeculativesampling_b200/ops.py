@@ -274,25 +274,38 @@ def verify_multi(p_probs: torch.Tensor, q_probs: torch.Tensor, draft_tok: torch.
 
 
 def verify_bild(p_probs: torch.Tensor, draft_tok: torch.Tensor, rollback_thres: float, u_final: torch.Tensor,
-                n_check: Optional[torch.Tensor] = None, nll: Optional[torch.Tensor] = None, err: Optional[ErrFlag] = None):
+                n_check: Optional[torch.Tensor] = None, nll: Optional[torch.Tensor] = None, err: Optional[ErrFlag] = None,
+                q_probs: Optional[torch.Tensor] = None, fallback_thres: float = 0.0, n_drafted: Optional[torch.Tensor] = None,
+                tokens: Optional[torch.Tensor] = None, seq_len: Optional[torch.Tensor] = None,
+                limit: Optional[torch.Tensor] = None, active: Optional[torch.Tensor] = None,
+                n_accepted: Optional[torch.Tensor] = None, next_tok: Optional[torch.Tensor] = None):
     """Kernel 2, BiLD variant (sd_verify_bild).  p_probs (B, C+1, V) fp32 target rows of the C unchecked draft tokens
     draft_tok (B, C) int64 (+ the row after them); keeps tokens while -log p[token] <= rollback_thres and samples the
-    target's own token from the first row it did not keep.  Returns (n_kept, next_tok)."""
+    target's own token from the first row it did not keep.  Engine mode: q_probs (B, C, V) + fallback_thres derive the
+    number of tokens the reference would have drafted (-> n_drafted), tokens / seq_len / limit / active as in `verify`.
+    Returns (n_kept, next_tok)."""
     _require_cuda(p_probs, "p_probs")
     B, c1, V = p_probs.shape
     C = c1 - 1
     assert p_probs.dtype == torch.float32 and p_probs.stride(2) == 1
     assert draft_tok.dtype == torch.int64 and draft_tok.shape == (B, C) and draft_tok.stride(1) == 1
     assert u_final.dtype == torch.float32 and u_final.numel() == B and u_final.is_contiguous()
+    if q_probs is not None:
+        assert q_probs.shape == (B, C, V) and q_probs.dtype == torch.float32 and q_probs.stride(2) == 1
     dev = p_probs.device
-    n_acc = torch.empty(B, dtype=torch.int32, device=dev)
-    nxt = torch.empty(B, dtype=torch.int64, device=dev)
+    if n_accepted is None:
+        n_accepted = torch.empty(B, dtype=torch.int32, device=dev)
+    if next_tok is None:
+        next_tok = torch.empty(B, dtype=torch.int64, device=dev)
     err = err or default_flag(dev)
-    rc = _cabi.load().sd_verify_bild(p_probs.data_ptr(), p_probs.stride(0), p_probs.stride(1), draft_tok.data_ptr(),
-                                     draft_tok.stride(0), _ptr(n_check), C, float(rollback_thres), u_final.data_ptr(), B, V,
-                                     n_acc.data_ptr(), nxt.data_ptr(), _ptr(nll), err.ptr(), _stream())
+    rc = _cabi.load().sd_verify_bild(
+        p_probs.data_ptr(), p_probs.stride(0), p_probs.stride(1), _ptr(q_probs),
+        q_probs.stride(0) if q_probs is not None else 0, q_probs.stride(1) if q_probs is not None else 0,
+        draft_tok.data_ptr(), draft_tok.stride(0), _ptr(n_check), C, float(fallback_thres), float(rollback_thres),
+        u_final.data_ptr(), B, V, n_accepted.data_ptr(), next_tok.data_ptr(), _ptr(nll), _ptr(n_drafted), _ptr(tokens),
+        tokens.stride(0) if tokens is not None else 0, _ptr(seq_len), _ptr(limit), _ptr(active), err.ptr(), _stream())
     _cabi.check(rc, "sd_verify_bild")
-    return n_acc, nxt
+    return n_accepted, next_tok
 
 
 def norm_sample_verify(logits: torch.Tensor, temperature: float, top_k: int, top_p: float, u: torch.Tensor,

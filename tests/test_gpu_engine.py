@@ -304,3 +304,35 @@ def test_kvcache_model_multi_draft_generate_and_rollback_choice(cuda_lib):
     x2 = m.generate(x[choice:choice + 1, :keep + 1], gamma, uniforms=u[1].cuda(), multi=W, strategy="iid")
     xo2 = o.generate(xo[choice:choice + 1, :keep + 1].repeat(W, 1), gamma, u[1])
     assert x2.cpu().tolist() == xo2.tolist()
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_bild_engine_matches_oracle_per_request(cuda_lib, use_graph):
+    """Batched BiLD engine (gamma tokens drafted up front in a fixed-shape graph; the kernel derives how many the
+    reference would have drafted, checks them and appends): per request the tokens, kept run lengths and draft counts of
+    the oracle's restatement of the reference loop — including the reference's exit with unchecked tokens at the limit."""
+    from llmspeculativesampling_b200.bild_engine import BiLDEngine
+    V, gamma, N = 1000, 4, 21
+    d, t = _pair(V, 19, 0.6)
+    dc, tc = replay_model.make_pair(V, seed=19, noise=0.6)
+    g = torch.Generator().manual_seed(6)
+    prompts = [torch.randint(3, V, (n,), generator=g) for n in (6, 9, 4, 7, 5)]
+    B = len(prompts)
+    tp = torch.rand(N + 1, B, 2 * gamma + 2, generator=g)
+    fb, rb = 0.45, 2.5
+    eng = BiLDEngine(d, t, B, max(len(p) for p in prompts) + N, gamma, fb, rb, 1.0, 20, 0.9, "cuda", use_cuda_graph=use_graph)
+    eng.load_prompts([p.cuda() for p in prompts], N)
+    iters = eng.run(tp.cuda())
+    assert eng.graph_captured == use_graph
+    outs = eng.results()
+    acc = eng.acc_hist[:iters].cpu()
+    drafted = eng.drafted_hist[:iters].cpu()
+    unchecked_exit = 0
+    for b in range(B):
+        want, det = spec_loop.bild_sampling(prompts[b].unsqueeze(0), dc, tc, N, gamma, fb, rb, 1.0, 20, 0.9, tape=tp[:, b])
+        assert outs[b][0].tolist() == want[0].tolist(), f"request {b}"
+        kept = [int(a) for a in acc[:, b] if a >= 0]
+        assert kept == det["acc_len"]
+        assert int(drafted[:, b].sum()) == det["approx_call_times"]
+        unchecked_exit += int((acc[:, b] < 0).logical_and(acc[:, b] > -1000).any())
+    assert outs[0].shape[1] >= len(prompts[0]) + N
