@@ -288,7 +288,7 @@ def run_variants(args):
                          "draft_tokens": d["approx_call_times"]},
                 "leading_tokens_identical_to_cpu_run": a, "of": n})
     print(json.dumps({"workload": "SURVEY 8f next rows on the config-1 models (llama-68m shapes, identical weights, fp32, batch 1, 64 new tokens)",
-                      "note": "N2 runs on the batched multi-draft engine (one CUDA graph per iteration); N3 is still the reference's host loop on the GPU building blocks",
+                      "note": "both run on their batched CUDA-graph engines (multi_engine.MultiDraftEngine, bild_engine.BiLDEngine), batch 1 here",
                       "results": out}))
     return 0
 

@@ -67,11 +67,12 @@ def test_bild_drop_in_matches_reference_golden_runs(cuda_lib):
         d, t = _pair(r["V"], r["seed"], r["noise"])
         prefix = torch.tensor([r["prefix"]], device="cuda")
         tp = tape.make_tape(r["seed"], r["max_len"] + 1, r["gamma"])
-        out, det = BiLD_sampling(prefix, d, t, r["gamma"], None, None, r["fallback_thres"], r["rollback_thres"], r["max_len"],
-                                 r["temperature"], r["top_k"], r["top_p"], details=True, uniforms=tp)
-        assert out[0].tolist() == r["tokens"], f"V={r['V']} k={r['top_k']} p={r['top_p']} gamma={r['gamma']}"
-        assert det["acc_len"] == r["acc_len"]
-        assert (det["target_call_times"], det["approx_call_times"]) == (r["target_call_times"], r["approx_call_times"])
+        for use_engine in (True, False):                       # batched CUDA-graph engine / the reference's loop on KVCacheModel
+            out, det = BiLD_sampling(prefix, d, t, r["gamma"], None, None, r["fallback_thres"], r["rollback_thres"], r["max_len"],
+                                     r["temperature"], r["top_k"], r["top_p"], details=True, uniforms=tp, use_engine=use_engine)
+            assert out[0].tolist() == r["tokens"], f"V={r['V']} k={r['top_k']} p={r['top_p']} gamma={r['gamma']} engine={use_engine}"
+            assert det["acc_len"] == r["acc_len"]
+            assert (det["target_call_times"], det["approx_call_times"]) == (r["target_call_times"], r["approx_call_times"])
     # EOS cut (:1833-1841): the output ends at the first new EOS
     r = runs[0]
     d, t = _pair(r["V"], r["seed"], r["noise"])
