@@ -126,7 +126,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t phase)
 // NG compute groups share NB slice buffers: work item i uses buffer i % NB and is processed by group i % NG.  A buffer
 // is only held from the TMA issue to the end of the re-scan (~40 % of an item's latency), so NG > NB groups keep the
 // buffers — i.e. the HBM pipe — busier than one group per buffer would.
-template <typename T, int NG, int NB, int CAP>
+template <typename T, int NG, int NB, int CAP, bool FV>   // FV: with the in-kernel verify (its code costs the bf16 variants 3-10 %)
 __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe_kernel(const NormParams p) {
   constexpr int PV = Elem<T>::kPerVec;
   constexpr int GT = kPipeGroupThreads;
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
     PIPE_DBG(1 + g, it * 100 + 7, gt == 0);
     // ---- fused verify: the group that finishes the last row of a request verifies it right away (one warp, from the
     //      compact lists the rows' clusters just wrote; a request that needs the dense scan is left for the end)
-    if (p.fv_rows > 0 && crank == 0) {
+    if constexpr (FV) if (p.fv_rows > 0 && crank == 0) {
       if (gt == 0) {
         __threadfence();                                       // this row's outputs (ordered by the barrier above) first
         const int b = row / p.fv_rows;
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
       norm_row<T, 32 + NG * kPipeGroupThreads>(p2, frow);
       __syncthreads();
       PIPE_DBG(10, 1000 + i * 10 + 4, tid == 0);
-      if (p.fv_rows > 0 && crank == 0) {        // fused verify: count the row; the leader CTA verifies a completed request
+      if constexpr (FV) if (p.fv_rows > 0 && crank == 0) {   // fused verify: count the row; the leader CTA verifies a completed request
         constexpr int TH = 32 + NG * kPipeGroupThreads;
         if (tid == 0) {
           __threadfence();
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe
       }
     }
   }
-  if (p.fv_rows > 0 && crank == 0 && sh.n_pend > 0) {       // requests whose lists were unavailable: dense scan by the CTA
+  if constexpr (FV) if (p.fv_rows > 0 && crank == 0 && sh.n_pend > 0) {   // requests whose lists were unavailable: dense scan by the CTA
     constexpr int TH = 32 + NG * kPipeGroupThreads;
     const int n_pend = sh.n_pend;
     for (int i = 0; i < n_pend; ++i) {
@@ -836,9 +836,9 @@ static bool pipe_fits(const PipeVariant& v, size_t slice_bytes, int C, int kcap)
   return slice_bytes + v.row_need <= static_cast<size_t>(v.nb) * slice_bytes + v.mask_off;
 }
 
-template <typename T, int NG, int NB, int CAP>
-static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStream_t st, int* query_max_clusters) {
-  auto kern = norm_topk_pipe_kernel<T, NG, NB, CAP>;
+template <typename T, int NG, int NB, int CAP, bool FV>
+static cudaError_t pipe_launch_or_query_fv(const NormParams& p, int rows, cudaStream_t st, int* query_max_clusters) {
+  auto kern = norm_topk_pipe_kernel<T, NG, NB, CAP, FV>;
   static bool attr_set_dev[64] = {};            // per device: the attribute belongs to the device's copy of the kernel
   int dev_id = 0;
   (void)cudaGetDevice(&dev_id);
@@ -865,6 +865,12 @@ static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStrea
   }
   cfg.gridDim = dim3(static_cast<unsigned>(p.pipe_clusters) * p.cluster);
   return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <typename T, int NG, int NB, int CAP>
+static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStream_t st, int* query_max_clusters) {
+  return p.fv_rows > 0 ? pipe_launch_or_query_fv<T, NG, NB, CAP, true>(p, rows, st, query_max_clusters)
+                       : pipe_launch_or_query_fv<T, NG, NB, CAP, false>(p, rows, st, query_max_clusters);
 }
 
 template <typename T>
