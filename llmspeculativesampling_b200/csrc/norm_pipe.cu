@@ -119,14 +119,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t phase)
     *reinterpret_cast<volatile long long*>(p.prof + static_cast<long long>(blockIdx.x) * 16 + (slot)) = (val); __threadfence_system(); } } while (0)
 #else
 #define PIPE_DBG(slot, val, cond) do { } while (0)
-#define PIPE_PROF(item, slot, cond) do { if (p.prof != nullptr && (cond) && (item) < 32) \
+#define PIPE_PROF(item, slot, cond) do { if constexpr (PROF) if (p.prof != nullptr && (cond) && (item) < 32) \
     p.prof[(static_cast<long long>(blockIdx.x) * 32 + (item)) * 16 + (slot)] = clock64(); } while (0)
 #endif
 
 // NG compute groups share NB slice buffers: work item i uses buffer i % NB and is processed by group i % NG.  A buffer
 // is only held from the TMA issue to the end of the re-scan (~40 % of an item's latency), so NG > NB groups keep the
 // buffers — i.e. the HBM pipe — busier than one group per buffer would.
-template <typename T, int NG, int NB, int CAP, bool FV>   // FV: with the in-kernel verify (its code costs the bf16 variants 3-10 %)
+// FV: with the in-kernel verify (its code costs the bf16 variants 3-10 %); PROF: with the clock64 timeline (3 % for fp32)
+template <typename T, int NG, int NB, int CAP, bool FV, bool PROF>
 __global__ void __launch_bounds__(32 + NG * kPipeGroupThreads, 1) norm_topk_pipe_kernel(const NormParams p) {
   constexpr int PV = Elem<T>::kPerVec;
   constexpr int GT = kPipeGroupThreads;
@@ -836,9 +837,9 @@ static bool pipe_fits(const PipeVariant& v, size_t slice_bytes, int C, int kcap)
   return slice_bytes + v.row_need <= static_cast<size_t>(v.nb) * slice_bytes + v.mask_off;
 }
 
-template <typename T, int NG, int NB, int CAP, bool FV>
+template <typename T, int NG, int NB, int CAP, bool FV, bool PROF>
 static cudaError_t pipe_launch_or_query_fv(const NormParams& p, int rows, cudaStream_t st, int* query_max_clusters) {
-  auto kern = norm_topk_pipe_kernel<T, NG, NB, CAP, FV>;
+  auto kern = norm_topk_pipe_kernel<T, NG, NB, CAP, FV, PROF>;
   static bool attr_set_dev[64] = {};            // per device: the attribute belongs to the device's copy of the kernel
   int dev_id = 0;
   (void)cudaGetDevice(&dev_id);
@@ -869,8 +870,9 @@ static cudaError_t pipe_launch_or_query_fv(const NormParams& p, int rows, cudaSt
 
 template <typename T, int NG, int NB, int CAP>
 static cudaError_t pipe_launch_or_query(const NormParams& p, int rows, cudaStream_t st, int* query_max_clusters) {
-  return p.fv_rows > 0 ? pipe_launch_or_query_fv<T, NG, NB, CAP, true>(p, rows, st, query_max_clusters)
-                       : pipe_launch_or_query_fv<T, NG, NB, CAP, false>(p, rows, st, query_max_clusters);
+  if (p.fv_rows > 0) return pipe_launch_or_query_fv<T, NG, NB, CAP, true, false>(p, rows, st, query_max_clusters);
+  if (p.prof != nullptr) return pipe_launch_or_query_fv<T, NG, NB, CAP, false, true>(p, rows, st, query_max_clusters);
+  return pipe_launch_or_query_fv<T, NG, NB, CAP, false, false>(p, rows, st, query_max_clusters);
 }
 
 template <typename T>
