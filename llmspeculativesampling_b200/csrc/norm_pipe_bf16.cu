@@ -1,0 +1,10 @@
+// Persistent top-k kernel, __nv_bfloat16 logits: the kernel instantiations of this dtype (see norm_pipe_kernel.cuh).
+#include "norm_pipe_kernel.cuh"
+
+namespace sd {
+
+cudaError_t pipe_dispatch_bf16(const NormParams& p, int rows, cudaStream_t st, int* q) {
+  return pipe_dispatch<__nv_bfloat16>(p, rows, st, q);
+}
+
+}  // namespace sd

@@ -1,0 +1,10 @@
+// Persistent top-k kernel, float logits: the kernel instantiations of this dtype (see norm_pipe_kernel.cuh).
+#include "norm_pipe_kernel.cuh"
+
+namespace sd {
+
+cudaError_t pipe_dispatch_f32(const NormParams& p, int rows, cudaStream_t st, int* q) {
+  return pipe_dispatch<float>(p, rows, st, q);
+}
+
+}  // namespace sd
