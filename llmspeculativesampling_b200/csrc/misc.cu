@@ -159,10 +159,13 @@ __global__ void build_step_kernel(long long* __restrict__ tokens, long long toke
   long long* trow = tokens + b * tokens_stride;
   if (threadIdx.x < q) {
     const int j = threadIdx.x;
-    long long tok = trow[start + j];
-    if (prev_tok != nullptr && j == q - 1) { tok = prev_tok[b]; trow[start + j] = tok; }
+    // A request that has finished keeps being stepped while others in the batch run (its results are discarded): its
+    // positions may reach past the token buffer.  Reads are clamped, the append is skipped — never touch row b + 1.
+    const bool inb = start + j < S;
+    long long tok = trow[inb ? start + j : S - 1];
+    if (prev_tok != nullptr && j == q - 1) { tok = prev_tok[b]; if (inb) trow[start + j] = tok; }
     input_ids[b * q + j] = tok;
-    position_ids[b * q + j] = start + j;
+    position_ids[b * q + j] = min(start + j, S - 1);
   }
   if (threadIdx.x == 0) write_pos[b] = start;
   if (mask != nullptr) {

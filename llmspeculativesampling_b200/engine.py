@@ -135,7 +135,9 @@ class SpecDecEngine:
         self.B, self.gamma = batch, gamma
         self.T, self.top_k, self.top_p = float(temperature), int(top_k or 0), float(top_p or 0.0)
         self.strict = strict
-        self.S = (max_total_len + gamma + 2 + 63) // 64 * 64
+        # a finished request is still stepped while others run: it can sit at limit + gamma and the target step then
+        # appends at limit + 2 * gamma - 1 (sd_build_step also bounds-checks)
+        self.S = (max_total_len + 2 * gamma + 2 + 63) // 64 * 64
         self.draft = ModelStepper(approx_model, batch, self.S, self.device)
         self.target = ModelStepper(target_model, batch, self.S, self.device)
         if self.draft.V != self.target.V:

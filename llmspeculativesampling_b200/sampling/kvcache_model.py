@@ -137,6 +137,11 @@ class KVCacheModel:
         assert self._stepper is not None and self._n > 0                   # reference: assert self._past_key_values
         self._n = min(self._n, int(end_pos))
         if choice is not None and self._stepper.B > 1:
-            c, n = int(choice), self._n
-            for t in self._stepper.cache.k + self._stepper.cache.v:
-                t[:, :, :n].copy_(t[c:c + 1, :, :n].expand(t.shape[0], -1, -1, -1).clone())
+            W, n, dev = self._stepper.B, self._n, self._tokens.device
+            ch = torch.full((1,), int(choice), dtype=torch.int32, device=dev)
+            start = torch.zeros(1, dtype=torch.int32, device=dev)
+            count = torch.full((1,), n, dtype=torch.int32, device=dev)
+            for k, v in zip(self._stepper.cache.k, self._stepper.cache.v):
+                ops.kv_select(k, v, W, ch, start, 1, count, n)             # the W rows are one "request" of W drafts
+            # the reference collapses _prob_history to the chosen row (:430-436); with static buffers every row gets it
+            self._prob_buf[:, :n].copy_(self._prob_buf[int(choice):int(choice) + 1, :n].expand(W, -1, -1).clone())

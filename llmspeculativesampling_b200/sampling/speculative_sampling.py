@@ -85,7 +85,12 @@ def _run(prefix, approx_model, target_model, eos_token_id, max_len, gamma, tempe
     rat = eng.ratio_hist[:iters].cpu().numpy()
     acc_len = [[int(a) for a in acc[:, b] if a >= 0] for b in range(B)]
     live = acc >= 0
-    rates = np.minimum(1.0, rat.astype(np.float64))[live]
+    if strict:
+        # v2 appends min(1, p/q) only for the tokens it tests — up to and including the first reject (:2155)
+        tested = np.arange(rat.shape[2])[None, None, :] <= acc[:, :, None]
+        rates = np.minimum(1.0, rat.astype(np.float64))[live[:, :, None] & tested]
+    else:
+        rates = np.minimum(1.0, rat.astype(np.float64))[live]              # every drafted token (:1966-1971)
     d = {
         "approx_time": 0, "target_time": 0, "other_time": elapsed,          # one fused graph: no per-phase split
         "acc_len": acc_len[0] if B == 1 else acc_len,

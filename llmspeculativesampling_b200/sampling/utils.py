@@ -15,6 +15,8 @@ def top_k_top_p_filter(logits: torch.Tensor, top_k: int = 0, top_p: float = 0.0)
     set's probabilities (an entry whose probability underflows to exactly 0 is masked too — it has
     probability 0 either way)."""
     assert logits.dim() == 2
+    if not top_k and not top_p:
+        return logits                                                     # both stages disabled: nothing to mask
     probs = ops.norm_probs(logits, 1.0, top_k or 0, top_p or 0.0)
     logits.masked_fill_(probs == 0, float("-inf"))
     return logits

@@ -9,6 +9,10 @@ Fixtures (all produced by code under /root/reference, imported in place by oracl
   bild_runs.json    end-to-end sampling.speculative_sampling.BiLD_sampling on the replay models
   spec_runs.json    end-to-end sampling.speculative_sampling on the replay models with the
                     uniform tape: emitted token ids, acc_len per iteration, acc_rate
+  v2_runs.json      end-to-end sampling.speculative_sampling.speculative_sampling_v2 (:2080-2194), same tape layout
+  ar_runs.json      end-to-end sampling.autoregressive_sampling.autoregressive_sampling (:9-61), one uniform per token
+
+    python -m oracle.make_golden [v2 ar ...]     only the named fixtures (default: all)
 """
 from __future__ import annotations
 
@@ -89,9 +93,64 @@ def write_multi():
         json.dump(runs, f)
 
 
+V2_CASES = [   # V, top_k, top_p, T, gamma, max_len, seed, noise
+    (1000, 20, 0.9, 0.8, 4, 40, 51, 0.5), (32000, 20, 0.9, 1.0, 4, 20, 52, 0.5), (500, 0, 0.0, 1.0, 4, 32, 53, 0.5),
+    (777, 0, 0.9, 1.3, 3, 32, 54, 0.3), (900, 5, 0.0, 0.7, 5, 32, 55, 0.8), (2048, 20, 0.9, 1.0, 1, 20, 56, 0.5),
+    (1000, 20, 0.9, 1.0, 8, 40, 57, 0.0), (1500, 10, 0.5, 1.0, 4, 32, 58, 2.0),
+]
+
+
+def write_v2():
+    """v2_runs.json: the reference's speculative_sampling_v2 (speculative_sampling.py:2080-2194) on the replay models."""
+    runs = []
+    for (V, k, p, T, gamma, max_len, seed, noise) in V2_CASES:
+        d, t = replay_model.make_pair(V, seed=seed, noise=noise)
+        prefix = torch.randint(3, V, (1, 7), generator=torch.Generator().manual_seed(seed))
+        tp = tape.make_tape(seed, max_len + 1, gamma)
+        out, det = ref_loader.run_reference_v2(prefix, d, t, max_len, gamma, T, k, p, tape=tp)
+        runs.append(dict(V=V, top_k=k, top_p=p, temperature=T, gamma=gamma, max_len=max_len, seed=seed, noise=noise,
+                         prefix=prefix[0].tolist(), tokens=out[0].tolist(), acc_len=[int(a) for a in det["acc_len"]],
+                         acc_rate=float(det["acc_rate"])))
+        print("v2", V, k, p, T, gamma, "mean acc", np.mean(det["acc_len"]))
+    with open(os.path.join(OUT, "v2_runs.json"), "w") as f:
+        json.dump(runs, f)
+
+
+AR_CASES = [   # V, top_k, top_p, T, N, seed, eos (None: never stops early)
+    (1000, 20, 0.9, 0.8, 40, 61, None), (32000, 20, 0.9, 1.0, 24, 62, None), (500, 0, 0.0, 1.0, 40, 63, None),
+    (777, 0, 0.9, 1.3, 32, 64, None), (900, 5, 0.0, 0.7, 32, 65, None), (300, 1, 0.0, 1.0, 16, 66, None),
+    (64, 0, 0.0, 1.0, 200, 67, 5), (50272, 20, 0.9, 0.8, 12, 68, None),
+]
+
+
+def ar_uniforms(seed: int, N: int) -> torch.Tensor:
+    return torch.rand(N, generator=torch.Generator().manual_seed(int(seed)))
+
+
+def write_ar():
+    """ar_runs.json: the reference's autoregressive_sampling (autoregressive_sampling.py:9-61) on the replay target."""
+    runs = []
+    for (V, k, p, T, N, seed, eos) in AR_CASES:
+        _, t = replay_model.make_pair(V, seed=seed, noise=0.5)
+        prefix = torch.randint(3, V, (1, 7), generator=torch.Generator().manual_seed(seed))
+        out = ref_loader.run_reference_ar(prefix, t, N, T, k, p, ar_uniforms(seed, N), eos_token_id=-1 if eos is None else eos)
+        runs.append(dict(V=V, top_k=k, top_p=p, temperature=T, N=N, seed=seed, eos=eos, prefix=prefix[0].tolist(),
+                         tokens=out[0].tolist()))
+        print("ar", V, k, p, T, N, "generated", out.shape[1] - 7)
+    with open(os.path.join(OUT, "ar_runs.json"), "w") as f:
+        json.dump(runs, f)
+
+
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
+    only = set(sys.argv[1:])
+    if only:
+        for name, fn in (("v2", write_v2), ("ar", write_ar), ("bild", write_bild), ("multi", write_multi)):
+            if name in only:
+                fn()
+        return
     utils = ref_loader.load_utils()
     blob = {}
     for ci, (V, rows, T, k, p, scale, seed, dtype) in enumerate(NORM_CASES):
@@ -127,6 +186,8 @@ def main():
         json.dump(runs, f)
     write_bild()
     write_multi()
+    write_v2()
+    write_ar()
     print("wrote", os.listdir(OUT))
 
 

@@ -302,3 +302,77 @@ def run_reference_multi(prefix, approx_model, target_model, max_len, gamma, widt
     finally:
         kv.sample, ss.sample, ss.torch = saved
     return out, d
+
+
+class V2TapeRNG:
+    """Feeds the reference's speculative_sampling_v2 (speculative_sampling.py:2080-2194) from the (iterations, 2*gamma+2)
+    tape: per iteration gamma draft samples (u_draft), the accept uniforms it draws lazily (u_acc, a prefix is used),
+    then exactly ONE more sample — the residual (:2161) or the bonus (:2178) — which uses u_final and closes the
+    iteration.  Slot gamma (u_discard) is unused: v2 has no discarded sample."""
+
+    def __init__(self, tape: torch.Tensor, gamma: int):
+        self.tape, self.gamma = tape, gamma
+        self.it = 0
+        self.n_sample = 0
+        self.n_rand = 0
+
+    def sample(self, probs: torch.Tensor, num_samples: int = 1):
+        g, c = self.gamma, self.n_sample
+        u = self.tape[self.it, c] if c < g else self.tape[self.it, 2 * g + 1]
+        tok = ref_ops.icdf_sample(probs.reshape(-1), float(u))            # raises 'prob error' on an empty residual
+        self.n_sample += 1
+        if c == g:
+            self.it += 1
+            self.n_sample = 0
+            self.n_rand = 0
+        return torch.tensor([[tok]], dtype=torch.long, device=probs.device)
+
+    def rand(self, *size, **kw):
+        u = self.tape[self.it, self.gamma + 1 + self.n_rand]
+        self.n_rand += 1
+        return u.reshape(1).clone().to(kw.get("device", "cpu"))
+
+
+def run_reference_v2(prefix, approx_model, target_model, max_len, gamma, temperature, top_k, top_p, tape=None, seed=0):
+    """Run the real ``sampling.speculative_sampling.speculative_sampling_v2`` (speculative_sampling.py:2080-2194, no KV
+    cache, so no cache shim is involved) on the tape.  Returns (tokens, details)."""
+    if tape is None:
+        tape = tape_mod.make_tape(seed, max_len + 1, gamma)
+    rng = V2TapeRNG(tape, gamma)
+    load_package()
+    ss = sys.modules["sampling.speculative_sampling"]
+    saved = (ss.sample, ss.torch)
+    real_torch = ss.torch
+
+    class _TorchProxy:
+        def __getattr__(self, name):
+            return rng.rand if name == "rand" else getattr(real_torch, name)
+
+    try:
+        ss.sample, ss.torch = rng.sample, _TorchProxy()
+        out, d = ss.speculative_sampling_v2(prefix, approx_model, target_model, max_len, gamma=gamma,
+                                            temperature=temperature, top_k=top_k, top_p=top_p, details=True)
+    finally:
+        ss.sample, ss.torch = saved
+    return out, d
+
+
+def run_reference_ar(x, model, N, temperature, top_k, top_p, uniforms, eos_token_id=-1):
+    """Run the real ``sampling.autoregressive_sampling.autoregressive_sampling`` (autoregressive_sampling.py:9-61) with
+    its ``sample`` fed from `uniforms` (one per generated token).  Returns the token tensor."""
+    load_package()
+    ar = importlib.import_module("sampling.autoregressive_sampling")
+    state = {"i": 0}
+
+    def tape_sample(probs, num_samples=1):
+        tok = ref_ops.icdf_sample(probs.reshape(-1), float(uniforms[state["i"]]))
+        state["i"] += 1
+        return torch.tensor([[tok]], dtype=torch.long, device=probs.device)
+
+    saved = ar.sample
+    try:
+        ar.sample = tape_sample
+        out = ar.autoregressive_sampling(x, model, N, eos_token_id, temperature=temperature, top_k=top_k, top_p=top_p)
+    finally:
+        ar.sample = saved
+    return out

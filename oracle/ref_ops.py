@@ -203,74 +203,6 @@ def verify_multi_request(p_rows: torch.Tensor, q_rows: torch.Tensor, draft: torc
     max_l, choice, all_acc = 0, 0, False
     ratios = np.zeros((W, gamma), dtype=np.float32)
     with np.errstate(divide="ignore", invalid="ignore"):
-        ratio = (p_at / q_at).astype(np.float32)
-    n_acc, ties = len(ratio), 0
-    for i in range(len(ratio)):
-        if q_at[i] == 0.0:
-            raise RuntimeError("s")                                        # ZeroDivisionError -> 's' (:2044-2046)
-        thr = min(np.float32(1.0), ratio[i]) if strict else ratio[i]
-        if u_acc[i] == thr:
-            ties += 1
-        ok = (u_acc[i] < thr) if strict else (not (u_acc[i] > thr))
-        if not ok:
-            n_acc = i
-            break
-    return n_acc, ratio, ties
-
-
-def verify_request(p_rows: torch.Tensor, q_rows: torch.Tensor, draft: torch.Tensor,
-                   u_acc, u_final: float, strict: bool = False, residual: str = "raw",
-                   return_margin: bool = False):
-    """One request's verify step.
-
-    p_rows (gamma+1, V) target probs for positions L-1 .. L+gamma-1, q_rows (gamma, V) draft
-    probs for positions L-1 .. L+gamma-2, draft (gamma,) drafted token ids.
-    residual='raw'        sample from max(0, p-q) directly (the kernels' rule);
-    residual='normalised' sample from max_fn(p-q), exactly what the patched reference does
-                          (speculative_sampling.py:2007); the two differ only when u lands within
-                          ~1e-7 of a CDF step.
-    Returns (n_accepted, next_token, ratios, ties[, margin]).
-    """
-    gamma = q_rows.shape[0]
-    d = draft.reshape(-1).tolist()
-    p_at = np.array([float(p_rows[i, d[i]]) for i in range(gamma)], dtype=np.float32)
-    q_at = np.array([float(q_rows[i, d[i]]) for i in range(gamma)], dtype=np.float32)
-    n_acc, ratio, ties = accept_scan(p_at, q_at, u_acc, strict)
-    if n_acc < gamma:                                                      # :2005-2015
-        res = residual_weights(p_rows[n_acc], q_rows[n_acc])
-        if residual == "normalised":
-            res = max_fn(res.unsqueeze(0))[0]
-        try:
-            out = icdf_sample(res, u_final, return_margin=True)
-        except RuntimeError:
-            if strict:                                                     # v2 re-raises (:2163-2170)
-                raise
-            out = icdf_sample(p_rows[n_acc].float(), u_final, return_margin=True)   # :2009-2010 fallback
-    else:                                                                  # :2016-2023 bonus token
-        out = icdf_sample(p_rows[gamma].float(), u_final, return_margin=True)
-    tok, margin = out
-    if return_margin:
-        return n_acc, tok, ratio, ties, margin
-    return n_acc, tok, ratio, ties
-
-
-def verify_multi_request(p_rows: torch.Tensor, q_rows: torch.Tensor, draft: torch.Tensor, u_seq, u_final: float,
-                         residual: str = "raw"):
-    """One request's verify step of multi_speculative_sampling(strategy='iid'), speculative_sampling.py:1612-1667.
-
-    p_rows (W, gamma+1, V), q_rows (W, gamma, V), draft (W, gamma); u_seq: the accept uniforms IN DRAWING ORDER (draft 0
-    until its first reject, then draft 1, ...).  Accept iff r < min(1, p/q) (fp32 divide; a NaN ratio rejects); the first
-    draft with the longest accepted run wins, an all-accepted draft ends the scan.  Residual / bonus sampling as in
-    verify_request (non-strict: an empty residual falls back to p).  Returns (choice, n_accepted, next_token, ratios)."""
-    W, gamma = draft.shape
-    n_rand = 0
-    max_l, choice, all_acc = 0, 0, False
-    ratios = np.zeros((W, gamma), dtype=np.float32)
-    for w in range(W):
-        for i in range(gamma):
-            j = int(draft[w, i])
-            ratios[w, i] = np.float32(p_rows[w, i, j]) / np.float32(q_rows[w, i, j]) if float(q_rows[w, i, j]) != 0 or float(p_rows[w, i, j]) != 0 else np.float32("nan")
-    with np.errstate(divide="ignore", invalid="ignore"):
         for w in range(W):
             for i in range(gamma):
                 j = int(draft[w, i])

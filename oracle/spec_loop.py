@@ -174,7 +174,6 @@ def autoregressive_sampling(x: torch.Tensor, model, N: int, eos_token_id: Option
                             uniforms: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
     """Target-only loop, one uniform per generated token.  autoregressive_sampling.py:9-61."""
     if uniforms is None:
-        uniforms = tape_mod.make_tape(seed, N, 0).reshape(-1)[:N] if N > 0 else torch.zeros(0)
         uniforms = torch.rand(N, generator=torch.Generator().manual_seed(int(seed)))
     kv = None
     for i in range(N):                                                      # n = len(x) = 1 -> exactly N tokens (:13-21)

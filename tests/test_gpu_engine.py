@@ -300,8 +300,11 @@ def test_kvcache_model_multi_draft_generate_and_rollback_choice(cuda_lib):
     assert x.cpu().tolist() == xo.tolist()
     assert torch.allclose(m._prob_history[:, 5:].cpu(), o.hist[:, 5:], rtol=1e-5, atol=2.0 ** -40)
     keep, choice = 8, 2
+    kept = m._prob_history[choice, :keep].clone()
     m.rollback(keep, choice)
     o.rollback(keep, choice)
+    # the reference collapses _prob_history to the chosen draft (kvcache_model.py:430-436): every row now holds it
+    assert m._prob_history.shape[1] == keep and all(torch.equal(m._prob_history[w], kept) for w in range(W))
     x2 = m.generate(x[choice:choice + 1, :keep + 1], gamma, uniforms=u[1].cuda(), multi=W, strategy="iid")
     xo2 = o.generate(xo[choice:choice + 1, :keep + 1].repeat(W, 1), gamma, u[1])
     assert x2.cpu().tolist() == xo2.tolist()

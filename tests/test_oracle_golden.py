@@ -88,6 +88,56 @@ def test_bild_restatement_matches_reference_runs():
         assert (det["target_call_times"], det["approx_call_times"]) == (r["target_call_times"], r["approx_call_times"])
 
 
+@pytest.mark.parametrize("residual", ["normalised", "raw"])
+def test_v2_restatement_matches_reference_runs(residual):
+    """The reference's speculative_sampling_v2 (speculative_sampling.py:2080-2194: no KV cache, strict accept test,
+    tape-driven, unmodified code) vs the oracle's restatement: tokens, accepted run per iteration, acc_rate."""
+    runs = json.load(open(os.path.join(GOLD, "v2_runs.json")))
+    torch.set_num_threads(1)
+    for r in runs:
+        if r["V"] > 4096:
+            continue                                    # keep the CPU suite short (the GPU tests cover V = 32000)
+        d, t = replay_model.make_pair(r["V"], seed=r["seed"], noise=r["noise"])
+        tp = tape.make_tape(r["seed"], r["max_len"] + 1, r["gamma"])
+        out, det = spec_loop.speculative_sampling_v2(torch.tensor([r["prefix"]]), d, t, r["max_len"], r["gamma"],
+                                                     r["temperature"], r["top_k"], r["top_p"], tape=tp, residual=residual)
+        assert out[0].tolist() == r["tokens"], r
+        assert det["acc_len"] == r["acc_len"]
+        assert abs(det["acc_rate"] - r["acc_rate"]) < 1e-6
+
+
+def test_autoregressive_restatement_matches_reference_runs():
+    """The reference's autoregressive_sampling (autoregressive_sampling.py:9-61, its sample fed from one uniform per
+    token, unmodified code) vs the oracle's restatement, including the EOS stop (:55)."""
+    from oracle import make_golden
+    runs = json.load(open(os.path.join(GOLD, "ar_runs.json")))
+    torch.set_num_threads(1)
+    assert any(r["eos"] is not None and len(r["tokens"]) < len(r["prefix"]) + r["N"] for r in runs), "no run stops at EOS"
+    for r in runs:
+        if r["V"] > 4096:
+            continue
+        _, t = replay_model.make_pair(r["V"], seed=r["seed"], noise=0.5)
+        out = spec_loop.autoregressive_sampling(torch.tensor([r["prefix"]]), t, r["N"], r["eos"], r["temperature"], r["top_k"],
+                                                r["top_p"], uniforms=make_golden.ar_uniforms(r["seed"], r["N"]))
+        assert out[0].tolist() == r["tokens"], r
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the dev container")
+def test_v2_and_autoregressive_oracle_match_live_reference():
+    torch.set_num_threads(1)
+    d, t = replay_model.make_pair(640, seed=47, noise=0.6)
+    prefix = torch.randint(3, 640, (1, 6), generator=torch.Generator().manual_seed(47))
+    for (T, k, p, gamma) in [(0.9, 20, 0.9, 4), (1.0, 0, 0.0, 3)]:
+        tp = tape.make_tape(47, 25, gamma)
+        a, da = ref_loader.run_reference_v2(prefix, d, t, 24, gamma, T, k, p, tape=tp)
+        b, db = spec_loop.speculative_sampling_v2(prefix, d, t, 24, gamma, T, k, p, tape=tp, residual="normalised")
+        assert torch.equal(a, b) and [int(x) for x in da["acc_len"]] == db["acc_len"]
+        assert abs(float(da["acc_rate"]) - db["acc_rate"]) < 1e-6
+        u = torch.rand(20, generator=torch.Generator().manual_seed(48))
+        assert torch.equal(ref_loader.run_reference_ar(prefix, t, 20, T, k, p, u),
+                           spec_loop.autoregressive_sampling(prefix, t, 20, None, T, k, p, uniforms=u))
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the dev container")
 def test_bild_oracle_matches_live_reference():
     torch.set_num_threads(1)
