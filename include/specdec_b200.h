@@ -105,6 +105,8 @@ int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_
  * cluster before the kernel ends); every other case uses the one-cluster-per-row kernel. */
 #define SD_NORM_DEFAULT 0
 #define SD_NORM_NO_PIPELINE 1   /* one-cluster-per-row kernel even where the pipeline applies                 */
+#define SD_NORM_NO_RING 4       /* skip the ring kernel (one CTA per SM, whole rows through a shared-memory ring): use the
+                                   cluster pipeline / one-cluster-per-row kernels even where a row fits one CTA           */
 #define SD_NORM_FORCE_GENERAL 2 /* test hook: sort-free threshold-search path (normally top_k = 0, top_k > 128
                                    or rows with massive ties only); implies SD_NORM_NO_PIPELINE                */
 

@@ -9,7 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libspecdec_b200.so")
-SOURCES = ["norm.cu", "norm_pipe.cu", "norm_pipe_f32.cu", "norm_pipe_bf16.cu", "norm_pipe_f16.cu", "verify.cu", "misc.cu", "api.cu"]
+SOURCES = ["norm.cu", "norm_pipe.cu", "norm_pipe_f32.cu", "norm_pipe_bf16.cu", "norm_pipe_f16.cu", "norm_ring.cu", "norm_ring_f32.cu",
+           "norm_ring_bf16.cu", "norm_ring_f16.cu", "verify.cu", "misc.cu", "api.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "specdec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

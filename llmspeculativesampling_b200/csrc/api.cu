@@ -64,6 +64,7 @@ static int fill_norm(const void* logits, int dtype, int64_t rows, int64_t V, int
   p.cmp = to_compact(compact);
   p.force_general = (flags & SD_NORM_FORCE_GENERAL) ? 1 : 0;
   p.no_pipeline = ((flags & SD_NORM_NO_PIPELINE) || workspace == nullptr) ? 1 : 0;
+  p.no_ring = (flags & SD_NORM_NO_RING) ? 1 : 0;
   p.sched = static_cast<unsigned int*>(workspace);
   return SD_OK;
 }

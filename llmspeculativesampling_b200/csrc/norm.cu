@@ -60,13 +60,13 @@ static cudaError_t launch_cfg(const NormParams& p, size_t smem, int rows, cudaSt
   (void)cudaGetDevice(&dev_id);
   bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, device_max_smem_optin());
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   int n_cl = rows;
-  if (p.row_filter != nullptr) n_cl = min(rows, max(1, 148 / p.cluster));   // follow-up mode: walk the rows
+  if (p.row_filter != nullptr) n_cl = min(rows, max(1, device_sm_count() / p.cluster));   // follow-up mode: walk the rows
   cfg.gridDim = dim3(static_cast<unsigned>(n_cl) * p.cluster);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem;
@@ -87,7 +87,7 @@ static cudaError_t launch_typed(NormParams p, int rows, cudaStream_t st) {
   const long long row_bytes = p.V * static_cast<long long>(es);
   int C = 1;
   while (C < kMaxPortableCluster && (row_bytes + C - 1) / C > 64 * 1024) C <<= 1;
-  while (C < kMaxPortableCluster && static_cast<long long>(rows) * C < 148 && row_bytes / (2 * C) >= 8192) C <<= 1;
+  while (C < kMaxPortableCluster && static_cast<long long>(rows) * C < device_sm_count() && row_bytes / (2 * C) >= 8192) C <<= 1;
   {
     // every CTA publishes at least min(k, slice) candidates: keep the per-rank share of the merged list above that
     const int kc = p.top_k > 0 ? p.top_k : (p.top_p > 0.f ? kTopPCandidates : 0);
@@ -112,15 +112,15 @@ static cudaError_t launch_typed(NormParams p, int rows, cudaStream_t st) {
   switch (threads) {
     case 512:
       smem = slice_bytes + sizeof(NormShared<512>);
-      if (smem > 227 * 1024) return cudaErrorInvalidValue;
+      if (smem > device_max_smem_optin()) return cudaErrorInvalidValue;
       return launch_cfg<T, 512, 1>(p, smem, rows, st);
     case 1024:
       smem = slice_bytes + sizeof(NormShared<1024>);
-      if (smem > 227 * 1024) return cudaErrorInvalidValue;
+      if (smem > device_max_smem_optin()) return cudaErrorInvalidValue;
       return launch_cfg<T, 1024, 1>(p, smem, rows, st);
     default:
       smem = slice_bytes + sizeof(NormShared<256>);
-      if (smem > 227 * 1024) return cudaErrorInvalidValue;
+      if (smem > device_max_smem_optin()) return cudaErrorInvalidValue;
       return launch_cfg<T, 256, 3>(p, smem, rows, st);
   }
 }
@@ -132,7 +132,9 @@ cudaError_t launch_norm(const NormParams& pin, int dtype, int rows, cudaStream_t
   p.prof = g_prof;
   p.row_filter = nullptr;
   p.fv_rows = 0;
-  // persistent pipelined kernel where it applies (it falls back to the general path per row by itself)
+  // ring kernel (one persistent CTA per SM, whole rows through a shared-memory ring) where a row fits one CTA;
+  // else the persistent cluster pipeline where it applies (both fall back to the general path per row by themselves)
+  if (g_tune_threads == 0 && g_tune_cluster == 0 && plan_ring(p, dtype, rows)) return launch_norm_ring(p, dtype, st);
   if (g_tune_threads == 0 && !p.no_pipeline && plan_pipe(p, dtype, rows, g_tune_cluster)) return launch_norm_pipe(p, dtype, rows, st);
   return launch_classic(p, dtype, rows, st);
 }

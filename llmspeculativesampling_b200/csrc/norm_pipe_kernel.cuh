@@ -813,7 +813,7 @@ constexpr int kNumPipeVariants = 4;
 // failed-item mask, and k + slack candidates per cluster rank
 static bool pipe_fits(const PipeVariant& v, size_t slice_bytes, int C, int kcap) {
   if (kcap > v.cap / C) return false;
-  if (static_cast<size_t>(v.nb) * slice_bytes + v.fixed > 227 * 1024) return false;
+  if (static_cast<size_t>(v.nb) * slice_bytes + v.fixed > device_max_smem_optin()) return false;
   return slice_bytes + v.row_need <= static_cast<size_t>(v.nb) * slice_bytes + v.mask_off;
 }
 
@@ -825,7 +825,7 @@ static cudaError_t pipe_launch_or_query_fv(const NormParams& p, int rows, cudaSt
   (void)cudaGetDevice(&dev_id);
   bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, device_max_smem_optin());
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -841,7 +841,7 @@ static cudaError_t pipe_launch_or_query_fv(const NormParams& p, int rows, cudaSt
   cfg.attrs = at; cfg.numAttrs = (pdl_enabled() && query_max_clusters == nullptr) ? 2 : 1;
   if (query_max_clusters != nullptr) {
     // a persistent grid must be co-resident: clusters cannot use every SM (GPC boundaries), ask the driver
-    cfg.gridDim = dim3(static_cast<unsigned>(p.cluster) * 148);
+    cfg.gridDim = dim3(static_cast<unsigned>(p.cluster * device_sm_count()));
     return cudaOccupancyMaxActiveClusters(query_max_clusters, kern, &cfg);
   }
   cfg.gridDim = dim3(static_cast<unsigned>(p.pipe_clusters) * p.cluster);

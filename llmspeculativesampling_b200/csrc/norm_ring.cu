@@ -1,0 +1,86 @@
+// Kernel 1, ring version — planning and launch (the kernel is in norm_ring_kernel.cuh, instantiated per logits dtype in
+// norm_ring_f32.cu / _bf16.cu / _f16.cu).
+//
+// The ring kernel serves the two settings the reference actually runs with (evaluation.py uses top_k = 20,
+// top_p = 0.9; the API default is top_k = 0, top_p = 0, /root/reference/sampling/speculative_sampling.py:1879-1880):
+//     TOPK   0 < top_k <= 128, any top_p
+//     DENSE  top_k = 0, top_p = 0
+// whenever a row fits the shared-memory ring of one CTA (V * sizeof(logit) <= slots * 16 KB: every vocabulary of the
+// named models in fp32 up to V = 53248, in bf16 / fp16 up to V = 106496), rows are 16-byte aligned and a scheduler
+// workspace is given.  Everything else keeps using the cluster kernels (norm_pipe.cu, norm.cu).
+#include "norm_ring_kernel.cuh"
+
+namespace sd {
+
+cudaError_t ring_dispatch_f32(const NormParams& p, cudaStream_t st);
+cudaError_t ring_dispatch_bf16(const NormParams& p, cudaStream_t st);
+cudaError_t ring_dispatch_f16(const NormParams& p, cudaStream_t st);
+
+namespace {
+struct DevInfo { int sms, smem_optin; bool valid; };
+DevInfo g_dev[64] = {};
+const DevInfo& dev_info() {
+  int dev = 0;
+  (void)cudaGetDevice(&dev);
+  DevInfo& d = g_dev[dev & 63];
+  if (!d.valid) {                          // (benign race: every thread writes the same values)
+    int sms = 0, smem = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || smem <= 0) smem = 227 * 1024;
+    d.sms = sms; d.smem_optin = smem; d.valid = true;
+  }
+  return d;
+}
+}  // namespace
+
+int device_sm_count() { return dev_info().sms; }
+int device_max_smem_optin() { return dev_info().smem_optin; }
+
+bool plan_ring(NormParams& p, int dtype, int rows) {
+  if (p.sched == nullptr || p.no_ring || p.no_pipeline || p.force_general || rows < 1) return false;
+  const size_t es = dtype == kF32 ? 4 : 2;
+  int mode;
+  if (p.top_k > 0 && p.top_k <= kFastK) mode = kRingTopK;
+  else if (p.top_k <= 0 && !(p.top_p > 0.f)) mode = kRingDense;
+  else return false;
+  // the dense sampler re-reads the probabilities it needs from the row the compute warps just wrote
+  if (mode == kRingDense && p.u != nullptr && p.probs == nullptr) return false;
+  const long long row_bytes = p.V * static_cast<long long>(es);
+  const bool aligned_in = (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) && ((p.ld_in * es) % 16 == 0) && (row_bytes % 16 == 0);
+  const bool aligned_out = p.probs == nullptr || (reinterpret_cast<uintptr_t>(p.probs) % 16 == 0 && p.ld_out % 4 == 0 && p.V % 4 == 0);
+  if (!aligned_in || !aligned_out) return false;
+  const int smem_max = device_max_smem_optin();
+  const size_t fixed = (sizeof(RingShared) + 127) & ~static_cast<size_t>(127);
+  const int extra = mode == kRingTopK ? 1 : 0;               // TOPK: one more chunk holds the zeros of the output rows' zero fill
+  int slots = static_cast<int>((static_cast<size_t>(smem_max) - fixed) / kRingChunkBytes) - extra;
+  if (slots > kRingMaxSlots) slots = kRingMaxSlots;
+  const int n_chunks = static_cast<int>((row_bytes + kRingChunkBytes - 1) / kRingChunkBytes);
+  if (slots < 2 || n_chunks > slots) return false;
+  const size_t shared_off = static_cast<size_t>(slots + extra) * kRingChunkBytes;
+  // in-kernel general-path fallback (norm_row with the whole row in this CTA) must fit in front of the deferred-row list
+  const long long slice = (p.V + 127) & ~127LL;
+  const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
+  if (mode == kRingTopK && slice_bytes + sizeof(NormShared<kRingThreads>) > shared_off + offsetof(RingShared, n_fail)) return false;
+  p.ring_mode = mode;
+  p.ring_slots = slots;
+  p.ring_shared_off = static_cast<int>(shared_off);
+  p.ring_smem_bytes = static_cast<int>(shared_off + fixed);
+  p.ring_ctas = rows < device_sm_count() ? rows : device_sm_count();
+  p.ring_row_elems = static_cast<int>(slice);
+  p.ring_row_smem_bytes = static_cast<int>(slice_bytes);
+  p.use_tma = 1;
+  p.vec_out = 1;
+  p.rows = rows;
+  return true;
+}
+
+cudaError_t launch_norm_ring(const NormParams& p, int dtype, cudaStream_t st) {
+  switch (dtype) {
+    case kF32: return ring_dispatch_f32(p, st);
+    case kBF16: return ring_dispatch_bf16(p, st);
+    case kF16: return ring_dispatch_f16(p, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace sd

@@ -1,0 +1,802 @@
+// Kernel 1, ring version: ONE persistent CTA per SM streams whole logits rows through a shared-memory ring of 16 KB
+// chunks (1-D TMA bulk copies), no thread-block cluster — every SM is usable whatever the vocabulary, and all 16
+// compute warps of the CTA work on the same row, so the latency between "last byte landed" and "row finished" is that
+// of one short selection / normalisation phase instead of a 4-warp group's.
+//
+//   warp 16  (loader)   draws rows (static first row, then a global ticket counter), publishes them, and issues the TMA
+//                       load of every chunk into the next ring slot as soon as the 16 compute warps have released it
+//   warp 17  (aux)      TOPK : writes the zeros of each output row (st.global.cs.v4) ahead of the compute warps
+//                       DENSE: the sampler — picks the token of a finished row from the exact per-piece weight sums
+//   warps 0..15         TOPK : pass 1 (three largest vector maxima per thread) runs chunk by chunk AS THE CHUNKS LAND;
+//                              pivot = k-th largest of the 512 thread maxima; re-scan of the hot threads' vectors; the
+//                              ring slots are released; merge, rank sort, top-k / top-p / softmax / sample on the ~k
+//                              candidates; scatter over the zero-filled row
+//                       DENSE: pass A = per-thread online (max, sum of exp) chunk by chunk as the chunks land, one
+//                              CTA-wide combine; pass B = exp2 of every element, 16-byte streaming stores, ring slots
+//                              released chunk by chunk; the sampler's 64-bit fixed-point weights are accumulated as two
+//                              20-bit limbs with round-down float adds (no float -> u64 conversion per element)
+//
+// Rows the fast top-k selection cannot serve (massive ties) are deferred to the general path (norm_row) and re-run by
+// the same CTA after its ring has drained, exactly as in the cluster pipeline (norm_pipe_kernel.cuh).
+//
+// Replaces /root/reference/sampling/utils.py:152-210 (+ :213-233 when a uniform is supplied), called per row from
+// sampling/kvcache_model.py:166-168, 235-236, 280-283.
+#pragma once
+#include "norm_row.cuh"
+
+namespace sd {
+
+constexpr int kRingComputeWarps = 16;
+constexpr int kRingComputeThreads = kRingComputeWarps * 32;
+constexpr int kRingThreads = kRingComputeThreads + 64;      // + loader warp + aux warp
+constexpr int kRingChunkBytes = 16384;
+constexpr int kRingVecPerChunk = kRingChunkBytes / 16;      // 16-byte vectors per chunk
+constexpr int kRingMaxSlots = 14;
+constexpr int kRingItemRing = 32;                           // row descriptors in flight (loader lead <= slots + 1)
+constexpr int kRingCap = 256;                               // merged candidates per row
+constexpr int kRingWarpCap = 48;                            // candidates one warp may collect per row
+constexpr int kRingMaxFail = 192;                           // rows per round that may be deferred to the general path
+constexpr int kRingFailSlack = 40;
+constexpr int kRingMaxPieces = kRingMaxSlots * kRingComputeWarps;   // (chunk, warp) pieces of 64 vectors
+constexpr int kRingEndDone = -1, kRingEndPause = -2;
+constexpr uint32_t kRingTieUlps = 8;
+
+enum : int { kRingTopK = 0, kRingDense = 1 };
+
+struct alignas(16) RingShared {
+  uint64_t full[kRingMaxSlots];        // chunk landed                       (TMA -> compute warps)
+  uint64_t empty[kRingMaxSlots];       // slot may be overwritten            (16 compute warps -> loader)
+  uint64_t rowfull[kRingItemRing];     // row of item it published           (loader -> everyone)
+  uint64_t zeroed[kRingItemRing];      // TOPK: output row zero-filled       (aux -> compute)
+  uint64_t row_done[2];                // DENSE: row written, piece sums ready (16 compute warps -> aux), by item parity
+  uint64_t tfree[2];                   // DENSE: piece table may be reused   (aux -> compute)
+  int row_of[kRingItemRing];
+  // ---- TOPK scratch
+  float tm_in[128];                    // maxima of 128 thread quads (unsorted)
+  float tm[128];                       // the same, sorted per warp (4 lists of 32)
+  uint2 w_pair[kRingComputeWarps][kRingWarpCap];
+  int w_cnt[kRingComputeWarps];
+  float tau;
+  int n_keep_p;
+  unsigned long long a_key[kRingCap];
+  float a_val[kRingCap];
+  float s_val[kRingCap];
+  int s_idx[kRingCap];
+  // ---- DENSE scratch
+  float wm[kRingComputeWarps];
+  double ws[kRingComputeWarps];
+  unsigned long long piece[2][kRingMaxPieces];
+  float info_c2[2];
+  // ---- kept LAST (survives norm_row, which re-purposes everything in front of it)
+  int n_fail, end_reason;
+  int fail_rows[kRingMaxFail];
+};
+
+__device__ __forceinline__ void ring_named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void ring_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float ex2_ftz(float x) {         // MUFU.EX2 (results below 2^-126 flush to 0: far under the 2^-40 sampling resolution)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// round-down float add (full-rate FADD.RM): with c = 2^23 the low mantissa bits of the result are floor(a), 0 <= a < 2^23
+__device__ __forceinline__ float fadd_rd(float a, float b) { return __fadd_rd(a, b); }
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormParams p) {
+  constexpr int PV = Elem<T>::kPerVec;
+  constexpr int CT = kRingComputeThreads;
+  constexpr int CW = kRingComputeWarps;
+  constexpr float kLog2e = 1.4426950408889634f;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int NS = p.ring_slots;
+  // layout: NS ring slots | (TOPK: one chunk of zeros, the source of the output rows' zero fill) | RingShared
+  unsigned char* zbuf = smem_raw + static_cast<size_t>(NS) * kRingChunkBytes;
+  RingShared& sh = *reinterpret_cast<RingShared*>(smem_raw + p.ring_shared_off);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = static_cast<int>(p.V);
+  const int n_vec = V / PV;                                   // (TMA path: V * sizeof(T) is a multiple of 16)
+  const int NCH = (n_vec + kRingVecPerChunk - 1) / kRingVecPerChunk;
+  const uint32_t row_bytes = static_cast<uint32_t>(n_vec) * 16u;
+  const float temp = p.temperature;
+  const float r_temp = 1.0f / temp;
+  const bool t1 = temp == 1.0f;
+  const int k_eff = min(p.top_k, V);
+  const bool want_probs = p.probs != nullptr;
+  const int static_rows = static_cast<int>(gridDim.x);         // first item of CTA b is row b
+  auto slot_ptr = [&](int slot) { return smem_raw + static_cast<size_t>(slot) * kRingChunkBytes; };
+
+  if constexpr (MODE == kRingTopK) {
+    for (int i = tid; i < kRingChunkBytes / 16; i += kRingThreads) reinterpret_cast<uint4*>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();                                       // generic writes above -> bulk-copy (async proxy) reads below
+  }
+
+  for (int round = 0;; ++round) {                              // (a second round only after a kRingEndPause)
+    if (tid == 0) {
+      for (int s = 0; s < NS; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], CW); }
+      for (int i = 0; i < kRingItemRing; ++i) { mbar_init(&sh.rowfull[i], 1); mbar_init(&sh.zeroed[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&sh.row_done[i], CW); mbar_init(&sh.tfree[i], 1); }
+      sh.n_fail = 0;
+      sh.end_reason = kRingEndDone;
+      fence_barrier_init();
+    }
+    if (round > 0) {
+      // the general path used the ring (and the zero chunk) through the generic proxy: restore the zeros, then order
+      // everything before the bulk copies of the new round
+      if constexpr (MODE == kRingTopK)
+        for (int i = tid; i < kRingChunkBytes / 16; i += kRingThreads) reinterpret_cast<uint4*>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async();
+    }
+    __syncthreads();
+    if (round == 0) pdl_wait();                                // everything above overlapped the previous kernel's tail
+
+    if (warp == CW) {
+      // =========================================================================== loader
+      if (lane == 0) {
+        auto draw = [&]() {
+          if (sh.n_fail >= kRingMaxFail - kRingFailSlack) return kRingEndPause;
+          const int t = static_cast<int>(atomicAdd(p.sched, 1u)) + static_rows;
+          return t < p.rows ? t : kRingEndDone;
+        };
+        int row = round == 0 ? (static_cast<int>(blockIdx.x) < p.rows ? static_cast<int>(blockIdx.x) : kRingEndDone) : draw();
+        int slot = 0, wraps = 0;
+        for (int it = 0;; ++it) {
+          sh.row_of[it % kRingItemRing] = row;
+          ring_arrive(&sh.rowfull[it % kRingItemRing]);
+          if (row < 0) { sh.end_reason = row; break; }
+          const int next = draw();                             // (latency hidden behind this row's loads)
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.logits) + static_cast<size_t>(row) * p.ld_in * sizeof(T);
+          for (int c = 0; c < NCH; ++c) {
+            if (wraps > 0) mbar_wait(&sh.empty[slot], static_cast<uint32_t>(wraps - 1) & 1u);
+            const uint32_t off = static_cast<uint32_t>(c) * kRingChunkBytes;
+            const uint32_t bytes = min(static_cast<uint32_t>(kRingChunkBytes), row_bytes - off);
+            mbar_expect_tx(&sh.full[slot], bytes);
+            tma_load_1d(slot_ptr(slot), src + off, bytes, &sh.full[slot]);
+            if (++slot == NS) { slot = 0; ++wraps; }
+          }
+          row = next;
+        }
+      }
+    } else if (warp == CW + 1) {
+      // =========================================================================== aux warp
+      if constexpr (MODE == kRingTopK) {
+        // zero fill of every output row: bulk copies (TMA) of the zero chunk, one elected thread, one item ahead of its
+        // completion wait — no store instruction of the SM is spent on the ~V zeros of a top-k filtered row
+        if (lane == 0) {
+          int it = 0;
+          for (;; ++it) {
+            mbar_wait(&sh.rowfull[it % kRingItemRing], static_cast<uint32_t>(it / kRingItemRing) & 1u);
+            const int row = *reinterpret_cast<volatile int*>(&sh.row_of[it % kRingItemRing]);
+            if (row < 0) break;
+            if (want_probs) {
+              unsigned char* o = reinterpret_cast<unsigned char*>(p.probs + static_cast<long long>(row) * p.ld_out);
+              const uint32_t out_bytes = static_cast<uint32_t>(V) * 4u;
+              for (uint32_t off = 0; off < out_bytes; off += kRingChunkBytes)
+                tma_store_1d(o + off, zbuf, min(static_cast<uint32_t>(kRingChunkBytes), out_bytes - off));
+            }
+            tma_store_commit();
+            if (it > 0) {
+              asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");     // the zeros of item it - 1 are in place
+              ring_arrive(&sh.zeroed[(it - 1) % kRingItemRing]);
+            }
+          }
+          tma_store_wait_all();
+          if (it > 0) ring_arrive(&sh.zeroed[(it - 1) % kRingItemRing]);
+        }
+      } else {
+        // ---- DENSE sampler: token of row `row` from the exact per-piece weight sums the compute warps left behind
+        const int n_pieces = NCH * CW;
+        for (int it = 0;; ++it) {
+          mbar_wait(&sh.rowfull[it % kRingItemRing], static_cast<uint32_t>(it / kRingItemRing) & 1u);
+          const int row = *reinterpret_cast<volatile int*>(&sh.row_of[it % kRingItemRing]);
+          if (row < 0) break;
+          const int par = it & 1;
+          mbar_wait(&sh.row_done[par], static_cast<uint32_t>(it >> 1) & 1u);
+          const bool do_sample = p.u != nullptr && p.u[row] >= 0.f;
+          if (do_sample) {
+            const volatile unsigned long long* tab = sh.piece[par];
+            const float c2 = *reinterpret_cast<volatile float*>(&sh.info_c2[par]);
+            const int e = frexp_exp(ex2_ftz(c2));
+            const int ppl = (n_pieces + 31) / 32;               // pieces per lane (contiguous range)
+            unsigned long long mine = 0ull;
+            for (int j = lane * ppl; j < min(n_pieces, (lane + 1) * ppl); ++j) mine += tab[j];
+            const unsigned long long incl = warp_scan_incl(mine, lane);
+            const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+            const float* orow = p.probs + static_cast<long long>(row) * p.ld_out;
+            if (total == 0ull) {
+              if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
+            } else {
+              const unsigned long long target = scale_target(total, u_to_int(p.u[row]));
+              const unsigned ball = __ballot_sync(0xffffffffu, incl > target);
+              const int owner = __ffs(ball) - 1;                // first lane whose range crosses the target
+              int pc = 0;
+              unsigned long long base = 0ull;
+              if (lane == owner) {
+                base = incl - mine;
+                pc = lane * ppl;
+                while (base + tab[pc] <= target) { base += tab[pc]; ++pc; }
+              }
+              pc = __shfl_sync(0xffffffffu, pc, owner);
+              base = __shfl_sync(0xffffffffu, base, owner);
+              // piece pc = 64 input vectors = 64 * PV elements, contiguous in the vocabulary; walk it 128 elements at a time
+              const int c = pc / CW, w = pc - c * CW;
+              const int e0 = (c * kRingVecPerChunk + w * 64) * PV;
+              int found = -1;
+              float pfound = 1.f;
+              unsigned long long run = base;
+              for (int blk = 0; blk < 64 * PV && found < 0; blk += 128) {
+                const int i0 = e0 + blk + lane * 4;
+                float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i0 < V) pr = __ldcg(reinterpret_cast<const float4*>(orow + i0));
+                const float pv[4] = {pr.x, pr.y, pr.z, pr.w};
+                unsigned long long wv[4], vs = 0ull;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { wv[j] = weight_of(pv[j], e); vs += wv[j]; }
+                const unsigned long long inc2 = warp_scan_incl(vs, lane) + run;
+                const unsigned b2 = __ballot_sync(0xffffffffu, inc2 > target);
+                if (b2) {
+                  const int ow = __ffs(b2) - 1;
+                  int f = -1;
+                  float pf = 1.f;
+                  if (lane == ow) {
+                    unsigned long long cc = inc2 - vs;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { cc += wv[j]; if (f < 0 && cc > target) { f = i0 + j; pf = pv[j]; } }
+                  }
+                  found = __shfl_sync(0xffffffffu, f, ow);
+                  pfound = __shfl_sync(0xffffffffu, pf, ow);
+                }
+                run = __shfl_sync(0xffffffffu, inc2, 31);
+              }
+              if (found >= 0 && pfound < kProbGuard) {
+                // utils.py:228-230: the reference falls back to argmax(probs) — rare (probability < ~1e-9 * V per
+                // row): one warp scans the row it just wrote
+                unsigned long long best = 0ull;
+                for (int i0 = lane * 4; i0 < V; i0 += 128) {
+                  const float4 pr = __ldcg(reinterpret_cast<const float4*>(orow + i0));
+                  const float pv[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const unsigned long long pk = (static_cast<unsigned long long>(f2key(pv[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(i0 + j));
+                    best = pk > best ? pk : best;
+                  }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
+                found = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffull));
+              }
+              if (lane == 0) {
+                if (found >= 0) p.tok_out[row] = found;
+                else { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) ring_arrive(&sh.tfree[par]);
+        }
+      }
+    } else {
+      // =========================================================================== compute warps
+      int slot0 = 0, wraps0 = 0;                                // ring position of the current row's first chunk
+      for (int it = 0;; ++it) {
+        mbar_wait(&sh.rowfull[it % kRingItemRing], static_cast<uint32_t>(it / kRingItemRing) & 1u);
+        const int row = *reinterpret_cast<volatile int*>(&sh.row_of[it % kRingItemRing]);
+        if (row < 0) break;
+        float* orow = want_probs ? p.probs + static_cast<long long>(row) * p.ld_out : nullptr;
+        auto slot_of = [&](int c) { const int s = slot0 + c; return s >= NS ? s - NS : s; };
+        auto wait_chunk = [&](int c) {
+          const int s = slot0 + c;
+          const bool wrapped = s >= NS;
+          mbar_wait(&sh.full[wrapped ? s - NS : s], static_cast<uint32_t>(wraps0 + (wrapped ? 1 : 0)) & 1u);
+        };
+
+        if constexpr (MODE == kRingTopK) {
+          // ---- pass 1, chunk by chunk as the chunks land: the three largest VECTOR maxima of the thread (tmax >= m2 >= m3)
+          //      and the vector indices of the first two.  Thread t owns vectors c * 1024 + t and c * 1024 + 512 + t.
+          float tmax = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          int i1 = 0, i2 = 0;
+          float nan_acc = -INFINITY;
+          for (int c = 0; c < NCH; ++c) {
+            wait_chunk(c);
+            const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot_of(c)));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int vl = h * CT + tid;
+              const int v = c * kRingVecPerChunk + vl;
+              float vm = -INFINITY;
+              if (v < n_vec) vm = vec_max_nan<T>(-INFINITY, s4[vl]);
+              asm("max.NaN.f32 %0, %0, %1;" : "+f"(nan_acc) : "f"(vm));
+              const float lo1 = fminf(tmax, vm);
+              const bool c1 = vm > tmax;
+              tmax = fmaxf(tmax, vm);
+              const bool c2 = lo1 > m2;
+              m3 = fmaxf(m3, fminf(m2, lo1));
+              m2 = fmaxf(m2, lo1);
+              i2 = c1 ? i1 : (c2 ? v : i2);
+              i1 = c1 ? v : i1;
+            }
+          }
+          if (nan_acc != nan_acc || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
+
+          // ---- pivot = k-th largest of the 128 QUAD maxima (max over four neighbouring threads): at least k elements of the
+          //      row reach it (one per quad), and four warps find it with four short binary searches
+          {
+            float q = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+            q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 2));
+            if ((lane & 3) == 0) sh.tm_in[warp * 8 + (lane >> 2)] = q;
+            if (tid == 0) sh.tau = -INFINITY;
+          }
+          ring_named_bar(1, CT);
+          if (warp < 4) {
+            const float sv = warp_sort_desc(sh.tm_in[warp * 32 + lane], lane);
+            sh.tm[warp * 32 + lane] = sv;
+            ring_named_bar(2, 128);
+            const int kk = min(k_eff, 32);
+            if (tid < 4 * kk) {                                  // element (list ew, position ej), one per thread
+              const int ew = tid / kk, ej = tid - ew * kk;
+              const float ev = sh.tm[ew * 32 + ej];
+              int lo[4], hi[4];
+#pragma unroll
+              for (int w = 0; w < 4; ++w) { lo[w] = 0; hi[w] = 32; }
+#pragma unroll
+              for (int s = 0; s < 6; ++s) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  const int mid = (lo[w] + hi[w]) >> 1;
+                  const float y = sh.tm[w * 32 + min(mid, 31)];
+                  const bool before = mid < 32 && ((y > ev) || (y == ev && w < ew));
+                  lo[w] = before ? mid + 1 : lo[w];
+                  hi[w] = before ? hi[w] : mid;
+                }
+              }
+              int rank = ej;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) rank += (w == ew) ? 0 : lo[w];
+              if (rank == k_eff - 1) sh.tau = ev;
+            }
+          }
+          ring_named_bar(1, CT);
+          const float tau = float_down(sh.tau, t1 ? 0u : kRingTieUlps);
+
+          // ---- pass 2: every element >= pivot of the threads whose maximum reaches it, into a per-warp region
+          auto vec_at = [&](int v) { return reinterpret_cast<const uint4*>(slot_ptr(slot_of(v >> 10)))[v & (kRingVecPerChunk - 1)]; };
+          static_assert(kRingVecPerChunk == 1024, "vec_at assumes 1024 vectors per chunk");
+          int wc = 0;
+          {
+            const bool hot = tmax >= tau;
+            const bool slow = hot && m3 >= tau;
+            const bool quick = hot && !slow;
+            const bool two = quick && m2 >= tau;
+            float o1[PV], o2[PV];
+            int c = 0;
+            if (quick) {
+              Elem<T>::unpack(vec_at(i1), o1);
+#pragma unroll
+              for (int j = 0; j < PV; ++j) c += (o1[j] >= tau) ? 1 : 0;
+              if (two) {
+                Elem<T>::unpack(vec_at(i2), o2);
+#pragma unroll
+                for (int j = 0; j < PV; ++j) c += (o2[j] >= tau) ? 1 : 0;
+              }
+            }
+            const int incl = warp_scan_incl(c, lane);
+            wc = __shfl_sync(0xffffffffu, incl, 31);
+            if (c > 0) {
+              int w = incl - c;
+#pragma unroll
+              for (int j = 0; j < PV; ++j)
+                if (o1[j] >= tau) {
+                  if (w < kRingWarpCap) sh.w_pair[warp][w] = make_uint2(__float_as_uint(o1[j]), static_cast<uint32_t>(i1 * PV + j));
+                  ++w;
+                }
+              if (two) {
+#pragma unroll
+                for (int j = 0; j < PV; ++j)
+                  if (o2[j] >= tau) {
+                    if (w < kRingWarpCap) sh.w_pair[warp][w] = make_uint2(__float_as_uint(o2[j]), static_cast<uint32_t>(i2 * PV + j));
+                    ++w;
+                  }
+              }
+            }
+            // a thread whose THIRD vector also reaches the pivot (rare): the warp walks all of that thread's vectors
+            unsigned hm = __ballot_sync(0xffffffffu, slow);
+            while (hm) {
+              const int t = warp * 32 + (__ffs(hm) - 1);
+              hm &= hm - 1;
+              for (int i0 = 0; i0 < 2 * NCH; i0 += 32) {
+                const int i = i0 + lane;                         // i-th vector of thread t: chunk i / 2, half i % 2
+                const int v = (i >> 1) * kRingVecPerChunk + (i & 1) * CT + t;
+                const bool inb = i < 2 * NCH && v < n_vec;
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (inb) raw = vec_at(v);
+                const float vmax = inb ? vec_max_nan<T>(-INFINITY, raw) : -INFINITY;
+                unsigned vmk = __ballot_sync(0xffffffffu, vmax >= tau);
+                float o[PV];
+                if (vmk) Elem<T>::unpack(raw, o);
+                while (vmk) {
+                  const int src = __ffs(vmk) - 1;
+                  vmk &= vmk - 1;
+#pragma unroll
+                  for (int j = 0; j < PV; ++j) {
+                    const float val = __shfl_sync(0xffffffffu, o[j], src);
+                    const int idx = __shfl_sync(0xffffffffu, v, src) * PV + j;
+                    if (val >= tau) {
+                      if (lane == 0 && wc < kRingWarpCap) sh.w_pair[warp][wc] = make_uint2(__float_as_uint(val), static_cast<uint32_t>(idx));
+                      ++wc;
+                    }
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) sh.w_cnt[warp] = wc;
+          }
+          // the row's logits are no longer needed: hand the ring slots back to the loader
+          __syncwarp();
+          if (lane == 0)
+            for (int c = 0; c < NCH; ++c) ring_arrive(&sh.empty[slot_of(c)]);
+          ring_named_bar(1, CT);
+
+          // ---- merge the per-warp regions into 64-bit sort keys (value key << 32 | ~index)
+          int n_tot = 0, my_ofs = 0;
+          bool ok = true;
+#pragma unroll
+          for (int w = 0; w < CW; ++w) {
+            const int c = sh.w_cnt[w];
+            ok &= c <= kRingWarpCap;
+            my_ofs = w == warp ? n_tot : my_ofs;
+            n_tot += c;
+          }
+          ok &= n_tot <= kRingCap && n_tot >= k_eff;             // self-check: every element >= pivot collected, at least k of them
+          if (ok) {
+            for (int i = lane; i < wc; i += 32) {                // warp w copies its own region
+              const uint2 e = sh.w_pair[warp][i];
+              const float xv = __fdiv_rn(__uint_as_float(e.x), temp) + 0.0f;            // logit / T;  -0 -> +0: equal values tie on the index
+              sh.a_key[my_ofs + i] = (static_cast<unsigned long long>(f2key(xv)) << 32) | (0xffffffffu - e.y);
+            }
+          }
+          if (!ok) {
+            if (tid == 0) sh.fail_rows[atomicAdd(&sh.n_fail, 1)] = row;
+            ring_named_bar(1, CT);
+          } else {
+          ring_named_bar(1, CT);
+
+          // ---- rank sort on 64-bit keys (value descending, then vocabulary index ascending): four threads per candidate
+          for (int base = 0; base < n_tot; base += CT / 4) {
+            const int i = base + (tid >> 2);
+            const bool live = i < n_tot;
+            const unsigned long long ki = live ? sh.a_key[i] : 0ull;
+            int r = 0;
+            if (live) {
+#pragma unroll 4
+              for (int j = tid & 3; j < n_tot; j += 4) r += sh.a_key[j] > ki ? 1 : 0;
+            }
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            if (live && (tid & 3) == 0) {
+              sh.s_val[r] = key2f(static_cast<uint32_t>(ki >> 32));
+              sh.s_idx[r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(ki & 0xffffffffull));
+            }
+          }
+          ring_named_bar(1, CT);
+
+          // ---- top-k cut (ties kept), top-p cut, softmax, optional sample: first warp
+          if (warp == 0) {
+            int nk = 0;
+            const float kth = sh.s_val[k_eff - 1];
+            for (int base = 0; base < n_tot; base += 32) {
+              const int i = base + lane;
+              const unsigned ge = __ballot_sync(0xffffffffu, i < n_tot && sh.s_val[i] >= kth);
+              nk += __popc(ge);
+              if (ge != 0xffffffffu) break;
+            }
+            if (nk <= 32) {
+              const bool in_k = lane < nk;
+              const float x = in_k ? sh.s_val[lane] : -INFINITY;
+              const int id = in_k ? sh.s_idx[lane] : 0x7fffffff;
+              const float M = __shfl_sync(0xffffffffu, x, 0);
+              const float e = in_k ? expf(x - M) : 0.f;
+              const double zs = warp_sum(static_cast<double>(e));
+              int np = nk;
+              if (p.top_p > 0.f) {
+                const float sp = e * (1.0f / static_cast<float>(zs));
+                const double cum = warp_scan_incl(static_cast<double>(sp), lane);
+                const unsigned ball = __ballot_sync(0xffffffffu, in_k && static_cast<float>(cum) > p.top_p);
+                if (ball) np = min(nk, __ffs(ball));
+              }
+              const bool in_p = lane < np;
+              const double z2 = warp_sum(in_p ? static_cast<double>(e) : 0.0);
+              const float logz = logf(static_cast<float>(z2));
+              const float pr = in_p ? expf((x - M) - logz) : 0.f;
+              if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
+              if (in_p) sh.a_val[lane] = pr;
+              if (lane == 0) sh.n_keep_p = np;
+              if (p.cmp.cnt != nullptr) {
+                const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
+                if (np <= p.cmp.cap) {
+                  if (in_p) { p.cmp.idx[cr * p.cmp.cap + lane] = id; p.cmp.val[cr * p.cmp.cap + lane] = pr; }
+                  if (lane == 0) p.cmp.cnt[cr] = np;
+                } else if (lane == 0) p.cmp.cnt[cr] = -1;
+              }
+              if (p.u != nullptr && p.u[row] >= 0.f) {
+                const int e2 = frexp_exp(__shfl_sync(0xffffffffu, pr, 0));
+                const unsigned long long wi = weight_of(pr, e2);
+                const unsigned long long tot = warp_sum(wi);
+                if (tot == 0ull) {
+                  if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
+                } else {
+                  const unsigned long long target = scale_target(tot, u_to_int(p.u[row]));
+                  unsigned long long before = 0ull;
+                  for (int j = 0; j < np; ++j) {
+                    const int idj = __shfl_sync(0xffffffffu, id, j);
+                    const unsigned long long wj = __shfl_sync(0xffffffffu, wi, j);
+                    before += idj < id ? wj : 0ull;
+                  }
+                  const int top_id = __shfl_sync(0xffffffffu, id, 0);
+                  if (in_p && wi > 0ull && target >= before && target < before + wi)
+                    p.tok_out[row] = (pr < kProbGuard) ? top_id : id;
+                }
+              }
+            } else {
+              const float M = sh.s_val[0];
+              double zs = 0.0;
+              for (int i = lane; i < nk; i += 32) zs += static_cast<double>(expf(sh.s_val[i] - M));
+              zs = warp_sum(zs);
+              int np = nk;
+              if (p.top_p > 0.f) {
+                const float rz = 1.0f / static_cast<float>(zs);
+                double run = 0.0;
+                for (int base = 0; base < nk; base += 32) {
+                  const int i = base + lane;
+                  const float sp = i < nk ? expf(sh.s_val[i] - M) * rz : 0.f;
+                  const double cum = warp_scan_incl(static_cast<double>(sp), lane) + run;
+                  const unsigned ball = __ballot_sync(0xffffffffu, i < nk && static_cast<float>(cum) > p.top_p);
+                  if (ball) { np = min(nk, base + __ffs(ball)); break; }
+                  run = __shfl_sync(0xffffffffu, cum, 31);
+                }
+              }
+              double z2 = 0.0;
+              for (int i = lane; i < np; i += 32) z2 += static_cast<double>(expf(sh.s_val[i] - M));
+              z2 = warp_sum(z2);
+              const float logz = logf(static_cast<float>(z2));
+              bool badp = false;
+              for (int i = lane; i < np; i += 32) {
+                const float pr = expf((sh.s_val[i] - M) - logz);
+                badp |= !(pr >= 0.f) || isinf(pr);
+                sh.a_val[i] = pr;
+              }
+              if (badp) atomicOr(p.err_flag, kErrNanLogit);
+              if (lane == 0) sh.n_keep_p = np;
+              __syncwarp();
+              if (p.cmp.cnt != nullptr) {
+                const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
+                if (np <= p.cmp.cap) {
+                  for (int i = lane; i < np; i += 32) { p.cmp.idx[cr * p.cmp.cap + i] = sh.s_idx[i]; p.cmp.val[cr * p.cmp.cap + i] = sh.a_val[i]; }
+                  if (lane == 0) p.cmp.cnt[cr] = np;
+                } else if (lane == 0) p.cmp.cnt[cr] = -1;
+              }
+              if (p.u != nullptr && p.u[row] >= 0.f) {
+                const int e = frexp_exp(sh.a_val[0]);
+                unsigned long long tot = 0ull;
+                for (int i = lane; i < np; i += 32) tot += weight_of(sh.a_val[i], e);
+                tot = warp_sum(tot);
+                if (tot == 0ull) {
+                  if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
+                } else {
+                  const unsigned long long target = scale_target(tot, u_to_int(p.u[row]));
+                  for (int i = lane; i < np; i += 32) {
+                    const int id = sh.s_idx[i];
+                    const unsigned long long wi = weight_of(sh.a_val[i], e);
+                    unsigned long long before = 0ull;
+                    for (int j = 0; j < np; ++j) before += (sh.s_idx[j] < id) ? weight_of(sh.a_val[j], e) : 0ull;
+                    if (wi > 0ull && target >= before && target < before + wi)
+                      p.tok_out[row] = (sh.a_val[i] < kProbGuard) ? sh.s_idx[0] : id;
+                  }
+                }
+              }
+            }
+          }
+          ring_named_bar(1, CT);
+          if (want_probs) {                                     // scatter the non-zeros over the zero-filled row
+            const int np = sh.n_keep_p;
+            if (tid < np) {
+              mbar_wait(&sh.zeroed[it % kRingItemRing], static_cast<uint32_t>(it / kRingItemRing) & 1u);
+              for (int i = tid; i < np; i += CT) orow[sh.s_idx[i]] = sh.a_val[i];
+            }
+          }
+          ring_named_bar(1, CT);                                // scratch is reused by the next row
+          }
+        } else {
+          // =================================================================== DENSE (top_k = 0, top_p = 0)
+          // thread -> vectors: warp w owns vectors c * 1024 + w * 64 + {lane, 32 + lane} of chunk c: one contiguous
+          // "piece" of 64 vectors per (chunk, warp), the unit of the sampler's exact prefix sums
+          // logit / T, correctly rounded; -inf (a masked token) is clamped to a huge negative number first so that no
+          // inf - inf can appear (its probability is exactly 0 either way)
+          auto xof = [&](float l) {
+            l = fmaxf(l, -1.0e30f);
+            const float q0 = l * r_temp;
+            return fmaf(fmaf(-q0, temp, l), r_temp, q0);
+          };
+          const int vl0 = warp * 64 + lane;
+          // ---- pass A: per-thread online (max, sum of exp2) in the log2 domain, as the chunks land
+          float m_t = -INFINITY, s_t = 0.f, nan_acc = -INFINITY;
+          for (int c = 0; c < NCH; ++c) {
+            wait_chunk(c);
+            const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot_of(c)));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int vl = vl0 + h * 32;
+              if (c * kRingVecPerChunk + vl < n_vec) {
+                float o[PV];
+                Elem<T>::unpack(s4[vl], o);
+                float vm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < PV; ++j) {
+                  if (!t1) o[j] = xof(o[j]);
+                  asm("max.NaN.f32 %0, %0, %1;" : "+f"(vm) : "f"(o[j]));
+                }
+                asm("max.NaN.f32 %0, %0, %1;" : "+f"(nan_acc) : "f"(vm));
+                if (vm > m_t) { s_t *= ex2_ftz((m_t - vm) * kLog2e); m_t = vm; }   // (m_t = -inf: s_t is 0, stays 0; a NaN vm changes nothing)
+                const float mm = m_t == -INFINITY ? 0.f : m_t;
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < PV; ++j) a += ex2_ftz((o[j] - mm) * kLog2e);
+                s_t += a;
+              }
+            }
+          }
+          if (nan_acc != nan_acc || nan_acc == INFINITY) atomicOr(p.err_flag, kErrNanLogit);
+          // ---- combine: warp, then CTA (every thread folds the 16 warp results itself: one barrier)
+          {
+            const float Mw = warp_max(m_t);
+            const float sc = (m_t == -INFINITY) ? 0.f : s_t * ex2_ftz((m_t - Mw) * kLog2e);
+            const double Sw = warp_sum(static_cast<double>(sc));
+            if (lane == 0) { sh.wm[warp] = Mw; sh.ws[warp] = Sw; }
+          }
+          ring_named_bar(1, CT);
+          float M = -INFINITY;
+#pragma unroll
+          for (int w = 0; w < CW; ++w) M = fmaxf(M, sh.wm[w]);
+          double z = 0.0;
+#pragma unroll
+          for (int w = 0; w < CW; ++w) {
+            const float mw = sh.wm[w];
+            if (mw > -INFINITY) z += sh.ws[w] * static_cast<double>(ex2_ftz((mw - M) * kLog2e));
+          }
+          const float logz = logf(static_cast<float>(z));
+          if (tid == 0 && (!(z > 0.0) || isinf(logz) || logz != logz)) atomicOr(p.err_flag, kErrNanLogit);
+          const float c2 = -logz * kLog2e;
+          const bool do_sample = p.u != nullptr && p.u[row] >= 0.f;        // row-uniform
+          const int par = it & 1;
+          if (it >= 2) mbar_wait(&sh.tfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);   // sampler is done with item it - 2
+          if (tid == 0) sh.info_c2[par] = c2;
+          // sampler weights  w = floor(p * 2^(40 - e)),  e = frexp exponent of the row maximum exp2(c2)
+          const float scale = ldexpf(1.0f, kScaleBits - frexp_exp(ex2_ftz(c2)));
+          const float scale_hi = scale * 9.5367431640625e-07f;              // 2^-20 * scale (exact)
+          // ---- pass B: probabilities out (16-byte streaming stores), exact weight sums per piece, slots released
+          for (int c = 0; c < NCH; ++c) {
+            const int slot = slot_of(c);
+            const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot));
+            uint32_t acc_hi = 0u, acc_lo = 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int vl = vl0 + h * 32;
+              const int v = c * kRingVecPerChunk + vl;
+              if (v < n_vec) {
+                float o[PV];
+                Elem<T>::unpack(s4[vl], o);
+#pragma unroll
+                for (int j = 0; j < PV; ++j) {
+                  const float x = t1 ? o[j] : xof(o[j]);
+                  o[j] = ex2_ftz(fmaf(x - M, kLog2e, c2));                  // exp((x - M) - logZ), utils.py:199
+                }
+                if (want_probs) {
+#pragma unroll
+                  for (int j = 0; j < PV; j += 4) st_cs_v4(orow + static_cast<long long>(v) * PV + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+                }
+                if (do_sample) {
+#pragma unroll
+                  for (int j = 0; j < PV; ++j) {
+                    // floor(W), W = p * scale < 2^40, as two 20-bit limbs.  A round-down add of 2^23 leaves floor() of the
+                    // other operand in the low mantissa bits; every operation below is exact (kernel 1)
+                    const float t1f = __fmaf_rd(o[j], scale_hi, 8388608.0f);          // 2^23 + floor(W / 2^20)
+                    const float hf = t1f - 8388608.0f;
+                    const float lo = fmaf(hf, -1048576.0f, o[j] * scale);             // W - 2^20 * floor(W / 2^20)  in [0, 2^20)
+                    const float t2f = fadd_rd(lo, 8388608.0f);                         // 2^23 + floor(lo)
+                    acc_hi += __float_as_uint(t1f) - 0x4B000000u;
+                    acc_lo += __float_as_uint(t2f) - 0x4B000000u;
+                  }
+                }
+              }
+            }
+            if (do_sample) {
+              const uint32_t hs = __reduce_add_sync(0xffffffffu, acc_hi), ls = __reduce_add_sync(0xffffffffu, acc_lo);
+              if (lane == 0) sh.piece[par][c * CW + warp] = (static_cast<unsigned long long>(hs) << 20) + ls;
+            }
+            __syncwarp();
+            if (lane == 0) ring_arrive(&sh.empty[slot]);
+          }
+          __syncwarp();
+          if (lane == 0) ring_arrive(&sh.row_done[par]);       // (release: this warp's stores and piece sums first)
+          if (p.cmp.cnt != nullptr && tid == 0) p.cmp.cnt[static_cast<long long>(row) * p.cmp.row_stride] = -1;   // no compact list
+        }
+        slot0 += NCH;
+        if (slot0 >= NS) { slot0 -= NS; ++wraps0; }
+      }
+    }
+
+    // =============================================================================== drained: general path for deferred rows
+    __syncthreads();
+    const int reason = sh.end_reason;
+    const int n_fail = sh.n_fail;
+    if (n_fail > 0 || reason != kRingEndDone) {
+      if (tid == 0) {                                           // retire the mbarriers before their memory is re-purposed / re-initialised
+        for (int s = 0; s < NS; ++s) { mbar_inval(&sh.full[s]); mbar_inval(&sh.empty[s]); }
+        for (int i = 0; i < kRingItemRing; ++i) { mbar_inval(&sh.rowfull[i]); mbar_inval(&sh.zeroed[i]); }
+        for (int i = 0; i < 2; ++i) { mbar_inval(&sh.row_done[i]); mbar_inval(&sh.tfree[i]); }
+      }
+      __syncthreads();
+    }
+    if (n_fail > 0) {
+      NormParams p2 = p;
+      p2.force_general = 1;
+      p2.prof = nullptr;
+      p2.cluster = 1;
+      p2.slice_elems = p.ring_row_elems;
+      p2.slice_smem_bytes = p.ring_row_smem_bytes;
+      for (int i = 0; i < n_fail; ++i) {
+        norm_row<T, kRingThreads>(p2, sh.fail_rows[i]);
+        __syncthreads();
+      }
+    }
+    if (reason == kRingEndDone) break;
+  }  // rounds
+
+  pdl_launch_dependents();
+  // the last CTA to finish re-arms the row counter for the next launch that uses this scheduler block
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1u) {
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+static cudaError_t ring_launch(const NormParams& p, cudaStream_t st) {
+  auto kern = norm_ring_kernel<T, MODE>;
+  static bool attr_set_dev[64] = {};
+  int dev_id = 0;
+  (void)cudaGetDevice(&dev_id);
+  bool& attr_set = attr_set_dev[dev_id & 63];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.ring_smem_bytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kRingThreads);
+  cfg.gridDim = dim3(static_cast<unsigned>(p.ring_ctas));
+  cfg.dynamicSmemBytes = static_cast<size_t>(p.ring_smem_bytes);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <typename T>
+static cudaError_t ring_dispatch(const NormParams& p, cudaStream_t st) {
+  return p.ring_mode == kRingDense ? ring_launch<T, kRingDense>(p, st) : ring_launch<T, kRingTopK>(p, st);
+}
+
+}  // namespace sd

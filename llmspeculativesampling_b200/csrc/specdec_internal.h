@@ -45,6 +45,10 @@ struct NormParams {
   unsigned int* sched;                     // pipelined kernel: {next row ticket, finished clusters}; zero between launches
   int pipe_groups;                         // persistent kernel: compute groups (= slice buffers) per CTA
   int pipe_buffers, pipe_cap, pipe_clusters;             // ... merged-candidate capacity, clusters in the persistent grid
+  // ring kernel (norm_ring.cu): one persistent CTA per SM, whole rows streamed through a ring of 16 KB chunks
+  int no_ring;                             // caller asked for the older kernels (SD_NORM_NO_RING)
+  int ring_mode, ring_slots, ring_smem_bytes, ring_ctas, ring_shared_off;
+  int ring_row_elems, ring_row_smem_bytes; // geometry of the in-kernel general-path fallback (whole row in one CTA)
   const int* row_filter;                   // norm_probs_kernel: process only rows with row_filter[row] != 0
   // pipelined kernel, optional: verify request b as soon as its fv_rows rows (b * fv_rows ..) are all normalised
   int fv_rows;                             // 0: disabled
@@ -59,6 +63,10 @@ void set_norm_prof(long long* ptr);
 void set_pdl(int enable);
 int pdl_enabled();
 bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster);
+bool plan_ring(NormParams& p, int dtype, int rows);
+cudaError_t launch_norm_ring(const NormParams& p, int dtype, cudaStream_t st);
+int device_sm_count();                    // multiprocessors of the current device (cached per device)
+int device_max_smem_optin();              // largest opt-in dynamic shared memory per block of the current device
 cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStream_t st);
 
 cudaError_t launch_verify(const VerifyParams& p, cudaStream_t st);

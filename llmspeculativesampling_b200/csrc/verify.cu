@@ -495,7 +495,7 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
   const long long row_bytes = p.V * 4;
   int C = 1;
   while (C < kMaxPortableCluster && (row_bytes + C - 1) / C > 48 * 1024) C <<= 1;
-  while (C < kMaxPortableCluster && static_cast<long long>(p.B) * C < 148 && row_bytes / (2 * C) >= 4096) C <<= 1;
+  while (C < kMaxPortableCluster && static_cast<long long>(p.B) * C < device_sm_count() && row_bytes / (2 * C) >= 4096) C <<= 1;
   if (g_verify_cluster > 0) C = g_verify_cluster;
   long long slice = ((p.V + C - 1) / C + 127) & ~127LL;
   while (C > 1 && slice * (C - 1) >= p.V) { C >>= 1; slice = ((p.V + C - 1) / C + 127) & ~127LL; }
@@ -507,14 +507,14 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
   p.use_tma = (al(p.p, p.p_req_stride, p.p_row_stride) && (p.q == nullptr || al(p.q, p.q_req_stride, p.q_row_stride)) &&
                p.V % 4 == 0) ? 1 : 0;
   const size_t smem = static_cast<size_t>(slice) * 4 + sizeof(VerifyShared<THREADS>);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > device_max_smem_optin()) return cudaErrorInvalidValue;
   auto kern = verify_kernel<THREADS, 3>;
   static bool attr_set_dev[64] = {};            // per device: the attribute belongs to the device's copy of the kernel
   int dev_id = 0;
   (void)cudaGetDevice(&dev_id);
   bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, device_max_smem_optin());
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

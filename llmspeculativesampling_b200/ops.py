@@ -87,7 +87,18 @@ def _default_workspace(device) -> int:
     return ws.data_ptr()
 
 
-NORM_NO_PIPELINE, NORM_FORCE_GENERAL = 1, 2
+NORM_NO_PIPELINE, NORM_FORCE_GENERAL, NORM_NO_RING = 1, 2, 4
+
+
+def _norm_flags(general: bool, pipeline) -> int:
+    """pipeline: True = the library's choice (ring kernel where a row fits one CTA, else the cluster pipeline),
+    'cluster' = skip the ring kernel (SD_NORM_NO_RING), False = one-cluster-per-row kernel (SD_NORM_NO_PIPELINE)."""
+    f = NORM_FORCE_GENERAL if general else 0
+    if pipeline == "cluster":
+        f |= NORM_NO_RING
+    elif not pipeline:
+        f |= NORM_NO_PIPELINE
+    return f
 
 
 class CompactRows:
@@ -153,7 +164,7 @@ def norm_probs(logits: torch.Tensor, temperature: float, top_k: int, top_p: floa
     lib = _cabi.load()
     k = int(top_k) if top_k else 0
     p = float(top_p) if top_p else 0.0
-    flags = (NORM_FORCE_GENERAL if general else 0) | (0 if pipeline else NORM_NO_PIPELINE)
+    flags = _norm_flags(general, pipeline)
     rc = lib.sd_norm_probs(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), k, p,
                            out.data_ptr(), out.stride(0), _cref(compact), err.ptr(), flags, ws, _stream())
     _cabi.check(rc, "sd_norm_probs")
@@ -176,7 +187,7 @@ def norm_sample(logits: torch.Tensor, temperature: float, top_k: int, top_p: flo
         assert probs_out.dtype == torch.float32 and probs_out.shape == (rows, V) and probs_out.stride(1) == 1
     ws = err.ws_ptr() if (err is not None and not err.shared) else _default_workspace(x.device)
     err = err or default_flag(x.device)
-    flags = (NORM_FORCE_GENERAL if general else 0) | (0 if pipeline else NORM_NO_PIPELINE)
+    flags = _norm_flags(general, pipeline)
     rc = _cabi.load().sd_norm_sample(x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature),
                                      int(top_k or 0), float(top_p or 0.0), _ptr(probs_out),
                                      probs_out.stride(0) if probs_out is not None else V, u.data_ptr(),
@@ -343,7 +354,7 @@ def norm_sample_verify(logits: torch.Tensor, temperature: float, top_k: int, top
         _ptr(tokens), tokens.stride(0) if tokens is not None else 0, _ptr(seq_len), _ptr(active),
         ctypes.addressof(p_compact) if p_compact is not None else None, p_cmp_req_stride,
         ctypes.addressof(q_compact) if q_compact is not None else None, q_cmp_req_stride, _ptr(stats))
-    flags = 0 if pipeline else NORM_NO_PIPELINE
+    flags = _norm_flags(False, pipeline)
     rc = _cabi.load().sd_norm_sample_verify(
         x.data_ptr(), _DT[x.dtype], rows, V, x.stride(0), float(temperature), int(top_k or 0), float(top_p or 0.0),
         probs_out.data_ptr(), probs_out.stride(0), u.data_ptr(), tok_out.data_ptr(), _cref(compact), ctypes.byref(va),

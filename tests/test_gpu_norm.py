@@ -35,14 +35,15 @@ CASES = [  # V, rows, T, k, p, scale, dtype
 
 
 @pytest.mark.parametrize("V,rows,T,k,p,scale,dtype", CASES)
-@pytest.mark.parametrize("path", ["pipeline", "classic", "general"])
+@pytest.mark.parametrize("path", ["pipeline", "cluster", "classic", "general"])
 def test_norm_probs_matches_oracle(cuda_lib, V, rows, T, k, p, scale, dtype, path):
-    """pipeline: persistent warp-specialised kernel where it applies (0 < top_k <= 128, aligned rows), else the
-    one-cluster-per-row kernel; classic: one-cluster-per-row kernel; general: its sort-free threshold search."""
+    """pipeline: the library's choice — the ring kernel (one persistent CTA per SM) where a row fits one CTA and the
+    setting is top-k or dense, else the persistent cluster pipeline, else the one-cluster-per-row kernel; cluster: the
+    same without the ring kernel; classic: one-cluster-per-row kernel; general: its sort-free threshold search."""
     from llmspeculativesampling_b200 import ops
     x = make_logits(rows, V, scale, seed=V + rows + k, dtype=dtype)
     want = oracle_probs(x, T, k, p)
-    got = ops.norm_probs(x.cuda(), T, k, p, general=(path == "general"), pipeline=(path == "pipeline"))
+    got = ops.norm_probs(x.cuda(), T, k, p, general=(path == "general"), pipeline={"pipeline": True, "cluster": "cluster"}.get(path, False))
     ops.default_flag("cuda").check()
     boundary = compare_probs(got, want, f"V={V} k={k} p={p} path={path}")
     assert boundary == 0, f"{boundary} rows with a different support (boundary ties) — none expected on these seeds"
@@ -156,21 +157,23 @@ def test_norm_sample_tokens_bit_exact(cuda_lib, V, T, k, p, dtype):
 
 @pytest.mark.parametrize("V,dtype,rows", [(32000, torch.float32, 576), (50272, torch.bfloat16, 300), (32000, torch.bfloat16, 149),
                                           (128256, torch.bfloat16, 40), (262144, torch.float32, 9)])
-def test_pipeline_kernel_many_rows_with_sampling(cuda_lib, V, dtype, rows):
-    """More rows than SMs: every persistent CTA walks several work items through all buffers / parities."""
+@pytest.mark.parametrize("kernel", [True, "cluster"])
+def test_pipeline_kernel_many_rows_with_sampling(cuda_lib, V, dtype, rows, kernel):
+    """More rows than SMs: every persistent CTA walks several work items through all buffers / parities (kernel True:
+    the ring kernel where a row fits one CTA; 'cluster': the persistent cluster pipeline)."""
     from llmspeculativesampling_b200 import ops
     x = make_logits(rows, V, 3.8, seed=rows, dtype=dtype).cuda()
     x[3] = 1.0                                               # an all-ties row must be flagged and served by the general path
     u = torch.rand(rows, generator=torch.Generator().manual_seed(1)).cuda()
     pa = torch.empty(rows, V, device="cuda"); pb = torch.empty(rows, V, device="cuda")
-    ta = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pa, pipeline=True)
+    ta = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pa, pipeline=kernel)
     tb = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pb, pipeline=False)
     ops.default_flag("cuda").check()
     assert torch.equal(pa, pb), "pipelined and classic kernels must agree bit for bit"
     assert torch.equal(ta, tb)
     # u < 0 switches sampling off for that row (its tok_out entry is left untouched)
     u2 = u.clone(); u2[1::2] = -1.0
-    for pipeline in (True, False):
+    for pipeline in (kernel, False):
         tc = torch.full((rows,), -5, dtype=torch.int64, device="cuda")
         ops.norm_sample(x, 0.8, 20, 0.9, u2, probs_out=pb, tok_out=tc, pipeline=pipeline)
         assert torch.equal(tc[0::2], ta[0::2]) and bool((tc[1::2] == -5).all())
@@ -181,7 +184,8 @@ def test_pipeline_kernel_many_rows_with_sampling(cuda_lib, V, dtype, rows):
 
 
 @pytest.mark.parametrize("V,rows,n_tied", [(4096, 9000, 3), (32000, 2400, 40), (2048, 40000, 40000), (4096, 30000, 15000)])
-def test_pipeline_kernel_dynamic_rows_and_deferred_rows(cuda_lib, V, rows, n_tied):
+@pytest.mark.parametrize("kernel", [True, "cluster"])
+def test_pipeline_kernel_dynamic_rows_and_deferred_rows(cuda_lib, V, rows, n_tied, kernel):
     """Rows are handed to the clusters through a ticket counter (tens of items per cluster: the row-index ring wraps), and
     rows the candidate path cannot serve (all ties) are deferred to the general path in bounded batches — with tens of
     thousands of them every cluster pauses, drains its list and resumes several times.  Two launches back to back check
@@ -196,13 +200,49 @@ def test_pipeline_kernel_dynamic_rows_and_deferred_rows(cuda_lib, V, rows, n_tie
     tb = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pb, pipeline=False)
     for _ in range(2):
         pa.fill_(-1.0)
-        ta = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pa, pipeline=True)
+        ta = ops.norm_sample(x, 0.8, 20, 0.9, u, probs_out=pa, pipeline=kernel)
         ops.default_flag("cuda").check()
         assert torch.equal(pa, pb), "pipelined and classic kernels must agree bit for bit"
         assert torch.equal(ta, tb)
     sel = [0, int(tied[0]), rows // 2, rows - 1]
     want = oracle_probs(x[sel].cpu(), 0.8, 20, 0.9)
     assert compare_probs(pa[sel], want, "pipeline vs oracle") == 0
+
+
+@pytest.mark.parametrize("V,dtype,rows,T", [(32000, torch.float32, 576, 1.0), (50272, torch.bfloat16, 300, 0.8), (32000, torch.float16, 149, 1.3),
+                                            (50272, torch.float32, 160, 1.0), (4096, torch.float32, 5000, 0.7), (1000, torch.bfloat16, 40, 1.0)])
+def test_ring_kernel_dense_rows_with_sampling(cuda_lib, V, dtype, rows, T):
+    """Dense rows (top_k = 0, top_p = 0 — the reference API's default, speculative_sampling.py:1879-1880) on the ring
+    kernel: probabilities against the oracle, the sampled token bit-exact against the inverse-CDF rule applied to the
+    SAME probabilities (the sampler's two-limb weight sums must be exact), rows with u < 0 left unsampled, a row that
+    contains -inf entries, and the one-cluster-per-row kernel as a cross-check of the probabilities."""
+    from llmspeculativesampling_b200 import ops
+    scale = 0.55 if rows % 2 else 3.0                        # flat (random-init-like) and peaked distributions
+    x = make_logits(rows, V, scale, seed=rows + V, dtype=dtype).cuda()
+    x[1, ::3] = float("-inf")
+    u = torch.rand(rows, generator=torch.Generator().manual_seed(2)).cuda()
+    u[2] = 0.0
+    u[3] = 1.0 - 2.0 ** -24
+    pa = torch.empty(rows, V, device="cuda"); pb = torch.empty(rows, V, device="cuda")
+    for rep in range(2):                                     # twice: the ticket counter must be re-armed
+        pa.fill_(-1.0)
+        ta = ops.norm_sample(x, T, 0, 0.0, u, probs_out=pa)
+        ops.default_flag("cuda").check()
+    ops.norm_probs(x, T, 0, 0.0, out=pb, pipeline=False)
+    assert compare_probs(pa, pb, "ring dense vs one-cluster-per-row kernel") == 0
+    pc = pa.cpu()
+    assert torch.allclose(pc.sum(-1), torch.ones(rows), atol=2e-5)
+    sel = sorted(set([0, 1, 2, 3, rows // 2, rows - 1]))
+    assert compare_probs(pa[sel], oracle_probs(x[sel].cpu(), T, 0, 0.0), "ring dense vs oracle") == 0
+    check = range(rows) if rows <= 600 else list(range(0, rows, 37)) + [rows - 1]
+    for i in check:
+        assert int(ta[i]) == ref_ops.icdf_sample(pc[i], float(u[i])), f"row {i}"
+    # rows with u < 0 are not sampled; probabilities only (no uniform) give the same rows
+    u2 = u.clone(); u2[1::2] = -1.0
+    tc = torch.full((rows,), -5, dtype=torch.int64, device="cuda")
+    ops.norm_sample(x, T, 0, 0.0, u2, probs_out=pb, tok_out=tc)
+    assert torch.equal(tc[0::2], ta[0::2]) and bool((tc[1::2] == -5).all()) and torch.equal(pa, pb)
+    assert torch.equal(ops.norm_probs(x, T, 0, 0.0), pa)
 
 
 def test_fuzz_shapes_parameters_and_ties_against_oracle(cuda_lib):
@@ -232,8 +272,8 @@ def test_fuzz_shapes_parameters_and_ties_against_oracle(cuda_lib):
         big[:, :V] = x
         xd = big.cuda()[:, :V]                                    # row stride V + pad
         want = oracle_probs(x, T, k, p)
-        for path in ("pipeline", "classic", "general"):
-            got = ops.norm_probs(xd, T, k, p, general=(path == "general"), pipeline=(path == "pipeline"))
+        for path in ("pipeline", "cluster", "classic", "general"):
+            got = ops.norm_probs(xd, T, k, p, general=(path == "general"), pipeline={"pipeline": True, "cluster": "cluster"}.get(path, False))
             ops.default_flag("cuda").check()
             boundary_rows += compare_probs(got, want, f"case {case} V={V} rows={rows} {dtype} T={T} k={k} p={p} mode={mode} path={path}")
             total_rows += rows

@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--prof", action="store_true")
     ap.add_argument("--scale", type=float, default=3.8, help="standard deviation of the synthetic logits")
     ap.add_argument("--classic", action="store_true")
+    ap.add_argument("--no-ring", action="store_true", help="skip the ring kernel: persistent cluster pipeline where it applies")
     ap.add_argument("--sample", action="store_true", help="time sd_norm_sample (one token per row) instead of sd_norm_probs")
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--k", type=int, default=-1, help="override the mode's top_k")
@@ -67,7 +68,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     a = ap.parse_args()
     global PIPELINE, SCALE
-    PIPELINE = not a.classic
+    PIPELINE = False if a.classic else ("cluster" if a.no_ring else True)
     SCALE = a.scale
     build.build()
     dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[a.dtype]
