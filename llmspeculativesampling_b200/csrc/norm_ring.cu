@@ -10,6 +10,8 @@
 // workspace is given.  Everything else keeps using the cluster kernels (norm_pipe.cu, norm.cu).
 #include "norm_ring_kernel.cuh"
 
+#include <cstdlib>
+
 namespace sd {
 
 cudaError_t ring_dispatch_f32(const NormParams& p, cudaStream_t st);
@@ -61,6 +63,7 @@ bool plan_ring(NormParams& p, int dtype, int rows) {
   const long long slice = (p.V + 127) & ~127LL;
   const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
   if (mode == kRingTopK && slice_bytes + sizeof(NormShared<kRingThreads>) > shared_off + offsetof(RingShared, n_fail)) return false;
+  { const char* ev = getenv("SD_RING_EARLY"); p.ring_early = ev != nullptr ? atoi(ev) : 0; }
   p.ring_mode = mode;
   p.ring_slots = slots;
   p.ring_shared_off = static_cast<int>(shared_off);

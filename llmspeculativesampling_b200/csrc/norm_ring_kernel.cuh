@@ -47,21 +47,22 @@ struct alignas(16) RingShared {
   uint64_t full[kRingMaxSlots];        // chunk landed                       (TMA -> compute warps)
   uint64_t empty[kRingMaxSlots];       // slot may be overwritten            (16 compute warps -> loader)
   uint64_t rowfull[kRingItemRing];     // row of item it published           (loader -> everyone)
-  uint64_t zeroed[kRingItemRing];      // TOPK: output row zero-filled       (aux -> compute)
+  uint64_t sorted[2];                  // TOPK: candidates of item it complete (16 compute warps -> aux), by item parity
+  uint64_t sfree[2];                   // TOPK: that candidate array may be reused    (aux -> compute)
   uint64_t row_done[2];                // DENSE: row written, piece sums ready (16 compute warps -> aux), by item parity
   uint64_t tfree[2];                   // DENSE: piece table may be reused   (aux -> compute)
   int row_of[kRingItemRing];
   // ---- TOPK scratch
-  float tm_in[128];                    // maxima of 128 thread quads (unsorted)
+  alignas(16) float tm_in[128];        // maxima of the 128 thread quads
   float tm[128];                       // the same, sorted per warp (4 lists of 32)
-  uint2 w_pair[kRingComputeWarps][kRingWarpCap];
-  int w_cnt[kRingComputeWarps];
+  uint2 w_pair[kRingComputeWarps][kRingWarpCap];     // slow path only: a warp's candidates before they are allocated
   float tau;
-  int n_keep_p;
-  unsigned long long a_key[kRingCap];
-  float a_val[kRingCap];
-  float s_val[kRingCap];
-  int s_idx[kRingCap];
+  int cand_cnt, cand_over;             // candidates allocated for the current row, per-warp overflow flag
+  int n_sorted[2];                     // length of the sorted list handed to the aux warp (-1: row deferred)
+  unsigned long long a_key[kRingCap];  // the row's candidates as sort keys (value key << 32 | ~index)
+  float s_val[2][kRingCap];            // sorted candidates (logit / T, descending), double buffered by item parity (compute -> aux)
+  int s_idx[2][kRingCap];
+  float f_val[kRingCap];               // ... and the final probabilities of the row it is finishing
   // ---- DENSE scratch
   float wm[kRingComputeWarps];
   double ws[kRingComputeWarps];
@@ -85,6 +86,11 @@ __device__ __forceinline__ float ex2_ftz(float x) {         // MUFU.EX2 (results
 }
 // round-down float add (full-rate FADD.RM): with c = 2^23 the low mantissa bits of the result are floor(a), 0 <= a < 2^23
 __device__ __forceinline__ float fadd_rd(float a, float b) { return __fadd_rd(a, b); }
+
+// debug timeline (tools/ring_prof.py): prof[(cta * 8 + item) * 16 + slot] = clock64() for the first 8 items of every CTA
+#define RING_PROF(slot) do { if (p.prof != nullptr && tid == 0 && it < 8) p.prof[(static_cast<long long>(blockIdx.x) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
+
+#define RING_PROF_AUX(slot) do { if (p.prof != nullptr && lane == 0 && it < 8) p.prof[(static_cast<long long>(blockIdx.x) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormParams p) {
@@ -118,10 +124,13 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
   for (int round = 0;; ++round) {                              // (a second round only after a kRingEndPause)
     if (tid == 0) {
       for (int s = 0; s < NS; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], CW); }
-      for (int i = 0; i < kRingItemRing; ++i) { mbar_init(&sh.rowfull[i], 1); mbar_init(&sh.zeroed[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&sh.row_done[i], CW); mbar_init(&sh.tfree[i], 1); }
+      for (int i = 0; i < kRingItemRing; ++i) mbar_init(&sh.rowfull[i], 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sh.row_done[i], CW); mbar_init(&sh.tfree[i], 1); mbar_init(&sh.sorted[i], 1); mbar_init(&sh.sfree[i], 1);
+      }
       sh.n_fail = 0;
       sh.end_reason = kRingEndDone;
+      sh.cand_cnt = 0; sh.cand_over = 0;
       fence_barrier_init();
     }
     if (round > 0) {
@@ -164,28 +173,159 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
     } else if (warp == CW + 1) {
       // =========================================================================== aux warp
       if constexpr (MODE == kRingTopK) {
-        // zero fill of every output row: bulk copies (TMA) of the zero chunk, one elected thread, one item ahead of its
-        // completion wait — no store instruction of the SM is spent on the ~V zeros of a top-k filtered row
-        if (lane == 0) {
-          int it = 0;
-          for (;; ++it) {
-            mbar_wait(&sh.rowfull[it % kRingItemRing], static_cast<uint32_t>(it / kRingItemRing) & 1u);
-            const int row = *reinterpret_cast<volatile int*>(&sh.row_of[it % kRingItemRing]);
-            if (row < 0) break;
-            if (want_probs) {
-              unsigned char* o = reinterpret_cast<unsigned char*>(p.probs + static_cast<long long>(row) * p.ld_out);
-              const uint32_t out_bytes = static_cast<uint32_t>(V) * 4u;
-              for (uint32_t off = 0; off < out_bytes; off += kRingChunkBytes)
-                tma_store_1d(o + off, zbuf, min(static_cast<uint32_t>(kRingChunkBytes), out_bytes - off));
-            }
+        // The finisher.  For every row: (1) its zero fill — bulk copies (TMA) of the zero chunk, issued by one thread as soon
+        // as the row is known, so no store instruction of the SM is spent on the ~V zeros of a top-k filtered row; (2) when
+        // the compute warps hand over the sorted candidate list: top-k cut (ties kept), top-p cut, softmax, optional
+        // inverse-CDF sample, compact list; (3) the scatter of the few non-zeros over the zero-filled row.  The compute
+        // warps are already selecting the next row meanwhile.
+        for (int it = 0;; ++it) {
+          mbar_wait(&sh.rowfull[it % kRingItemRing], static_cast<uint32_t>(it / kRingItemRing) & 1u);
+          const int row = *reinterpret_cast<volatile int*>(&sh.row_of[it % kRingItemRing]);
+          if (row < 0) break;
+          float* orow = want_probs ? p.probs + static_cast<long long>(row) * p.ld_out : nullptr;
+          if (want_probs && lane == 0) {
+            unsigned char* o = reinterpret_cast<unsigned char*>(orow);
+            const uint32_t out_bytes = static_cast<uint32_t>(V) * 4u;
+            for (uint32_t off = 0; off < out_bytes; off += kRingChunkBytes)
+              tma_store_1d(o + off, zbuf, min(static_cast<uint32_t>(kRingChunkBytes), out_bytes - off));
             tma_store_commit();
-            if (it > 0) {
-              asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");     // the zeros of item it - 1 are in place
-              ring_arrive(&sh.zeroed[(it - 1) % kRingItemRing]);
-            }
           }
-          tma_store_wait_all();
-          if (it > 0) ring_arrive(&sh.zeroed[(it - 1) % kRingItemRing]);
+          const float u_row = p.u != nullptr ? __ldg(p.u + row) : -1.f;        // (requested now, needed after the softmax)
+          const int par = it & 1;
+          mbar_wait(&sh.sorted[par], static_cast<uint32_t>(it >> 1) & 1u);
+          const int n_tot = *reinterpret_cast<volatile int*>(&sh.n_sorted[par]);
+          RING_PROF_AUX(8);
+          if (n_tot >= 0) {                                        // (< 0: the row goes to the general path)
+            const float* sv = sh.s_val[par];
+            const int* si = sh.s_idx[par];
+            int np_out = 0;
+            int nk = 0;
+            const float kth = sv[k_eff - 1];
+            for (int base = 0; base < n_tot; base += 32) {
+              const int i = base + lane;
+              const unsigned ge = __ballot_sync(0xffffffffu, i < n_tot && sv[i] >= kth);
+              nk += __popc(ge);
+              if (ge != 0xffffffffu) break;
+            }
+            if (nk <= 32) {
+              const bool in_k = lane < nk;
+              const float x = in_k ? sv[lane] : -INFINITY;
+              const int id = in_k ? si[lane] : 0x7fffffff;
+              const float M = __shfl_sync(0xffffffffu, x, 0);
+              const float e = in_k ? expf(x - M) : 0.f;
+              const double zs = warp_sum(static_cast<double>(e));
+              int np = nk;
+              if (p.top_p > 0.f) {
+                const float sp = e * (1.0f / static_cast<float>(zs));
+                const double cum = warp_scan_incl(static_cast<double>(sp), lane);
+                const unsigned ball = __ballot_sync(0xffffffffu, in_k && static_cast<float>(cum) > p.top_p);
+                if (ball) np = min(nk, __ffs(ball));
+              }
+              const bool in_p = lane < np;
+              const double z2 = warp_sum(in_p ? static_cast<double>(e) : 0.0);
+              const float logz = logf(static_cast<float>(z2));
+              const float pr = in_p ? expf((x - M) - logz) : 0.f;
+              if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
+              if (in_p) sh.f_val[lane] = pr;
+              np_out = np;
+              if (p.cmp.cnt != nullptr) {
+                const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
+                if (np <= p.cmp.cap) {
+                  if (in_p) { p.cmp.idx[cr * p.cmp.cap + lane] = id; p.cmp.val[cr * p.cmp.cap + lane] = pr; }
+                  if (lane == 0) p.cmp.cnt[cr] = np;
+                } else if (lane == 0) p.cmp.cnt[cr] = -1;
+              }
+              if (p.u != nullptr && u_row >= 0.f) {
+                const int e2 = frexp_exp(__shfl_sync(0xffffffffu, pr, 0));
+                const unsigned long long wi = weight_of(pr, e2);
+                const unsigned long long tot = warp_sum(wi);
+                if (tot == 0ull) {
+                  if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
+                } else {
+                  const unsigned long long target = scale_target(tot, u_to_int(u_row));
+                  unsigned long long before = 0ull;
+                  for (int j = 0; j < np; ++j) {
+                    const int idj = __shfl_sync(0xffffffffu, id, j);
+                    const unsigned long long wj = __shfl_sync(0xffffffffu, wi, j);
+                    before += idj < id ? wj : 0ull;
+                  }
+                  const int top_id = __shfl_sync(0xffffffffu, id, 0);
+                  if (in_p && wi > 0ull && target >= before && target < before + wi)
+                    p.tok_out[row] = (pr < kProbGuard) ? top_id : id;
+                }
+              }
+            } else {
+              const float M = sv[0];
+              double zs = 0.0;
+              for (int i = lane; i < nk; i += 32) zs += static_cast<double>(expf(sv[i] - M));
+              zs = warp_sum(zs);
+              int np = nk;
+              if (p.top_p > 0.f) {
+                const float rz = 1.0f / static_cast<float>(zs);
+                double run = 0.0;
+                for (int base = 0; base < nk; base += 32) {
+                  const int i = base + lane;
+                  const float sp = i < nk ? expf(sv[i] - M) * rz : 0.f;
+                  const double cum = warp_scan_incl(static_cast<double>(sp), lane) + run;
+                  const unsigned ball = __ballot_sync(0xffffffffu, i < nk && static_cast<float>(cum) > p.top_p);
+                  if (ball) { np = min(nk, base + __ffs(ball)); break; }
+                  run = __shfl_sync(0xffffffffu, cum, 31);
+                }
+              }
+              double z2 = 0.0;
+              for (int i = lane; i < np; i += 32) z2 += static_cast<double>(expf(sv[i] - M));
+              z2 = warp_sum(z2);
+              const float logz = logf(static_cast<float>(z2));
+              bool badp = false;
+              for (int i = lane; i < np; i += 32) {
+                const float pr = expf((sv[i] - M) - logz);
+                badp |= !(pr >= 0.f) || isinf(pr);
+                sh.f_val[i] = pr;
+              }
+              if (badp) atomicOr(p.err_flag, kErrNanLogit);
+              np_out = np;
+              __syncwarp();
+              if (p.cmp.cnt != nullptr) {
+                const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
+                if (np <= p.cmp.cap) {
+                  for (int i = lane; i < np; i += 32) { p.cmp.idx[cr * p.cmp.cap + i] = si[i]; p.cmp.val[cr * p.cmp.cap + i] = sh.f_val[i]; }
+                  if (lane == 0) p.cmp.cnt[cr] = np;
+                } else if (lane == 0) p.cmp.cnt[cr] = -1;
+              }
+              if (p.u != nullptr && u_row >= 0.f) {
+                const int e = frexp_exp(sh.f_val[0]);
+                unsigned long long tot = 0ull;
+                for (int i = lane; i < np; i += 32) tot += weight_of(sh.f_val[i], e);
+                tot = warp_sum(tot);
+                if (tot == 0ull) {
+                  if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
+                } else {
+                  const unsigned long long target = scale_target(tot, u_to_int(u_row));
+                  for (int i = lane; i < np; i += 32) {
+                    const int id = si[i];
+                    const unsigned long long wi = weight_of(sh.f_val[i], e);
+                    unsigned long long before = 0ull;
+                    for (int j = 0; j < np; ++j) before += (si[j] < id) ? weight_of(sh.f_val[j], e) : 0ull;
+                    if (wi > 0ull && target >= before && target < before + wi)
+                      p.tok_out[row] = (sh.f_val[i] < kProbGuard) ? si[0] : id;
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            RING_PROF_AUX(9);
+            if (want_probs) {                                     // scatter the non-zeros over the zero-filled row
+              if (lane == 0) tma_store_wait_all();                // the zeros of this row are in place
+              __syncwarp();
+              for (int i = lane; i < np_out; i += 32) orow[si[i]] = sh.f_val[i];
+            }
+          } else if (lane == 0) {
+            sh.fail_rows[atomicAdd(&sh.n_fail, 1)] = row;         // deferred to the general path (runs after the ring has drained)
+            if (want_probs) tma_store_wait_all();                 // its zero fill must not land after the general path's writes
+          }
+          __syncwarp();
+          RING_PROF_AUX(10);
+          if (lane == 0) ring_arrive(&sh.sfree[par]);
         }
       } else {
         // ---- DENSE sampler: token of row `row` from the exact per-piece weight sums the compute warps left behind
@@ -294,13 +434,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           mbar_wait(&sh.full[wrapped ? s - NS : s], static_cast<uint32_t>(wraps0 + (wrapped ? 1 : 0)) & 1u);
         };
 
+        RING_PROF(0);
         if constexpr (MODE == kRingTopK) {
           // ---- pass 1, chunk by chunk as the chunks land: the three largest VECTOR maxima of the thread (tmax >= m2 >= m3)
           //      and the vector indices of the first two.  Thread t owns vectors c * 1024 + t and c * 1024 + 512 + t.
           float tmax = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
           int i1 = 0, i2 = 0;
           float nan_acc = -INFINITY;
-          for (int c = 0; c < NCH; ++c) {
+          auto scan_chunk = [&](int c) {
             wait_chunk(c);
             const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot_of(c)));
 #pragma unroll
@@ -319,18 +460,27 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               i2 = c1 ? i1 : (c2 ? v : i2);
               i1 = c1 ? v : i1;
             }
-          }
-          if (nan_acc != nan_acc || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
+          };
+          // The pivot is taken EARLY, from the chunks that have landed when about a quarter of the row is still in flight:
+          // the k-th largest quad maximum of any part of the row is a value that at least k elements reach, so it is a valid
+          // (slightly less selective) pivot — and finding it overlaps the wait for the row's last chunks instead of sitting
+          // on the critical path behind them.
+          const int c_piv = NCH - 1 - min(p.ring_early, NCH - 1);   // (ring_early chunks are scanned while warps 0-3 find the pivot)
+          for (int c = 0; c <= c_piv; ++c) scan_chunk(c);
+          RING_PROF(1);
 
           // ---- pivot = k-th largest of the 128 QUAD maxima (max over four neighbouring threads): at least k elements of the
-          //      row reach it (one per quad), and four warps find it with four short binary searches
+          //      row reach it (one per quad).  Warps 0-3 sort the 128 values (one bitonic sort of 32 each) and rank the heads
+          //      of the four lists by binary search; the other twelve warps go straight on with the row's remaining chunks.
           {
             float q = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
             q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 2));
             if ((lane & 3) == 0) sh.tm_in[warp * 8 + (lane >> 2)] = q;
-            if (tid == 0) sh.tau = -INFINITY;
           }
           ring_named_bar(1, CT);
+          // (every thread has read the previous row's count by now.  Done by a thread of a warp that does NOT sort below: a
+          //  single-lane branch in front of the shuffles made warp 0 diverge there — measured 5k cycles for a 0.5k sort)
+          if (tid == CT - 1) { sh.cand_cnt = 0; sh.cand_over = 0; }
           if (warp < 4) {
             const float sv = warp_sort_desc(sh.tm_in[warp * 32 + lane], lane);
             sh.tm[warp * 32 + lane] = sv;
@@ -343,7 +493,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
 #pragma unroll
               for (int w = 0; w < 4; ++w) { lo[w] = 0; hi[w] = 32; }
 #pragma unroll
-              for (int s = 0; s < 6; ++s) {
+              for (int st = 0; st < 6; ++st) {
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
                   const int mid = (lo[w] + hi[w]) >> 1;
@@ -356,16 +506,25 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               int rank = ej;
 #pragma unroll
               for (int w = 0; w < 4; ++w) rank += (w == ew) ? 0 : lo[w];
-              if (rank == k_eff - 1) sh.tau = ev;
+              if (rank == k_eff - 1) sh.tau = ev;                // (exactly one value has this rank: k_eff <= 128)
             }
           }
+          RING_PROF(4);
+          for (int c = c_piv + 1; c < NCH; ++c) scan_chunk(c);    // the rest of pass 1 while the pivot settles
+          if (nan_acc != nan_acc || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
           ring_named_bar(1, CT);
           const float tau = float_down(sh.tau, t1 ? 0u : kRingTieUlps);
+          RING_PROF(2);
 
-          // ---- pass 2: every element >= pivot of the threads whose maximum reaches it, into a per-warp region
+          // ---- pass 2: every element >= pivot of the threads whose maximum reaches it goes straight into the row's candidate
+          //      array (sort keys: value key << 32 | ~index); a warp allocates its slots with one shared-memory atomic
+          const int par = it & 1;
           auto vec_at = [&](int v) { return reinterpret_cast<const uint4*>(slot_ptr(slot_of(v >> 10)))[v & (kRingVecPerChunk - 1)]; };
           static_assert(kRingVecPerChunk == 1024, "vec_at assumes 1024 vectors per chunk");
-          int wc = 0;
+          auto key_of = [&](float logit, int idx) {
+            const float xv = __fdiv_rn(logit, temp) + 0.0f;        // logit / T;  -0 -> +0: equal values tie on the index
+            return (static_cast<unsigned long long>(f2key(xv)) << 32) | (0xffffffffu - static_cast<uint32_t>(idx));
+          };
           {
             const bool hot = tmax >= tau;
             const bool slow = hot && m3 >= tau;
@@ -384,25 +543,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               }
             }
             const int incl = warp_scan_incl(c, lane);
-            wc = __shfl_sync(0xffffffffu, incl, 31);
-            if (c > 0) {
-              int w = incl - c;
-#pragma unroll
-              for (int j = 0; j < PV; ++j)
-                if (o1[j] >= tau) {
-                  if (w < kRingWarpCap) sh.w_pair[warp][w] = make_uint2(__float_as_uint(o1[j]), static_cast<uint32_t>(i1 * PV + j));
-                  ++w;
-                }
-              if (two) {
-#pragma unroll
-                for (int j = 0; j < PV; ++j)
-                  if (o2[j] >= tau) {
-                    if (w < kRingWarpCap) sh.w_pair[warp][w] = make_uint2(__float_as_uint(o2[j]), static_cast<uint32_t>(i2 * PV + j));
-                    ++w;
-                  }
-              }
-            }
-            // a thread whose THIRD vector also reaches the pivot (rare): the warp walks all of that thread's vectors
+            const int wq = __shfl_sync(0xffffffffu, incl, 31);    // candidates of the quick threads
+            // a thread whose THIRD vector also reaches the pivot (rare): the warp walks all of that thread's vectors and stages
+            // what it finds in its private region
+            int ws = 0;
             unsigned hm = __ballot_sync(0xffffffffu, slow);
             while (hm) {
               const int t = warp * 32 + (__ffs(hm) - 1);
@@ -425,191 +569,70 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
                     const float val = __shfl_sync(0xffffffffu, o[j], src);
                     const int idx = __shfl_sync(0xffffffffu, v, src) * PV + j;
                     if (val >= tau) {
-                      if (lane == 0 && wc < kRingWarpCap) sh.w_pair[warp][wc] = make_uint2(__float_as_uint(val), static_cast<uint32_t>(idx));
-                      ++wc;
+                      if (lane == 0 && ws < kRingWarpCap) sh.w_pair[warp][ws] = make_uint2(__float_as_uint(val), static_cast<uint32_t>(idx));
+                      ++ws;
                     }
                   }
                 }
               }
             }
             __syncwarp();
-            if (lane == 0) sh.w_cnt[warp] = wc;
+            int base = 0;
+            if (lane == 0 && wq + ws > 0) {
+              base = atomicAdd(&sh.cand_cnt, wq + ws);
+              if (ws > kRingWarpCap) sh.cand_over = 1;
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (c > 0) {
+              int w = base + incl - c;
+#pragma unroll
+              for (int j = 0; j < PV; ++j)
+                if (o1[j] >= tau) { if (w < kRingCap) sh.a_key[w] = key_of(o1[j], i1 * PV + j); ++w; }
+              if (two) {
+#pragma unroll
+                for (int j = 0; j < PV; ++j)
+                  if (o2[j] >= tau) { if (w < kRingCap) sh.a_key[w] = key_of(o2[j], i2 * PV + j); ++w; }
+              }
+            }
+            for (int i = lane; i < min(ws, kRingWarpCap); i += 32)
+              if (base + wq + i < kRingCap) sh.a_key[base + wq + i] = key_of(__uint_as_float(sh.w_pair[warp][i].x), static_cast<int>(sh.w_pair[warp][i].y));
           }
           // the row's logits are no longer needed: hand the ring slots back to the loader
           __syncwarp();
           if (lane == 0)
             for (int c = 0; c < NCH; ++c) ring_arrive(&sh.empty[slot_of(c)]);
+          // the aux warp must be done with the sorted list of item it - 2 before the rank sort below overwrites it
+          if (it >= 2) mbar_wait(&sh.sfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);
           ring_named_bar(1, CT);
-
-          // ---- merge the per-warp regions into 64-bit sort keys (value key << 32 | ~index)
-          int n_tot = 0, my_ofs = 0;
-          bool ok = true;
-#pragma unroll
-          for (int w = 0; w < CW; ++w) {
-            const int c = sh.w_cnt[w];
-            ok &= c <= kRingWarpCap;
-            my_ofs = w == warp ? n_tot : my_ofs;
-            n_tot += c;
-          }
-          ok &= n_tot <= kRingCap && n_tot >= k_eff;             // self-check: every element >= pivot collected, at least k of them
+          RING_PROF(12);
+          const int n_tot = sh.cand_cnt;
+          // self-check: every element >= pivot collected (no overflow), at least k of them; else the general path
+          const bool ok = sh.cand_over == 0 && n_tot <= kRingCap && n_tot >= k_eff;
           if (ok) {
-            for (int i = lane; i < wc; i += 32) {                // warp w copies its own region
-              const uint2 e = sh.w_pair[warp][i];
-              const float xv = __fdiv_rn(__uint_as_float(e.x), temp) + 0.0f;            // logit / T;  -0 -> +0: equal values tie on the index
-              sh.a_key[my_ofs + i] = (static_cast<unsigned long long>(f2key(xv)) << 32) | (0xffffffffu - e.y);
-            }
-          }
-          if (!ok) {
-            if (tid == 0) sh.fail_rows[atomicAdd(&sh.n_fail, 1)] = row;
-            ring_named_bar(1, CT);
-          } else {
-          ring_named_bar(1, CT);
-
-          // ---- rank sort on 64-bit keys (value descending, then vocabulary index ascending): four threads per candidate
-          for (int base = 0; base < n_tot; base += CT / 4) {
-            const int i = base + (tid >> 2);
-            const bool live = i < n_tot;
-            const unsigned long long ki = live ? sh.a_key[i] : 0ull;
-            int r = 0;
-            if (live) {
+            // ---- rank sort on the 64-bit keys (value descending, then vocabulary index ascending): four threads per candidate
+            for (int b0 = 0; b0 < n_tot; b0 += CT / 4) {
+              const int i = b0 + (tid >> 2);
+              const bool live = i < n_tot;
+              const unsigned long long ki = live ? sh.a_key[i] : 0ull;
+              int r = 0;
+              if (live) {
 #pragma unroll 4
-              for (int j = tid & 3; j < n_tot; j += 4) r += sh.a_key[j] > ki ? 1 : 0;
-            }
-            r += __shfl_xor_sync(0xffffffffu, r, 1);
-            r += __shfl_xor_sync(0xffffffffu, r, 2);
-            if (live && (tid & 3) == 0) {
-              sh.s_val[r] = key2f(static_cast<uint32_t>(ki >> 32));
-              sh.s_idx[r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(ki & 0xffffffffull));
-            }
-          }
-          ring_named_bar(1, CT);
-
-          // ---- top-k cut (ties kept), top-p cut, softmax, optional sample: first warp
-          if (warp == 0) {
-            int nk = 0;
-            const float kth = sh.s_val[k_eff - 1];
-            for (int base = 0; base < n_tot; base += 32) {
-              const int i = base + lane;
-              const unsigned ge = __ballot_sync(0xffffffffu, i < n_tot && sh.s_val[i] >= kth);
-              nk += __popc(ge);
-              if (ge != 0xffffffffu) break;
-            }
-            if (nk <= 32) {
-              const bool in_k = lane < nk;
-              const float x = in_k ? sh.s_val[lane] : -INFINITY;
-              const int id = in_k ? sh.s_idx[lane] : 0x7fffffff;
-              const float M = __shfl_sync(0xffffffffu, x, 0);
-              const float e = in_k ? expf(x - M) : 0.f;
-              const double zs = warp_sum(static_cast<double>(e));
-              int np = nk;
-              if (p.top_p > 0.f) {
-                const float sp = e * (1.0f / static_cast<float>(zs));
-                const double cum = warp_scan_incl(static_cast<double>(sp), lane);
-                const unsigned ball = __ballot_sync(0xffffffffu, in_k && static_cast<float>(cum) > p.top_p);
-                if (ball) np = min(nk, __ffs(ball));
+                for (int j = tid & 3; j < n_tot; j += 4) r += sh.a_key[j] > ki ? 1 : 0;
               }
-              const bool in_p = lane < np;
-              const double z2 = warp_sum(in_p ? static_cast<double>(e) : 0.0);
-              const float logz = logf(static_cast<float>(z2));
-              const float pr = in_p ? expf((x - M) - logz) : 0.f;
-              if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
-              if (in_p) sh.a_val[lane] = pr;
-              if (lane == 0) sh.n_keep_p = np;
-              if (p.cmp.cnt != nullptr) {
-                const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
-                if (np <= p.cmp.cap) {
-                  if (in_p) { p.cmp.idx[cr * p.cmp.cap + lane] = id; p.cmp.val[cr * p.cmp.cap + lane] = pr; }
-                  if (lane == 0) p.cmp.cnt[cr] = np;
-                } else if (lane == 0) p.cmp.cnt[cr] = -1;
-              }
-              if (p.u != nullptr && p.u[row] >= 0.f) {
-                const int e2 = frexp_exp(__shfl_sync(0xffffffffu, pr, 0));
-                const unsigned long long wi = weight_of(pr, e2);
-                const unsigned long long tot = warp_sum(wi);
-                if (tot == 0ull) {
-                  if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
-                } else {
-                  const unsigned long long target = scale_target(tot, u_to_int(p.u[row]));
-                  unsigned long long before = 0ull;
-                  for (int j = 0; j < np; ++j) {
-                    const int idj = __shfl_sync(0xffffffffu, id, j);
-                    const unsigned long long wj = __shfl_sync(0xffffffffu, wi, j);
-                    before += idj < id ? wj : 0ull;
-                  }
-                  const int top_id = __shfl_sync(0xffffffffu, id, 0);
-                  if (in_p && wi > 0ull && target >= before && target < before + wi)
-                    p.tok_out[row] = (pr < kProbGuard) ? top_id : id;
-                }
-              }
-            } else {
-              const float M = sh.s_val[0];
-              double zs = 0.0;
-              for (int i = lane; i < nk; i += 32) zs += static_cast<double>(expf(sh.s_val[i] - M));
-              zs = warp_sum(zs);
-              int np = nk;
-              if (p.top_p > 0.f) {
-                const float rz = 1.0f / static_cast<float>(zs);
-                double run = 0.0;
-                for (int base = 0; base < nk; base += 32) {
-                  const int i = base + lane;
-                  const float sp = i < nk ? expf(sh.s_val[i] - M) * rz : 0.f;
-                  const double cum = warp_scan_incl(static_cast<double>(sp), lane) + run;
-                  const unsigned ball = __ballot_sync(0xffffffffu, i < nk && static_cast<float>(cum) > p.top_p);
-                  if (ball) { np = min(nk, base + __ffs(ball)); break; }
-                  run = __shfl_sync(0xffffffffu, cum, 31);
-                }
-              }
-              double z2 = 0.0;
-              for (int i = lane; i < np; i += 32) z2 += static_cast<double>(expf(sh.s_val[i] - M));
-              z2 = warp_sum(z2);
-              const float logz = logf(static_cast<float>(z2));
-              bool badp = false;
-              for (int i = lane; i < np; i += 32) {
-                const float pr = expf((sh.s_val[i] - M) - logz);
-                badp |= !(pr >= 0.f) || isinf(pr);
-                sh.a_val[i] = pr;
-              }
-              if (badp) atomicOr(p.err_flag, kErrNanLogit);
-              if (lane == 0) sh.n_keep_p = np;
-              __syncwarp();
-              if (p.cmp.cnt != nullptr) {
-                const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
-                if (np <= p.cmp.cap) {
-                  for (int i = lane; i < np; i += 32) { p.cmp.idx[cr * p.cmp.cap + i] = sh.s_idx[i]; p.cmp.val[cr * p.cmp.cap + i] = sh.a_val[i]; }
-                  if (lane == 0) p.cmp.cnt[cr] = np;
-                } else if (lane == 0) p.cmp.cnt[cr] = -1;
-              }
-              if (p.u != nullptr && p.u[row] >= 0.f) {
-                const int e = frexp_exp(sh.a_val[0]);
-                unsigned long long tot = 0ull;
-                for (int i = lane; i < np; i += 32) tot += weight_of(sh.a_val[i], e);
-                tot = warp_sum(tot);
-                if (tot == 0ull) {
-                  if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
-                } else {
-                  const unsigned long long target = scale_target(tot, u_to_int(p.u[row]));
-                  for (int i = lane; i < np; i += 32) {
-                    const int id = sh.s_idx[i];
-                    const unsigned long long wi = weight_of(sh.a_val[i], e);
-                    unsigned long long before = 0ull;
-                    for (int j = 0; j < np; ++j) before += (sh.s_idx[j] < id) ? weight_of(sh.a_val[j], e) : 0ull;
-                    if (wi > 0ull && target >= before && target < before + wi)
-                      p.tok_out[row] = (sh.a_val[i] < kProbGuard) ? sh.s_idx[0] : id;
-                  }
-                }
+              r += __shfl_xor_sync(0xffffffffu, r, 1);
+              r += __shfl_xor_sync(0xffffffffu, r, 2);
+              if (live && (tid & 3) == 0) {
+                sh.s_val[par][r] = key2f(static_cast<uint32_t>(ki >> 32));
+                sh.s_idx[par][r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(ki & 0xffffffffull));
               }
             }
           }
-          ring_named_bar(1, CT);
-          if (want_probs) {                                     // scatter the non-zeros over the zero-filled row
-            const int np = sh.n_keep_p;
-            if (tid < np) {
-              mbar_wait(&sh.zeroed[it % kRingItemRing], static_cast<uint32_t>(it / kRingItemRing) & 1u);
-              for (int i = tid; i < np; i += CT) orow[sh.s_idx[i]] = sh.a_val[i];
-            }
+          ring_named_bar(1, CT);                                // sorted list complete
+          if (tid == 0) {
+            sh.n_sorted[par] = ok ? n_tot : -1;
+            ring_arrive(&sh.sorted[par]);                        // hand the row over to the aux warp and go on
           }
-          ring_named_bar(1, CT);                                // scratch is reused by the next row
-          }
+          RING_PROF(7);
         } else {
           // =================================================================== DENSE (top_k = 0, top_p = 0)
           // thread -> vectors: warp w owns vectors c * 1024 + w * 64 + {lane, 32 + lane} of chunk c: one contiguous
@@ -650,6 +673,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
             }
           }
           if (nan_acc != nan_acc || nan_acc == INFINITY) atomicOr(p.err_flag, kErrNanLogit);
+          RING_PROF(1);
           // ---- combine: warp, then CTA (every thread folds the 16 warp results itself: one barrier)
           {
             const float Mw = warp_max(m_t);
@@ -677,6 +701,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           // sampler weights  w = floor(p * 2^(40 - e)),  e = frexp exponent of the row maximum exp2(c2)
           const float scale = ldexpf(1.0f, kScaleBits - frexp_exp(ex2_ftz(c2)));
           const float scale_hi = scale * 9.5367431640625e-07f;              // 2^-20 * scale (exact)
+          RING_PROF(2);
           // ---- pass B: probabilities out (16-byte streaming stores), exact weight sums per piece, slots released
           for (int c = 0; c < NCH; ++c) {
             const int slot = slot_of(c);
@@ -722,6 +747,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           }
           __syncwarp();
           if (lane == 0) ring_arrive(&sh.row_done[par]);       // (release: this warp's stores and piece sums first)
+          RING_PROF(7);
           if (p.cmp.cnt != nullptr && tid == 0) p.cmp.cnt[static_cast<long long>(row) * p.cmp.row_stride] = -1;   // no compact list
         }
         slot0 += NCH;
@@ -736,8 +762,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
     if (n_fail > 0 || reason != kRingEndDone) {
       if (tid == 0) {                                           // retire the mbarriers before their memory is re-purposed / re-initialised
         for (int s = 0; s < NS; ++s) { mbar_inval(&sh.full[s]); mbar_inval(&sh.empty[s]); }
-        for (int i = 0; i < kRingItemRing; ++i) { mbar_inval(&sh.rowfull[i]); mbar_inval(&sh.zeroed[i]); }
-        for (int i = 0; i < 2; ++i) { mbar_inval(&sh.row_done[i]); mbar_inval(&sh.tfree[i]); }
+        for (int i = 0; i < kRingItemRing; ++i) mbar_inval(&sh.rowfull[i]);
+        for (int i = 0; i < 2; ++i) { mbar_inval(&sh.row_done[i]); mbar_inval(&sh.tfree[i]); mbar_inval(&sh.sorted[i]); mbar_inval(&sh.sfree[i]); }
       }
       __syncthreads();
     }
