@@ -692,12 +692,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
             if (mw > -INFINITY) z += sh.ws[w] * static_cast<double>(ex2_ftz((mw - M) * kLog2e));
           }
           const float logz = logf(static_cast<float>(z));
-          if (tid == 0 && (!(z > 0.0) || isinf(logz) || logz != logz)) atomicOr(p.err_flag, kErrNanLogit);
+          if (!(z > 0.0) || isinf(logz) || logz != logz) { if (tid == 0) atomicOr(p.err_flag, kErrNanLogit); }   // (uniform condition)
           const float c2 = -logz * kLog2e;
           const bool do_sample = p.u != nullptr && p.u[row] >= 0.f;        // row-uniform
           const int par = it & 1;
           if (it >= 2) mbar_wait(&sh.tfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);   // sampler is done with item it - 2
-          if (tid == 0) sh.info_c2[par] = c2;
+          if (warp == 0) sh.info_c2[par] = c2;                   // (whole warp, same value: no single-lane branch in front of the warp reductions below)
           // sampler weights  w = floor(p * 2^(40 - e)),  e = frexp exponent of the row maximum exp2(c2)
           const float scale = ldexpf(1.0f, kScaleBits - frexp_exp(ex2_ftz(c2)));
           const float scale_hi = scale * 9.5367431640625e-07f;              // 2^-20 * scale (exact)
