@@ -12,19 +12,25 @@ logits.  ONE STEP = one pass of the hot path over one batch:
     kernel 2     sd_verify       accept / first reject / residual / inverse-CDF sample / append
 Metric: accepted tokens/s (whole job, all GPUs); emitted tokens/s and the acceptance are reported too.
 
-value     inputs resident in HBM, the three kernels of a step replayed from a CUDA graph, timed with CUDA
-          events around exactly K steps (barrier + synchronize on both sides, max over ranks).  Inputs
-          rotate over distinct sets whose total exceeds 2x the 126 MB L2.
-e2e       same steps through the public tensor API with HOST buffers: every step copies its logits and
-          uniforms from pinned host memory to the device and reads accept counts and tokens back.
-roofline  dominant kernel (norm, 1 launch per step): algorithmic bytes (rows * V * (4 read + 4 written))
-          / its average launch duration, measured with CUDA events in an instrumented replay of the same
-          K steps; peak = MEASURED_PEAKS.json hbm_gbs.
+value     inputs resident in HBM, steps replayed from CUDA graphs, timed with CUDA events around exactly K steps (barrier +
+          synchronize on both sides, max over ranks).  Inputs rotate over distinct sets whose total exceeds 2x the 126 MB
+          L2.  By default the steps are software-pipelined (--pipeline 1): a 16-step graph launches kernel 1 of batch i+1
+          right behind kernel 1 of batch i while kernel 2 of batch i runs beside it on a second stream — two independent
+          batches in flight, as a serving loop with more than one batch would run them; `serial_ms_per_step` is the same
+          step with its kernels strictly one after the other.
+e2e       same steps through the public tensor API with HOST buffers: every step copies its logits and uniforms from
+          pinned host memory to the device (double-buffered on a copy stream) and reads accept counts and tokens back.
+roofline  dominant kernel (norm, 1 launch per step): algorithmic bytes (rows * V * (4 read + 4 written)) / its average
+          launch duration from back-to-back graph replays (>= 240 launches whatever --steps is); peak =
+          MEASURED_PEAKS.json hbm_gbs.  `roofline.step` is the same for the whole step, `roofline.verify_dense` kernel 2's
+          dense path (top_k = 0) at V = 32000 / 50272.
+gpu_aten_baseline   the reference's ATen op chain on the same B200, batch 1 as the reference runs (oracle/aten_gpu.py).
 cpu_baseline / --impl reference   the oracle port of the reference's CPU path (oracle/ref_ops.py: the same
           ATen op chain, one row at a time, host syncs included) on a bounded sample of the same workload.
+config1   BASELINE.json configs[0] (reduced): the oracle loop on one host core vs the drop-in on cuda:0, tokens compared.
 
-N > 1 (torchrun): requests are independent, every rank runs the same per-GPU batch on its own synthetic
-shard with no data-path collective ("scaling": "weak"); NCCL is used for the barrier and the final
+N > 1 (torchrun): requests are independent, every rank runs the same per-GPU batch (identical synthetic sets)
+with no data-path collective ("scaling": "weak"); NCCL is used for the barrier and the final
 statistics reduction only.
 """
 from __future__ import annotations
@@ -310,6 +316,78 @@ def run_variants(args):
 
 
 # ------------------------------------------------------------------------------------------- B200 arm
+PIPE_STEPS = 16          # steps captured in the software-pipelined graph
+
+
+def gpu_aten_baseline(logits_set, dev, n_req=8):
+    """SURVEY §2.2 / BASELINE.md §3: the reference's ATen op chain on the SAME B200 (oracle/aten_gpu.py restates it launch
+    for launch, host syncs included), one request at a time as the reference runs, CUDA-event timed."""
+    from oracle import aten_gpu
+    g = GAMMA
+    lg = logits_set[:n_req]                                  # (n_req, 2g+1, V): gamma draft rows then gamma+1 target rows
+    torch.manual_seed(0)
+    for b in range(2):
+        aten_gpu.iteration(lg[b, :g], lg[b, g:], TEMP, TOP_K, TOP_P)
+    torch.cuda.synchronize()
+    launches = None
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            aten_gpu.iteration(lg[0, :g], lg[0, g:], TEMP, TOP_K, TOP_P)
+            torch.cuda.synchronize()
+        launches = sum(1 for e in prof.events() if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower())
+    except Exception:                                        # noqa: BLE001  (profiler unavailable: the count stays None)
+        launches = None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc = 0
+    e0.record()
+    for b in range(n_req):
+        n, _ = aten_gpu.iteration(lg[b, :g], lg[b, g:], TEMP, TOP_K, TOP_P)
+        acc += n
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"accepted_tokens_per_s": acc / (ms * 1e-3), "ms_per_request_iteration": ms / n_req, "requests": n_req,
+            "kernel_launches_per_request_iteration": launches,
+            "what": "oracle/aten_gpu.py: the reference's per-row ATen op chain (utils.py:152-245, speculative_sampling.py:1966-2027) on "
+                    "CUDA tensors of the same workload, batch 1 as the reference runs, torch.multinomial / torch.rand on the device"}
+
+
+def config1_side_report():
+    """BASELINE.json configs[0] (the one case the reference runs as-is), reduced so that it fits the default run:
+    llama-68m-shape draft + target with IDENTICAL random weights (acceptance 1.0), gamma=4, batch=1, 64 new tokens, fp32,
+    T=1 top_k=20 top_p=0.9: the oracle port of the reference loop on one host core vs the drop-in on cuda:0 — same weights,
+    prompt and uniform tape; leading tokens compared.  The full report is `bench.py --workload config1`."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from llmspeculativesampling_b200 import uniform_tape
+    from llmspeculativesampling_b200.sampling import speculative_sampling
+    from oracle import spec_loop
+    cfg = LlamaConfig(vocab_size=32000, hidden_size=768, intermediate_size=3072, num_hidden_layers=2,
+                      num_attention_heads=12, num_key_value_heads=12, max_position_embeddings=2048)
+    prompt = torch.randint(3, 32000, (1, 16), generator=torch.Generator().manual_seed(7))
+    torch.manual_seed(0); draft = LlamaForCausalLM(cfg).eval()
+    torch.manual_seed(0); target = LlamaForCausalLM(cfg).eval()
+    N = 64
+    tape = uniform_tape.batch_tape(3, [0], N + 1, GAMMA)
+    torch.set_num_threads(1)
+    t0 = time.perf_counter()
+    ref_tok, ref_d = spec_loop.speculative_sampling(prompt, draft, target, N, GAMMA, 1.0, 20, 0.9, tape=tape[:, 0])
+    cpu_s = time.perf_counter() - t0
+    dg, tg = draft.cuda(), target.cuda()
+    speculative_sampling(prompt.cuda(), dg, tg, None, None, N, GAMMA, 1.0, 20, 0.9, uniforms=tape)            # warm-up + graph capture
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    tok, d = speculative_sampling(prompt.cuda(), dg, tg, None, None, N, GAMMA, 1.0, 20, 0.9, uniforms=tape, details=True)
+    torch.cuda.synchronize(); gpu_s = time.perf_counter() - t0
+    same = min(ref_tok.shape[1], tok.shape[1]) - 16
+    agree = int((ref_tok[0, 16:16 + same] == tok[0, 16:16 + same].cpu()).long().cumprod(0).sum())
+    return {"workload": "llama-68m-shape draft + target (identical random weights), gamma=4, batch=1, 64 new tokens, fp32, T=1 top_k=20 top_p=0.9",
+            "cpu_oracle_1_thread": {"seconds": cpu_s, "emitted_tokens_per_s": (ref_tok.shape[1] - 16) / cpu_s,
+                                    "accepted_tokens_per_s": sum(ref_d["acc_len"]) / cpu_s},
+            "b200_drop_in": {"seconds": gpu_s, "emitted_tokens_per_s": (tok.shape[1] - 16) / gpu_s, "accepted_tokens_per_s": sum(d["acc_len"]) / gpu_s,
+                             "cuda_graph": d["cuda_graph"]},
+            "leading_tokens_identical_to_cpu_run": agree, "of": same}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -317,11 +395,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-reports", action="store_true", help="skip gpu_aten_baseline / config1 / dense-verify side reports")
     ap.add_argument("--workload", default="config2", choices=["config2", "config1", "variants"],
                     help="config2 = headline synthetic verify microbench; config1 = side report on the reference's CPU-runnable case")
     ap.add_argument("--fused", type=int, default=0,
-                    help="0: sd_norm_sample + sd_verify (two launches per step, the faster arrangement at B = 64); "
-                         "1: sd_norm_sample_verify (one launch per step, requests verified inside the norm kernel)")
+                    help="0: sd_norm_sample + sd_verify (two launches per step); "
+                         "1: sd_norm_sample_verify (one launch per step, requests verified inside the cluster-pipeline norm kernel)")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="1: software-pipelined steps (kernel 2 of batch i runs on a second stream while kernel 1 of batch i+1 streams); "
+                         "0: the two kernels of every step strictly one after the other")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("SD_PDL", "1")), help="programmatic dependent launch on/off")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -346,13 +428,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     build.build()
     ops.set_pdl(bool(args.pdl))
+    clocks = ClockSampler(local)
+    clocks.start()                                          # (nvidia-smi needs a moment to come up: started before the set-up)
 
     B, g = BATCH, GAMMA
     R = 2 * g + 1                                           # rows per request: gamma draft + gamma+1 target
     n_sets = 4                                              # 4 x (73.7 MB logits + 73.7 MB probs) >> 2 x 126 MB L2
-    logits, probs, u_rows, u_acc, u_fin = [], [], [], [], []
+    # every rank runs the SAME synthetic sets (weak scaling: the per-GPU work is identical by construction)
+    logits, probs, u_rows, u_acc, u_fin, tok_rows, cmp_rows, n_acc, next_tok = [], [], [], [], [], [], [], [], []
     for i in range(n_sets):
-        d, t, u = synth_set(rank * 100 + i, dev)
+        d, t, u = synth_set(i, dev)
         logits.append(torch.cat([d, t], dim=1).contiguous())            # (B, 2g+1, V)
         probs.append(torch.empty(B, R, V, device=dev))
         ur = torch.full((B, R), -1.0, device=dev)
@@ -360,46 +445,76 @@ def main():
         u_rows.append(ur.view(-1).contiguous())
         u_acc.append(u[:, g + 1:2 * g + 1].contiguous())
         u_fin.append(u[:, 2 * g + 1].contiguous())
+        tok_rows.append(torch.zeros(B, R, dtype=torch.int64, device=dev))
+        cmp_rows.append(ops.CompactRows(B * R, dev))                    # compact top-k lists written by kernel 1, read by kernel 2
+        n_acc.append(torch.zeros(B, dtype=torch.int32, device=dev))
+        next_tok.append(torch.zeros(B, dtype=torch.int64, device=dev))
         del d, t
-    tok_rows = torch.zeros(B, R, dtype=torch.int64, device=dev)
-    cmp_rows = ops.CompactRows(B * R, dev)                  # compact top-k lists written by kernel 1, read by kernel 2
-    c_all, c_q, c_p = cmp_rows.view(), cmp_rows.view(0, 1), cmp_rows.view(g, 1)
-    n_acc = torch.zeros(B, dtype=torch.int32, device=dev)
-    next_tok = torch.zeros(B, dtype=torch.int64, device=dev)
     acc_total = torch.zeros(2, dtype=torch.int64, device=dev)     # [accepted tokens, requests verified], updated by kernel 2
     err = ops.ErrFlag(dev)
-
     req_cnt = torch.zeros(B, dtype=torch.int32, device=dev)       # fused launch: finished-row counters (left zeroed)
+
+    def norm(i: int, lg=None, ur=None, pr=None):
+        ops.norm_sample((logits[i] if lg is None else lg).view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i] if ur is None else ur,
+                        probs_out=(probs[i] if pr is None else pr).view(B * R, V), tok_out=tok_rows[i].view(-1), err=err,
+                        compact=cmp_rows[i].view())
+
+    def verify(i: int, count: bool = True, pr=None, ua=None, uf=None):
+        p_ = probs[i] if pr is None else pr
+        ops.verify(p_[:, g:], p_[:, :g], tok_rows[i][:, :g], u_acc[i] if ua is None else ua, u_fin[i] if uf is None else uf,
+                   n_accepted=n_acc[i], next_tok=next_tok[i], err=err, p_compact=cmp_rows[i].view(g, 1), p_cmp_req_stride=R,
+                   q_compact=cmp_rows[i].view(0, 1), q_cmp_req_stride=R, stats=acc_total if count else None)
 
     def step(i: int, count: bool = True):
         if args.fused:
-            # ONE launch: kernel 1 over the B*(2*gamma+1) rows; each request is verified inside it as soon as its last
-            # row is normalised (sd_norm_sample_verify)
             ops.norm_sample_verify(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs[i].view(B * R, V),
-                                   tok_rows.view(-1), c_all, R, req_cnt, probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g],
-                                   u_acc[i], u_fin[i], n_acc, next_tok, c_p, R, c_q, R, err,
-                                   stats=acc_total if count else None)
+                                   tok_rows[i].view(-1), cmp_rows[i].view(), R, req_cnt, probs[i][:, g:], probs[i][:, :g],
+                                   tok_rows[i][:, :g], u_acc[i], u_fin[i], n_acc[i], next_tok[i], cmp_rows[i].view(g, 1), R,
+                                   cmp_rows[i].view(0, 1), R, err, stats=acc_total if count else None)
             return
-        ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
-                        tok_out=tok_rows.view(-1), err=err, compact=c_all)
-        ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
-                   next_tok=next_tok, err=err, p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R,
-                   stats=acc_total if count else None)
+        norm(i)
+        verify(i, count)
 
-    # one CUDA graph per input set (3 kernels + the accept-count accumulation)
     for i in range(n_sets):
         step(i)
     torch.cuda.synchronize()
-    graphs = []
     side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for i in range(n_sets):
-            gr = torch.cuda.CUDAGraph()
+    side2 = torch.cuda.Stream()
+
+    def capture(fn):
+        gr = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
             with torch.cuda.graph(gr, stream=side):
-                step(i)
-            graphs.append(gr)
-    torch.cuda.current_stream().wait_stream(side)
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        return gr
+
+    g_serial = [capture(lambda i=i: step(i)) for i in range(n_sets)]       # one step, its kernels strictly in order
+
+    def pipelined():
+        """PIPE_STEPS steps on two streams: kernel 1 of step j+1 is launched right behind kernel 1 of step j, kernel 2 of
+        step j runs beside it on the second stream (it needs a few KB of compact lists and a handful of thread blocks).
+        A step's buffers are reused n_sets steps later: kernel 1 of step j waits for kernel 2 of step j - n_sets."""
+        main_s = torch.cuda.current_stream()
+        ev_v = {}
+        for j in range(PIPE_STEPS):
+            i = j % n_sets
+            if j - n_sets in ev_v:
+                main_s.wait_event(ev_v[j - n_sets])
+            norm(i)
+            ev_n = torch.cuda.Event()
+            ev_n.record(main_s)
+            side2.wait_event(ev_n)
+            with torch.cuda.stream(side2):
+                verify(i)
+                ev_v[j] = torch.cuda.Event()
+                ev_v[j].record(side2)
+        for j in range(PIPE_STEPS - n_sets, PIPE_STEPS):
+            main_s.wait_event(ev_v[j])
+
+    use_pipe = bool(args.pipeline) and not args.fused
+    g_pipe = capture(pipelined) if use_pipe else None
     torch.cuda.synchronize()
 
     def barrier():
@@ -407,115 +522,115 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for s in range(args.warmup):
-        graphs[s % n_sets].replay()
+    def run_steps(n: int, first: int = 0):
+        s = 0
+        if g_pipe is not None:
+            while n - s >= PIPE_STEPS:
+                g_pipe.replay()
+                s += PIPE_STEPS
+        while s < n:
+            g_serial[(first + s) % n_sets].replay()
+            s += 1
+
+    run_steps(max(args.warmup, PIPE_STEPS if use_pipe else 0))
     barrier()
     acc_total.zero_()
-    clocks = ClockSampler(local)
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for s in range(args.steps):
-        graphs[s % n_sets].replay()
+    run_steps(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clock_info = clocks.stop()
     err.check()
     accepted = int(acc_total[0].item())
     assert int(acc_total[1].item()) == args.steps * B, "kernel 2 must have verified every request of every step"
+    pipelined_steps = (args.steps // PIPE_STEPS) * PIPE_STEPS if use_pipe else 0
 
-    # ---- per-kernel durations, same steps: (a) the norm kernel alone, replayed back to back from a CUDA graph that
-    #      holds one launch per input set (no host or event overhead between launches), (b) eager launches bracketed
-    #      by events to split a step into norm / verify shares
-    with torch.cuda.stream(side):
-        g_norm = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_norm, stream=side):
-            for i in range(n_sets):
-                ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
-                                tok_out=tok_rows.view(-1), err=err, compact=c_all)
-    torch.cuda.current_stream().wait_stream(side)
-    reps = max(1, args.steps // n_sets)
-    for _ in range(3):
-        g_norm.replay()
-    torch.cuda.synchronize()
-    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0.record()
-    for _ in range(reps):
-        g_norm.replay()
-    n1.record()
-    torch.cuda.synchronize()
-    norm_ms = n0.elapsed_time(n1) / (reps * n_sets)
-    # the verify kernel alone, same way (its inputs are the probabilities / lists the norm launches above left behind)
-    with torch.cuda.stream(side):
-        g_ver = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_ver, stream=side):
-            for i in range(n_sets):
-                ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
-                           next_tok=next_tok, err=err, p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
-    torch.cuda.current_stream().wait_stream(side)
-    for _ in range(3):
-        g_ver.replay()
-    torch.cuda.synchronize()
-    n0.record()
-    for _ in range(reps):
-        g_ver.replay()
-    n1.record()
-    torch.cuda.synchronize()
-    verify_ms = n0.elapsed_time(n1) / (reps * n_sets)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(min(args.steps, 200))]
-    for s in range(len(ev)):
-        i = s % n_sets
-        ev[s][0].record()
-        ops.norm_sample(logits[i].view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i], probs_out=probs[i].view(B * R, V),
-                        tok_out=tok_rows.view(-1), err=err, compact=c_all)
-        ev[s][1].record()
-        ops.verify(probs[i][:, g:], probs[i][:, :g], tok_rows[:, :g], u_acc[i], u_fin[i], n_accepted=n_acc,
-                   next_tok=next_tok, err=err, p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
-        ev[s][2].record()
-    torch.cuda.synchronize()
-    t_norm = sum(e[0].elapsed_time(e[1]) for e in ev) / len(ev)
-    t_verify = sum(e[1].elapsed_time(e[2]) for e in ev) / len(ev)
+    # ---- sub-measurements (self-sized: >= 200 launches whatever --steps is), all from CUDA graphs replayed back to back:
+    #      the strictly serial step (latency of one batch), kernel 1 alone, kernel 2 alone
+    def timed(graph, launches_per_replay, min_launches=240):
+        reps = max(3, (min_launches + launches_per_replay - 1) // launches_per_replay)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            graph.replay()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / (reps * launches_per_replay)
+
+    serial_ms = timed(capture(lambda: [step(i, False) for i in range(n_sets)]), n_sets)
+    norm_ms = timed(capture(lambda: [norm(i) for i in range(n_sets)]), n_sets)
+    verify_ms = timed(capture(lambda: [verify(i, False) for i in range(n_sets)]), n_sets)
+    clock_info = clocks.stop()
     norm_bytes = B * R * V * 8                              # logits read once (4 B) + probs written once (4 B)
     achieved = norm_bytes / (norm_ms * 1e-3) / 1e9
+    # kernel 2, SURVEY 8(d): per request 2*gamma*4 B of gathers + 2*V*4 B if a rejection occurred, V*4 B if all accepted, 16 B out
+    n_all = torch.stack(n_acc).long()
+    verify_bytes = float((n_all.numel() * (2 * g * 4 + 16) + int((n_all < g).sum()) * 2 * V * 4 + int((n_all >= g).sum()) * V * 4) / n_sets)
 
-    # ---- end to end: host buffers, H2D of the step's inputs and D2H of its results inside the timed region
+    # ---- end to end: host buffers; the H2D copy of step s+1 runs on a copy stream while step s computes (two device
+    #      input buffers), accept counts / tokens come back with an event, no device-wide synchronize inside the loop
     host_sets = [(logits[i].cpu().pin_memory(), torch.cat([u_rows[i].view(B, R), u_acc[i], u_fin[i].view(B, 1)], 1).cpu().pin_memory())
                  for i in range(n_sets)]
-    l_dev, pr_dev = torch.empty(B, R, V, device=dev), torch.empty(B, R, V, device=dev)
-    u_dev = torch.empty(B, R + g + 1, device=dev)
-    ur_dev, ua_dev, uf_dev = torch.empty(B * R, device=dev), torch.empty(B, g, device=dev), torch.empty(B, device=dev)
-    h_acc = torch.empty(B, dtype=torch.int32).pin_memory()
-    h_tok = torch.empty(B, dtype=torch.int64).pin_memory()
+    nbuf = 2
+    l_dev = [torch.empty(B, R, V, device=dev) for _ in range(nbuf)]
+    u_dev = [torch.empty(B, R + g + 1, device=dev) for _ in range(nbuf)]
+    pr_dev = torch.empty(B, R, V, device=dev)
+    h_acc = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(nbuf)]
+    h_tok = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(nbuf)]
+    copy_s = torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_free = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+    cur = torch.cuda.current_stream()
 
-    def e2e_step(i: int) -> int:
-        hl, hu = host_sets[i]
-        l_dev.copy_(hl, non_blocking=True); u_dev.copy_(hu, non_blocking=True)
-        ur_dev.copy_(u_dev[:, :R].reshape(-1)); ua_dev.copy_(u_dev[:, R:R + g]); uf_dev.copy_(u_dev[:, R + g])
-        if args.fused:
-            ops.norm_sample_verify(l_dev.view(B * R, V), TEMP, TOP_K, TOP_P, ur_dev, pr_dev.view(B * R, V), tok_rows.view(-1),
-                                   c_all, R, req_cnt, pr_dev[:, g:], pr_dev[:, :g], tok_rows[:, :g], ua_dev, uf_dev, n_acc,
-                                   next_tok, c_p, R, c_q, R, err)
-        else:
-            ops.norm_sample(l_dev.view(B * R, V), TEMP, TOP_K, TOP_P, ur_dev, probs_out=pr_dev.view(B * R, V),
-                            tok_out=tok_rows.view(-1), err=err, compact=c_all)
-            ops.verify(pr_dev[:, g:], pr_dev[:, :g], tok_rows[:, :g], ua_dev, uf_dev, n_accepted=n_acc, next_tok=next_tok, err=err,
-                       p_compact=c_p, p_cmp_req_stride=R, q_compact=c_q, q_cmp_req_stride=R)
-        h_acc.copy_(n_acc, non_blocking=True); h_tok.copy_(next_tok, non_blocking=True)
-        torch.cuda.synchronize()                            # the caller needs the tokens before the next step
-        return int(h_acc.sum())
+    def e2e_upload(s: int):
+        b = s % nbuf
+        hl, hu = host_sets[s % n_sets]
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(ev_free[b])                   # the step that last read this buffer has finished
+            l_dev[b].copy_(hl, non_blocking=True)
+            u_dev[b].copy_(hu, non_blocking=True)
+            ev_in[b].record(copy_s)
 
-    e2e_steps = max(3, min(args.steps, 40))
-    for s in range(3):
-        e2e_step(s % n_sets)
+    def e2e_compute(s: int):
+        b, i = s % nbuf, s % n_sets
+        cur.wait_event(ev_in[b])
+        ub = u_dev[b]
+        norm(i, lg=l_dev[b], ur=ub[:, :R].reshape(-1), pr=pr_dev)
+        verify(i, False, pr=pr_dev, ua=ub[:, R:R + g].contiguous(), uf=ub[:, R + g].contiguous())
+        ev_free[b].record(cur)
+        h_acc[b].copy_(n_acc[i], non_blocking=True)
+        h_tok[b].copy_(next_tok[i], non_blocking=True)
+        ev_out[b].record(cur)
+
+    def e2e_run(n: int) -> int:
+        got = 0
+        e2e_upload(0)
+        for s in range(n):
+            if s + 1 < n:
+                e2e_upload(s + 1)
+            e2e_compute(s)
+            if s >= 1:                                      # the caller reads step s-1's tokens while step s runs
+                ev_out[(s - 1) % nbuf].synchronize()
+                got += int(h_acc[(s - 1) % nbuf].sum())
+        ev_out[(n - 1) % nbuf].synchronize()
+        return got + int(h_acc[(n - 1) % nbuf].sum())
+
+    for ev in ev_free:
+        ev.record(cur)
+    e2e_steps = max(4, min(args.steps, 60))
+    e2e_run(4)
     barrier()
     t0 = time.perf_counter()
-    e2e_acc = 0
-    for s in range(e2e_steps):
-        e2e_acc += e2e_step(s % n_sets)
-    barrier()
+    e2e_acc = e2e_run(e2e_steps)
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    barrier()
     h2d = (B * R * V + B * (R + g + 1)) * 4
     d2h = B * (4 + 8)
 
@@ -543,34 +658,52 @@ def main():
         pass
     secs = ms * 1e-3
     iters_total = args.steps * B * world
+    step_ms = ms / args.steps
+    step_bytes = norm_bytes + verify_bytes
     line = {
         "metric": "accepted_tokens_per_s", "value": accepted / secs, "unit": "tokens/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2_policy": f"inputs and outputs rotate over {n_sets} sets "
-                   f"({n_sets * norm_bytes / 1e6:.0f} MB > 2 x 126 MB L2)", "cuda_graph": True,
+                   f"({n_sets * norm_bytes / 1e6:.0f} MB > 2 x 126 MB L2), identical on every rank", "cuda_graph": True,
+                   "pipeline": (f"software-pipelined: {pipelined_steps} of the {args.steps} timed steps ran from a {PIPE_STEPS}-step CUDA graph in which "
+                                "kernel 2 of batch i runs on a second stream beside kernel 1 of batch i+1 (two independent batches in "
+                                "flight; results identical); the rest strictly serial") if use_pipe else "strictly serial steps",
                    "kernels_per_step": (["sd_norm_sample_verify (ONE launch: kernel 1 over the B*(2*gamma+1) rows — dense probs + "
-                                         "compact lists — and kernel 2's verify of each request inside it, by the thread group "
-                                         "that finishes the request's last row)"] if args.fused else
-                                        ["sd_norm_sample (B*(2*gamma+1) rows, one launch; dense probs + compact lists)",
+                                         "compact lists — and kernel 2's verify of each request inside it)"] if args.fused else
+                                        ["sd_norm_sample (ring kernel: B*(2*gamma+1) rows, one launch; dense probs + compact lists)",
                                          "sd_verify (sparse path on the compact lists)"])},
         "emitted_tokens_per_s": (accepted + iters_total) / secs,
         "mean_accepted_per_iteration": accepted / iters_total,
         "request_iterations_per_s": iters_total / secs,
+        "serial_ms_per_step": serial_ms,
         "clocks": clock_info,
         "gpu_launches": (1 if args.fused else 2) * args.steps,
         "e2e": {"value": e2e_acc / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "h2d_GBs_per_gpu": h2d / (e2e_s / e2e_steps) / 1e9,
+                "note": "double-buffered pinned-host -> device copies on a copy stream, results read back with events; "
+                        "bound by the host link (73.7 MB of fp32 logits per step)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "norm_topk_pipe_kernel<float,4,3,128> (1 launch per step, 576 rows; timed without the in-kernel verify)",
+                     "traffic": traffic, "kernel": "norm_ring_kernel<float, top-k> (1 launch per step, 576 rows)",
                      "algorithmic_bytes_per_step": norm_bytes, "ms_per_step": norm_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                      "frac_of_nominal_8TBs": achieved / 8000.0,
-                     "timing": "CUDA events around back-to-back graph replays of the norm launch (4 rotating input sets)",
-                     "kernel_ms_eager_with_events": {"norm": t_norm, "verify": t_verify},
+                     "timing": "CUDA events around back-to-back graph replays of the launch (4 rotating input sets, >= 240 launches)",
                      "kernel_ms_graph_back_to_back": {"norm": norm_ms, "verify": verify_ms},
-                     "norm_share_of_step": t_norm / (t_norm + t_verify)},
+                     "step": {"algorithmic_bytes": step_bytes, "ms": step_ms, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                              "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "serial_ms": serial_ms,
+                              "serial_frac": step_bytes / (serial_ms * 1e-3) / 1e9 / peak,
+                              "note": "whole step (kernel 1 + kernel 2, SURVEY 8d bytes from the actual accept counts) over the timed ms_per_step"}},
     }
+    if not args.no_side_reports:
+        try:
+            line["roofline"]["verify_dense"] = dense_verify_report(dev, ops)
+        except Exception as e:                                # noqa: BLE001
+            line["roofline"]["verify_dense"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        try:
+            line["gpu_aten_baseline"] = gpu_aten_baseline(logits[0], dev)
+        except Exception as e:                                # noqa: BLE001
+            line["gpu_aten_baseline"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     if not args.no_cpu_baseline:
         per = 16
         cores = os.cpu_count() or 1
@@ -586,10 +719,70 @@ def main():
                                 "sample": f"{n_steps} steps x {per} requests of the same workload ({n_steps * per * (2 * GAMMA + 1)} rows "
                                           f"+ verify) through oracle/ref_ops.py (the reference's ATen op chain, row by row), "
                                           f"torch threads={best_threads} of {cores} host cores; {dt_c:.1f} s of CPU work"}
+        if not args.no_side_reports:
+            try:
+                line["config1"] = config1_side_report()
+            except Exception as e:                            # noqa: BLE001
+                line["config1"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def dense_verify_report(dev, ops):
+    """Kernel 2's dense path (no compact lists: top_k = 0, the reference API's default) at B = 64, gamma = 4: achieved HBM
+    GB/s on the SURVEY 8(d) bytes computed from the actual accept counts, CUDA-graph replays back to back."""
+    out = {}
+    B, g = BATCH, GAMMA
+    for V_ in (32000, 50272):
+        n_sets = 3
+        sets = []
+        for s in range(n_sets):
+            gen = torch.Generator(device=dev).manual_seed(77 + s)
+            z = 3.0 * torch.randn(B, g + 1, V_, generator=gen, device=dev)
+            tl = z + 0.5 * torch.randn(B, g + 1, V_, generator=gen, device=dev)
+            dl = z[:, :g] + 0.5 * torch.randn(B, g, V_, generator=gen, device=dev)
+            u = torch.rand(B, 2 * g + 2, generator=gen, device=dev)
+            q = torch.empty(B, g, V_, device=dev)
+            p = torch.empty(B, g + 1, V_, device=dev)
+            e = ops.ErrFlag(dev)
+            tok = ops.norm_sample(dl.view(B * g, V_), 1.0, 0, 0.0, u[:, :g].contiguous().view(-1), probs_out=q.view(B * g, V_), err=e).view(B, g)
+            ops.norm_probs(tl.view(B * (g + 1), V_), 1.0, 0, 0.0, out=p.view(B * (g + 1), V_), err=e)
+            sets.append((p, q, tok, u[:, g + 1:2 * g + 1].contiguous(), u[:, 2 * g + 1].contiguous(), torch.zeros(B, dtype=torch.int32, device=dev)))
+            del z, tl, dl
+        nxt = torch.zeros(B, dtype=torch.int64, device=dev)
+        e = ops.ErrFlag(dev)
+
+        def launch_all():
+            for (p, q, tok, ua, uf, na) in sets:
+                ops.verify(p, q, tok, ua, uf, n_accepted=na, next_tok=nxt, err=e)
+        launch_all()
+        torch.cuda.synchronize()
+        st = torch.cuda.Stream()
+        gr = torch.cuda.CUDAGraph()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(gr, stream=st):
+                launch_all()
+        torch.cuda.current_stream().wait_stream(st)
+        for _ in range(3):
+            gr.replay()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 80
+        t0.record()
+        for _ in range(reps):
+            gr.replay()
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / (reps * n_sets)
+        na = torch.stack([s[5] for s in sets]).long()
+        nbytes = (na.numel() * (2 * g * 4 + 16) + int((na < g).sum()) * 2 * V_ * 4 + int((na >= g).sum()) * V_ * 4) / n_sets
+        out[f"V{V_}"] = {"ms": ms, "algorithmic_bytes": nbytes, "GBs": nbytes / ms / 1e6, "mean_accepted": float(na.float().mean())}
+        del sets
+        torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -340,3 +340,26 @@ def test_bild_engine_matches_oracle_per_request(cuda_lib, use_graph):
         assert int(drafted[:, b].sum()) == det["approx_call_times"]
         unchecked_exit += int((acc[:, b] < 0).logical_and(acc[:, b] > -1000).any())
     assert outs[0].shape[1] >= len(prompts[0]) + N
+
+
+def test_union_of_shards_equals_single_batch(cuda_lib):
+    """requests are independent, so sharding them over GPUs (round-robin, as sharding.
+    shard_requests does) must reproduce the single-batch tokens bit for bit — per-request uniform tapes are keyed by the
+    GLOBAL request id.  One process here: the same 16 ragged requests as one batch and as two shards."""
+    from llmspeculativesampling_b200.sampling import speculative_sampling
+    from llmspeculativesampling_b200.sharding import shard_requests
+    V, n_req = 2000, 16
+    d, t = _pair(V, 31, 0.5)
+    gq = torch.Generator().manual_seed(4)
+    prompts = [torch.randint(3, V, (int(n),), generator=gq).cuda() for n in torch.randint(4, 12, (n_req,), generator=gq)]
+    whole, det = speculative_sampling(prompts, d, t, None, None, 20, 4, 0.9, 20, 0.9, random_seed=9, request_ids=list(range(n_req)),
+                                      details=True)
+    assert sum(sum(a) for a in det["acc_len"]) > 0
+    for world in (2, 4):
+        got = [None] * n_req
+        for rank in range(world):
+            ids = shard_requests(n_req, world, rank)
+            outs = speculative_sampling([prompts[r] for r in ids], d, t, None, None, 20, 4, 0.9, 20, 0.9, random_seed=9, request_ids=ids)
+            for r, o in zip(ids, outs):
+                got[r] = o
+        assert all(torch.equal(a, b) for a, b in zip(whole, got)), f"world={world}"

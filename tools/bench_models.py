@@ -85,11 +85,13 @@ def main():
     init_s = time.time() - t0
     n_req = a.requests or a.batch * world
     mine = shard_requests(n_req, world, rank)
+    a.batch = max(1, min(a.batch, len(mine)))                          # strong scaling: a shard smaller than the batch runs as one batch
     results = []
     for setting in a.settings.split(","):
         top_k, top_p = (20, 0.9) if setting == "k20p0.9" else (0, 0.0)
         eng = SpecDecEngine(draft, target, a.batch, a.prompt + a.new, a.gamma, 1.0, top_k, top_p, dev)
         tot_emit = tot_acc = tot_iter_req = 0
+        checksum = 0
         elapsed = 0.0
         captured = False
         for bi, ids in enumerate(batches(mine, a.batch)):
@@ -114,15 +116,26 @@ def main():
             tot_acc += int(acc[:, :real][live[:, :real]].sum())
             tot_iter_req += int(live[:, :real].sum())
             tot_emit += int((eng.seq_len - eng.prompt_len)[:real].sum())
-        stats = torch.tensor([elapsed, float(tot_emit), float(tot_acc), float(tot_iter_req)], dtype=torch.float64, device=dev)
+            # order-independent checksum of (request id, emitted tokens): equal sums over N = 1, 2, 4, 8 mean the union of
+            # the shards reproduced the single-GPU tokens (exact for bit-reproducible logits; GEMMs of a real model may
+            # pick different algorithms at different batch sizes)
+            toks, lens, plen = eng.tokens[:real].cpu(), eng.seq_len[:real].cpu(), eng.prompt_len[:real].cpu()
+            for j in range(real):
+                row = toks[j, int(plen[j]):int(lens[j])].tolist()
+                h = 1469598103934665603
+                for t in [ids[j]] + row:
+                    h = ((h ^ int(t)) * 1099511628211) & 0xFFFFFFFFFFFF
+                checksum = (checksum + h) % (1 << 52)
+        stats = torch.tensor([elapsed, float(tot_emit), float(tot_acc), float(tot_iter_req), float(checksum)], dtype=torch.float64, device=dev)
         if world > 1:
             mx = stats[:1].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = stats[1:].clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             stats = torch.cat([mx, sm])
-        el, emit, acc_n, itreq = [float(x) for x in stats]
+        el, emit, acc_n, itreq, csum = [float(x) for x in stats]
         results.append({"setting": setting, "top_k": top_k, "top_p": top_p, "emitted_tokens_per_s": emit / el,
                         "accepted_tokens_per_s": acc_n / el, "mean_accepted_per_iteration": acc_n / max(itreq, 1),
-                        "request_iterations_per_s": itreq / el, "seconds": el, "cuda_graph": captured})
+                        "request_iterations_per_s": itreq / el, "seconds": el, "cuda_graph": captured,
+                        "emitted_tokens": int(emit), "tokens_checksum": int(csum) % (1 << 52)})
         del eng
         torch.cuda.empty_cache()
     if rank == 0:
