@@ -7,7 +7,10 @@
  *
  * Conventions
  *  - every pointer is a DEVICE pointer owned by the caller (torch tensors in the Python host code);
- *    the library allocates nothing, frees nothing, keeps no global state besides the sd_set_tuning knobs;
+ *    the library allocates nothing and frees nothing.  Process-wide state it does keep: the sd_set_tuning /
+ *    sd_set_pdl / sd_debug_set_prof knobs (plain ints / a pointer, meant to be set once before use, not synchronised),
+ *    a mutex-protected cache of launch plans per (dtype, V, top_k), and per-device "attribute set" flags and device
+ *    properties (SM count, shared-memory limit) read from the driver on first use;
  *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, never synchronise,
  *    and are CUDA-graph capturable;
  *  - return value: SD_OK (0), SD_EINVAL (-1, argument error) or a positive cudaError_t;
@@ -31,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SD_VERSION 110
+#define SD_VERSION 200
 #define SD_OK 0
 #define SD_EINVAL (-1)
 
@@ -203,13 +206,18 @@ int sd_verify_multi(const float* p_probs, int64_t p_req_stride, int64_t p_draft_
  * max q[i] < fallback_thres (:1784) — and written to n_drafted[b]; tokens / seq_len (optional, together) get the fused
  * append tokens[b, seq_len + n] = next_tok, seq_len += n + 1; with limit[b] (optional total-length limit) a request with
  * less room than drafted tokens ends like the reference's loop (:1764): the drafted tokens stay unchecked, no target
- * token, n_accepted = -1 - kept tokens, next_tok = -1.  active optional (B,). */
+ * token, n_accepted = -1 - kept tokens, next_tok = -1.  active optional (B,).
+ * q_compact (optional, engine mode): compact lists of the q rows as written by kernel 1 (request b, row i -> logical row
+ * b * q_cmp_req_stride + i): max q is then the maximum of the <= cap listed values instead of a scan of the dense row.
+ * eos_token_id (engine mode, < 0: none): the reference tests for EOS after every draft token (:1826-1841) — an EOS drafted
+ * before the token that triggers the check ends the request with the drafted tokens up to it kept unchecked
+ * (n_accepted = -1 - kept tokens, next_tok = -1). */
 int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_stride, const float* q_probs,
                    int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
                    const int32_t* n_check, int max_check, float fallback_thres, float rollback_thres, const float* u_final,
                    int B, int64_t V, int32_t* n_accepted, int64_t* next_tok, float* nll, int32_t* n_drafted, int64_t* tokens,
-                   int64_t tokens_stride, int32_t* seq_len, const int32_t* limit, const int32_t* active, int* err_flag,
-                   void* stream);
+                   int64_t tokens_stride, int32_t* seq_len, const int32_t* limit, const int32_t* active,
+                   const sd_compact_t* q_compact, int64_t q_cmp_req_stride, int64_t eos_token_id, int* err_flag, void* stream);
 
 /* max_fn — out = max(x,0) / (sum(max(x,0)) + 1e-6) per row.  Replaces sampling/utils.py:236-245. */
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream);
@@ -231,6 +239,12 @@ int sd_kv_append(const void* k_new, const void* v_new, int64_t stride_b, int64_t
 int sd_kv_select(void* k_cache, void* v_cache, int B, int W, int H, int S, int D, int elem_size, int max_count,
                  const int32_t* choice, const int32_t* start, int start_stride, const int32_t* count, const int32_t* active,
                  int active_stride, void* stream);
+
+/* The same for EVERY layer of a model in one launch: k_caches / v_caches are DEVICE arrays of n_layers cache pointers (all
+ * layers share the geometry).  Replaces the per-layer loop of sampling/kvcache_model.py:390-396. */
+int sd_kv_select_layers(void* const* k_caches, void* const* v_caches, int n_layers, int B, int W, int H, int S, int D,
+                        int elem_size, int max_count, const int32_t* choice, const int32_t* start, int start_stride,
+                        const int32_t* count, const int32_t* active, int active_stride, void* stream);
 
 /* Token append of the multi-draft loop (sampling/speculative_sampling.py:1644, :1677): every row b*W + w of request b
  * becomes prefix + the winning draft's n_acc[b] accepted tokens + next_tok[b]; seq_len of all W rows advances by

@@ -24,13 +24,14 @@ SIGNATURES = {
     "sd_norm_sample": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp, i32, vp, vp]),
     "sd_norm_sample_verify": (i32, [vp, i32, i64, i64, i64, f32, i32, f32, vp, i64, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp]),
     "sd_verify_multi": (i32, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, vp, i64, vp, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp]),
-    "sd_verify_bild": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, vp, i32, f32, f32, vp, i32, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
+    "sd_verify_bild": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, vp, i32, f32, f32, vp, i32, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, i64, vp, vp]),
     "sd_sample": (i32, [vp, i64, i64, i64, vp, vp, vp, vp]),
     "sd_verify": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, vp, i32, i32, i64, i32,
                         vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
     "sd_max_fn": (i32, [vp, i64, i64, i64, vp, i64, vp]),
     "sd_kv_append": (i32, [vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "sd_kv_select": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]),
+    "sd_kv_select_layers": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp]),
     "sd_multi_commit": (i32, [vp, i64, vp, i32, i32, vp, vp, vp, vp, i32, vp]),
     "sd_build_step": (i32, [vp, i64, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]),
 }

@@ -29,7 +29,11 @@ class BiLDEngine(SpecDecEngine):
         super().__init__(approx_model, target_model, batch, max_total_len, gamma, temperature, top_k, top_p, device,
                          strict=False, use_cuda_graph=use_cuda_graph, max_iterations=max_iterations)
         self.fallback_thres, self.rollback_thres = float(fallback_thres), float(rollback_thres)
+        # compact lists of the q rows only (kernel 2's BiLD variant takes max q from them); the check itself reads dense p rows
+        self.use_q_compact = 0 < self.top_k <= 128
         self.use_compact = False
+        self.q_cmp = ops.CompactRows(batch * gamma, self.device) if self.use_q_compact else None
+        self._eos_id = -1
         self.n_drafted = torch.zeros(batch, dtype=torch.int32, device=self.device)
         self.drafted_hist = torch.zeros(self.max_iterations, batch, dtype=torch.int32, device=self.device)
 
@@ -43,7 +47,7 @@ class BiLDEngine(SpecDecEngine):
             else:
                 logits = self.draft.forward(self.tokens, self.seq_len, i - 1, 1, self.cur_tok)[:, 0]
             ops.norm_sample(logits, self.T, self.top_k, self.top_p, self.u_draft_t[i], probs_out=self.q_probs[:, i],
-                            tok_out=self.cur_tok, err=self.err)
+                            tok_out=self.cur_tok, err=self.err, compact=self.q_cmp.view(i, g) if self.use_q_compact else None)
             self.draft_tok[:, i].copy_(self.cur_tok)
         logits = self.target.forward(self.tokens, self.seq_len, -1, g + 1, self.cur_tok)
         ops.norm_probs(logits.reshape(B * (g + 1), V), self.T, self.top_k, self.top_p, out=self.p_probs.view(B * (g + 1), V),
@@ -51,7 +55,8 @@ class BiLDEngine(SpecDecEngine):
         # kernel 2, BiLD variant (engine mode): drafted length, check, the target's token, append, lengths
         ops.verify_bild(self.p_probs, self.draft_tok, self.rollback_thres, self.u_final, q_probs=self.q_probs,
                         fallback_thres=self.fallback_thres, n_drafted=self.n_drafted, tokens=self.tokens, seq_len=self.seq_len,
-                        limit=self.limit, active=self.active, n_accepted=self.n_acc, next_tok=self.next_tok, err=self.err)
+                        limit=self.limit, active=self.active, n_accepted=self.n_acc, next_tok=self.next_tok, err=self.err,
+                        q_compact=self.q_cmp.view() if self.use_q_compact else None, q_cmp_req_stride=g, eos_token_id=self._eos_id)
         it = self.it_dev
         idle = torch.full_like(self.n_acc, -1000)
         self.acc_hist.index_copy_(0, it, torch.where(self.active > 0, self.n_acc, idle).unsqueeze(0))
@@ -62,5 +67,10 @@ class BiLDEngine(SpecDecEngine):
         self.active.copy_(((self.seq_len < self.limit) & ~hit_eos & (self.active > 0)).to(torch.int32))
 
     def load_prompts(self, prompts, max_new_tokens, eos_token_id: Optional[int] = None) -> None:
+        eos = -1 if eos_token_id is None else int(eos_token_id)
+        if eos != self._eos_id:                                   # the EOS id is a launch argument: re-capture the graph
+            self._eos_id = eos
+            self._graph = None
+            self.graph_captured = False
         super().load_prompts(prompts, max_new_tokens, eos_token_id)
         self.acc_hist.fill_(-1000)

@@ -186,8 +186,8 @@ int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_str
                    int64_t q_req_stride, int64_t q_row_stride, const int64_t* draft_tok, int64_t draft_stride,
                    const int32_t* n_check, int max_check, float fallback_thres, float rollback_thres, const float* u_final,
                    int B, int64_t V, int32_t* n_accepted, int64_t* next_tok, float* nll, int32_t* n_drafted, int64_t* tokens,
-                   int64_t tokens_stride, int32_t* seq_len, const int32_t* limit, const int32_t* active, int* err_flag,
-                   void* stream) {
+                   int64_t tokens_stride, int32_t* seq_len, const int32_t* limit, const int32_t* active,
+                   const sd_compact_t* q_compact, int64_t q_cmp_req_stride, int64_t eos_token_id, int* err_flag, void* stream) {
   if (B == 0) return SD_OK;
   if (!p_probs || !draft_tok || !u_final || !n_accepted || !next_tok || !err_flag) return fail(SD_EINVAL, "sd_verify_bild: null argument");
   if (B < 0 || max_check < 1 || max_check > 32 || V <= 0 || V >= (1LL << 24)) return fail(SD_EINVAL, "sd_verify_bild: bad shape (1 <= max_check <= 32)");
@@ -199,8 +199,9 @@ int sd_verify_bild(const float* p_probs, int64_t p_req_stride, int64_t p_row_str
   p.u_final = u_final; p.B = B; p.gamma = max_check; p.V = V;
   p.n_accepted = n_accepted; p.next_tok = reinterpret_cast<long long*>(next_tok); p.ratios = nll; p.err_flag = err_flag;
   p.tokens = reinterpret_cast<long long*>(tokens); p.tokens_stride = tokens_stride; p.seq_len = seq_len; p.active = active;
+  p.qc = to_compact(q_compact); p.qc_req_stride = q_cmp_req_stride;
   return done("sd_verify_bild launch", sd::launch_verify_bild(p, n_check, fallback_thres, rollback_thres, limit, n_drafted,
-                                                              static_cast<cudaStream_t>(stream)));
+                                                              static_cast<long long>(eos_token_id), static_cast<cudaStream_t>(stream)));
 }
 
 int sd_max_fn(const float* x, int64_t rows, int64_t V, int64_t ld, float* out, int64_t ld_out, void* stream) {
@@ -227,6 +228,15 @@ int sd_kv_select(void* k_cache, void* v_cache, int B, int W, int H, int S, int D
   if (!k_cache || !v_cache || !choice || !start || !count) return fail(SD_EINVAL, "sd_kv_select: null argument");
   return done("sd_kv_select launch", sd::launch_kv_select(k_cache, v_cache, B, W, H, S, D, elem_size, max_count, choice, start,
                                                           start_stride, count, active, active_stride, static_cast<cudaStream_t>(stream)));
+}
+
+int sd_kv_select_layers(void* const* k_caches, void* const* v_caches, int n_layers, int B, int W, int H, int S, int D,
+                        int elem_size, int max_count, const int32_t* choice, const int32_t* start, int start_stride,
+                        const int32_t* count, const int32_t* active, int active_stride, void* stream) {
+  if (!k_caches || !v_caches || !choice || !start || !count) return fail(SD_EINVAL, "sd_kv_select_layers: null argument");
+  return done("sd_kv_select_layers launch",
+              sd::launch_kv_select_layers(k_caches, v_caches, n_layers, B, W, H, S, D, elem_size, max_count, choice, start,
+                                          start_stride, count, active, active_stride, static_cast<cudaStream_t>(stream)));
 }
 
 int sd_multi_commit(int64_t* tokens, int64_t tokens_stride, int32_t* seq_len, int B, int W, const int32_t* choice,

@@ -77,9 +77,13 @@ cudaError_t launch_kv_append(const void* k_new, const void* v_new, long long sb,
 // forward expands it to all rows again, :180-200).  On static caches with W rows per request: the kept positions
 // [start, start + count) of the winning row are copied over the other W - 1 rows (everything before `start` is the
 // shared prefix and identical already).  One warp per (request, draft != choice, head, position).
-__global__ void kv_select_kernel(unsigned char* __restrict__ kc, unsigned char* __restrict__ vc, int B, int W, int H, int S,
+// With layer tables (kcs / vcs != nullptr: device arrays of per-layer cache pointers) blockIdx.y is the layer: ONE launch
+// rolls back every layer of a model.
+__global__ void kv_select_kernel(unsigned char* __restrict__ kc, unsigned char* __restrict__ vc, unsigned char* const* __restrict__ kcs,
+                                 unsigned char* const* __restrict__ vcs, int B, int W, int H, int S,
                                  int row_bytes, int max_count, const int* __restrict__ choice, const int* __restrict__ start,
                                  int start_stride, const int* __restrict__ count, const int* __restrict__ active, int active_stride) {
+  if (kcs != nullptr) { kc = kcs[blockIdx.y]; vc = vcs[blockIdx.y]; }
   const int warps_per_block = blockDim.x >> 5;
   const long long r = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
   if (r >= static_cast<long long>(B) * W * H * max_count) return;
@@ -109,8 +113,23 @@ cudaError_t launch_kv_select(void* k_cache, void* v_cache, int B, int W, int H, 
   if (rows <= 0) return cudaSuccess;
   const int wpb = 8;
   kv_select_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-      static_cast<unsigned char*>(k_cache), static_cast<unsigned char*>(v_cache), B, W, H, S, row_bytes, max_count, choice,
-      start, start_stride, count, active, active_stride);
+      static_cast<unsigned char*>(k_cache), static_cast<unsigned char*>(v_cache), nullptr, nullptr, B, W, H, S, row_bytes, max_count,
+      choice, start, start_stride, count, active, active_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kv_select_layers(void* const* k_caches, void* const* v_caches, int n_layers, int B, int W, int H, int S, int D,
+                                    int elem_size, int max_count, const int* choice, const int* start, int start_stride,
+                                    const int* count, const int* active, int active_stride, cudaStream_t st) {
+  const int row_bytes = D * elem_size;
+  if (row_bytes % 16 != 0 || max_count < 1 || n_layers < 1 || n_layers > 65535) return cudaErrorInvalidValue;
+  const long long rows = static_cast<long long>(B) * W * H * max_count;
+  if (rows <= 0) return cudaSuccess;
+  const int wpb = 8;
+  dim3 grid(static_cast<unsigned>((rows + wpb - 1) / wpb), static_cast<unsigned>(n_layers));
+  kv_select_kernel<<<grid, wpb * 32, 0, st>>>(nullptr, nullptr, reinterpret_cast<unsigned char* const*>(k_caches),
+                                              reinterpret_cast<unsigned char* const*>(v_caches), B, W, H, S, row_bytes, max_count,
+                                              choice, start, start_stride, count, active, active_stride);
   return cudaGetLastError();
 }
 

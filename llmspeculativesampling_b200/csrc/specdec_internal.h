@@ -71,7 +71,7 @@ cudaError_t launch_norm_pipe(const NormParams& p, int dtype, int rows, cudaStrea
 
 cudaError_t launch_verify(const VerifyParams& p, cudaStream_t st);
 cudaError_t launch_verify_bild(const VerifyParams& v, const int* n_check, float fallback_thres, float rollback_thres,
-                               const int* limit, int* n_drafted, cudaStream_t st);
+                               const int* limit, int* n_drafted, long long eos, cudaStream_t st);
 cudaError_t launch_verify_multi(const VerifyParams& v, long long p_draft_stride, long long q_draft_stride,
                                 long long draft_draft_stride, int width, int* choice, cudaStream_t st);
 void set_verify_tuning(int cluster);
@@ -84,6 +84,9 @@ cudaError_t launch_kv_append(const void* k_new, const void* v_new, long long sb,
 cudaError_t launch_kv_select(void* k_cache, void* v_cache, int B, int W, int H, int S, int D, int elem_size, int max_count,
                              const int* choice, const int* start, int start_stride, const int* count, const int* active,
                              int active_stride, cudaStream_t st);
+cudaError_t launch_kv_select_layers(void* const* k_caches, void* const* v_caches, int n_layers, int B, int W, int H, int S, int D,
+                                    int elem_size, int max_count, const int* choice, const int* start, int start_stride,
+                                    const int* count, const int* active, int active_stride, cudaStream_t st);
 cudaError_t launch_multi_commit(long long* tokens, long long tokens_stride, int* seq_len, int B, int W, const int* choice,
                                 const int* n_acc, const long long* next_tok, const int* active, int S, cudaStream_t st);
 cudaError_t launch_build_step(long long* tokens, long long tokens_stride, const int* seq_len, int offset, int q,

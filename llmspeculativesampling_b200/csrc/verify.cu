@@ -10,6 +10,7 @@
 #include "rowops.cuh"
 #include "specdec_internal.h"
 #include "verify_sparse.cuh"
+#include "verify_row.cuh"
 
 namespace sd {
 
@@ -163,6 +164,76 @@ __global__ void __launch_bounds__(THREADS, MINB) verify_kernel(const VerifyParam
     }
   }
   if (C > 1) cx.cluster.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense verify, one CTA per request, row staged in shared memory (verify_row.cuh) — used whenever a row of V fp32
+// probabilities fits one CTA (V <= ~57k); larger vocabularies use the cluster kernel above.
+__global__ void __launch_bounds__(kRowThreads, 1) verify_row_kernel(const VerifyParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int V = static_cast<int>(p.V), gamma = p.gamma;
+  float* row = reinterpret_cast<float*>(smem_raw);
+  RowSampleShared& sh = *reinterpret_cast<RowSampleShared*>(smem_raw + ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)));
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (p.active != nullptr && p.active[b] == 0) return;
+  const bool has_q = p.q != nullptr;
+  // ---- accept scan: lane i tests drafted token i (speculative_sampling.py:1975-1990)
+  if (warp == 0) {
+    int n_acc = 0;
+    if (has_q) {
+      bool acc = true, tie = false;
+      if (lane < gamma) {
+        long long tok = p.draft[b * p.draft_stride + lane];
+        if (tok < 0 || tok >= V) { atomicOr(p.err_flag, kErrBadToken); tok = 0; }
+        const float pv = p.p[b * p.p_req_stride + lane * p.p_row_stride + tok];
+        const float qv = p.q[b * p.q_req_stride + lane * p.q_row_stride + tok];
+        if (qv == 0.f) atomicOr(p.err_flag, kErrZeroQ);
+        const float ratio = __fdiv_rn(pv, qv);
+        const float u = p.u_acc[b * p.u_acc_stride + lane];
+        const float thr = p.strict ? fminf(1.0f, ratio) : ratio;
+        acc = p.strict ? (u < thr) : !(u > thr);
+        tie = (u == thr);
+        if (p.ratios != nullptr) p.ratios[b * gamma + lane] = ratio;
+      }
+      const unsigned rej = __ballot_sync(0xffffffffu, !acc);
+      n_acc = rej ? (__ffs(rej) - 1) : gamma;
+      if (p.tie_count != nullptr && tie && lane < gamma && lane <= n_acc) atomicAdd(p.tie_count, 1);
+    }
+    if (lane == 0) sh.n_acc = n_acc;
+  }
+  __syncthreads();
+  const int n_acc = sh.n_acc;
+  const bool use_q = has_q && n_acc < gamma;
+  const float* prow = p.p + b * p.p_req_stride + (has_q ? n_acc : 0) * p.p_row_stride;
+  const float* qrow = use_q ? p.q + b * p.q_req_stride + n_acc * p.q_row_stride : nullptr;
+  const long long tok = row_residual_sample(prow, qrow, V, p.u_final[b], !p.strict, row, sh, p.err_flag);
+  if (tok == -2) {
+    if (tid == 0) { p.next_tok[b] = 0; if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc; }
+  } else if (tok >= 0) {
+    verify_commit(p, b, n_acc, tok);
+  }
+}
+
+// Static shared memory of the row kernels (scratch + a few words) comes out of the same per-block budget as the staged row.
+constexpr int kRowStaticReserve = 4096;
+static bool row_kernel_fits(long long V) {
+  return row_sample_smem(V) + kRowStaticReserve <= static_cast<size_t>(device_max_smem_optin());
+}
+
+template <class K>
+static cudaError_t set_row_smem(K kern, bool* flags) {
+  int dev_id = 0;
+  (void)cudaGetDevice(&dev_id);
+  if (!flags[dev_id & 63]) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    if (fa.sharedSizeBytes > static_cast<size_t>(kRowStaticReserve)) return cudaErrorInvalidValue;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, device_max_smem_optin() - kRowStaticReserve);
+    if (e != cudaSuccess) return e;
+    flags[dev_id & 63] = true;
+  }
+  return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -349,7 +420,11 @@ struct VerifyMultiParams {
   int* choice;
 };
 
-__global__ void __launch_bounds__(kMultiThreads) verify_multi_kernel(const VerifyMultiParams mp) {
+// ROW: the winning draft's residual row is staged in shared memory (verify_row.cuh, kRowThreads threads); otherwise the
+// CTA scans it straight from global memory (vocabularies too large for one CTA's shared memory)
+template <bool ROW>
+__global__ void __launch_bounds__(ROW ? kRowThreads : kMultiThreads) verify_multi_kernel(const VerifyMultiParams mp) {
+  constexpr int THREADS = ROW ? kRowThreads : kMultiThreads;
   __shared__ RowScratch<kMultiThreads> rs;
   __shared__ int s_choice, s_n_acc;
   const VerifyParams& p = mp.v;
@@ -357,7 +432,7 @@ __global__ void __launch_bounds__(kMultiThreads) verify_multi_kernel(const Verif
   const int V = static_cast<int>(p.V), gamma = p.gamma, W = mp.width;
   if (p.active != nullptr && p.active[b] == 0) return;
   if (p.ratios != nullptr) {                                               // statistics: p/q of EVERY drafted token (:1600-1609)
-    for (int idx = tid; idx < W * gamma; idx += kMultiThreads) {
+    for (int idx = tid; idx < W * gamma; idx += THREADS) {
       const int w = idx / gamma, i = idx - w * gamma;
       long long tok = p.draft[b * p.draft_stride + w * mp.draft_draft_stride + i];
       if (tok < 0 || tok >= V) tok = 0;
@@ -395,14 +470,33 @@ __global__ void __launch_bounds__(kMultiThreads) verify_multi_kernel(const Verif
   vp.p = p.p + s_choice * mp.p_draft_stride;
   vp.q = p.q + s_choice * mp.q_draft_stride;
   vp.strict = 0;
-  dense_verify_cta<kMultiThreads>(vp, b, s_n_acc, &rs);
+  if constexpr (ROW) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* row = reinterpret_cast<float*>(smem_raw);
+    RowSampleShared& sh = *reinterpret_cast<RowSampleShared*>(smem_raw + ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)));
+    const int n_acc = s_n_acc;
+    const float* prow = vp.p + b * vp.p_req_stride + n_acc * vp.p_row_stride;
+    const float* qrow = n_acc < gamma ? vp.q + b * vp.q_req_stride + n_acc * vp.q_row_stride : nullptr;
+    const long long tok = row_residual_sample(prow, qrow, V, vp.u_final[b], true, row, sh, vp.err_flag);
+    if (tok == -2) { if (tid == 0) { vp.next_tok[b] = 0; if (vp.n_accepted != nullptr) vp.n_accepted[b] = n_acc; } }
+    else if (tok >= 0) verify_commit(vp, b, n_acc, tok);
+  } else {
+    dense_verify_cta<kMultiThreads>(vp, b, s_n_acc, &rs);
+  }
 }
 
 cudaError_t launch_verify_multi(const VerifyParams& v, long long p_draft_stride, long long q_draft_stride,
                                 long long draft_draft_stride, int width, int* choice, cudaStream_t st) {
   if (v.gamma < 1 || v.gamma > 32 || width < 1) return cudaErrorInvalidValue;
   VerifyMultiParams mp = {v, p_draft_stride, q_draft_stride, draft_draft_stride, width, choice};
-  verify_multi_kernel<<<static_cast<unsigned>(v.B), kMultiThreads, 0, st>>>(mp);
+  if (row_kernel_fits(v.V)) {
+    static bool attr_dev[64] = {};
+    cudaError_t e = set_row_smem(verify_multi_kernel<true>, attr_dev);
+    if (e != cudaSuccess) return e;
+    verify_multi_kernel<true><<<static_cast<unsigned>(v.B), kRowThreads, row_sample_smem(v.V), st>>>(mp);
+  } else {
+    verify_multi_kernel<false><<<static_cast<unsigned>(v.B), kMultiThreads, 0, st>>>(mp);
+  }
   return cudaGetLastError();
 }
 
@@ -410,9 +504,11 @@ cudaError_t launch_verify_multi(const VerifyParams& v, long long p_draft_stride,
 // BiLD check (reference BiLD_sampling, speculative_sampling.py:1793-1813): the target keeps unchecked draft tokens while
 // -log p[token] <= rollback_thres, then ALWAYS samples its own next token from its distribution at the first
 // position it did not keep (plain sample of a p row — there is no residual in BiLD).
-__global__ void __launch_bounds__(kMultiThreads) verify_bild_kernel(const VerifyParams p, const int* n_check, const float fallback_thres,
-                                                                    const float rollback_thres, const int* limit, int* n_drafted) {
-  __shared__ RowScratch<kMultiThreads> rs;
+template <bool ROW>
+__global__ void __launch_bounds__(ROW ? kRowThreads : kMultiThreads) verify_bild_kernel(const VerifyParams p, const int* n_check, const float fallback_thres,
+                                                                                         const float rollback_thres, const int* limit, int* n_drafted, const long long eos) {
+  constexpr int THREADS = ROW ? kRowThreads : kMultiThreads;
+  __shared__ RowScratch<THREADS> rs;
   __shared__ int s_n;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int V = static_cast<int>(p.V);
@@ -421,17 +517,46 @@ __global__ void __launch_bounds__(kMultiThreads) verify_bild_kernel(const Verify
   if (p.q != nullptr) {
     // engine mode: gamma tokens were drafted up front; the reference would have stopped drafting at the first token whose
     // distribution was unsure (max q < fallback_thres, speculative_sampling.py:1784) — tokens after it do not exist for it
-    RowCtx<kMultiThreads> cx(&rs, 1);
+    RowCtx<THREADS> cx(&rs, 1);
     nc = p.gamma;
     for (int i = 0; i < p.gamma; ++i) {
       const float* qrow = p.q + b * p.q_req_stride + i * p.q_row_stride;
       float m = 0.f;
-      for (int j = tid; j < V; j += kMultiThreads) m = fmaxf(m, qrow[j]);
+      const int qcnt = p.qc.cnt != nullptr ? p.qc.cnt[(b * p.qc_req_stride + i) * p.qc.row_stride] : -1;
+      if (qcnt > 0 && qcnt <= p.qc.cap) {
+        // kernel 1 left the row's non-zeros in its compact list: the maximum of <= cap values instead of a scan of V
+        const long long cr = (b * p.qc_req_stride + i) * p.qc.row_stride * p.qc.cap;
+        for (int j = tid; j < qcnt; j += THREADS) m = fmaxf(m, p.qc.val[cr + j]);
+      } else if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(qrow) & 15) == 0) {
+        for (int j = tid; j < (V >> 2); j += THREADS) {
+          const uint4 qv = ld_nc_v4(reinterpret_cast<const uint4*>(qrow) + j);
+          m = fmaxf(fmaxf(m, fmaxf(__uint_as_float(qv.x), __uint_as_float(qv.y))), fmaxf(__uint_as_float(qv.z), __uint_as_float(qv.w)));
+        }
+      } else {
+        for (int j = tid; j < V; j += THREADS) m = fmaxf(m, qrow[j]);
+      }
       m = cx.allreduce_max(m);
       if (m < fallback_thres) { nc = i + 1; break; }                       // block-uniform
     }
   }
   if (n_drafted != nullptr && tid == 0) n_drafted[b] = nc;
+  if (eos >= 0 && p.q != nullptr && p.seq_len != nullptr) {
+    // the reference tests for EOS after EVERY draft token (speculative_sampling.py:1826-1841): an EOS drafted before the
+    // token that triggers the check ends generation right there, with the drafted tokens kept unchecked
+    int first = nc;
+    for (int i = 0; i < nc - 1; ++i)
+      if (p.draft[b * p.draft_stride + i] == eos) { first = i; break; }
+    if (first < nc - 1) {
+      const int keep = limit != nullptr ? min(first + 1, max(limit[b] - p.seq_len[b], 0)) : first + 1;
+      if (tid == 0) {
+        p.n_accepted[b] = -1 - keep;
+        p.next_tok[b] = -1;
+        p.seq_len[b] += keep;
+        if (n_drafted != nullptr) n_drafted[b] = keep;
+      }
+      return;
+    }
+  }
   if (limit != nullptr && p.seq_len != nullptr) {
     // the reference tests its length limit before every draft token (:1764): with fewer than nc tokens of room it leaves
     // the loop with the drafted tokens unchecked and no target token
@@ -464,13 +589,30 @@ __global__ void __launch_bounds__(kMultiThreads) verify_bild_kernel(const Verify
   vp.gamma = 0;                                                            // never a residual: plain sample of p row n
   vp.strict = 0;
   vp.q = nullptr;
-  dense_verify_cta<kMultiThreads>(vp, b, s_n, &rs);
+  if constexpr (ROW) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* row = reinterpret_cast<float*>(smem_raw);
+    RowSampleShared& sh = *reinterpret_cast<RowSampleShared*>(smem_raw + ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)));
+    const int n = s_n;
+    const long long tok = row_residual_sample(vp.p + b * vp.p_req_stride + n * vp.p_row_stride, nullptr, V, vp.u_final[b], false, row, sh, vp.err_flag);
+    if (tok == -2) { if (tid == 0) { vp.next_tok[b] = 0; if (vp.n_accepted != nullptr) vp.n_accepted[b] = n; } }
+    else if (tok >= 0) verify_commit(vp, b, n, tok);
+  } else {
+    dense_verify_cta<kMultiThreads>(vp, b, s_n, &rs);
+  }
 }
 
 cudaError_t launch_verify_bild(const VerifyParams& v, const int* n_check, float fallback_thres, float rollback_thres,
-                               const int* limit, int* n_drafted, cudaStream_t st) {
+                               const int* limit, int* n_drafted, long long eos, cudaStream_t st) {
   if (v.gamma < 1 || v.gamma > 32) return cudaErrorInvalidValue;
-  verify_bild_kernel<<<static_cast<unsigned>(v.B), kMultiThreads, 0, st>>>(v, n_check, fallback_thres, rollback_thres, limit, n_drafted);
+  if (row_kernel_fits(v.V)) {
+    static bool attr_dev[64] = {};
+    cudaError_t e = set_row_smem(verify_bild_kernel<true>, attr_dev);
+    if (e != cudaSuccess) return e;
+    verify_bild_kernel<true><<<static_cast<unsigned>(v.B), kRowThreads, row_sample_smem(v.V), st>>>(v, n_check, fallback_thres, rollback_thres, limit, n_drafted, eos);
+  } else {
+    verify_bild_kernel<false><<<static_cast<unsigned>(v.B), kMultiThreads, 0, st>>>(v, n_check, fallback_thres, rollback_thres, limit, n_drafted, eos);
+  }
   return cudaGetLastError();
 }
 
@@ -491,6 +633,13 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
     sat[0].val.programmaticStreamSerializationAllowed = 1;
     scfg.attrs = sat; scfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&scfg, verify_sparse_kernel, p);
+  }
+  if (g_verify_cluster == 0 && row_kernel_fits(p.V)) {                     // one CTA per request, row staged in shared memory
+    static bool attr_dev[64] = {};
+    cudaError_t e = set_row_smem(verify_row_kernel, attr_dev);
+    if (e != cudaSuccess) return e;
+    verify_row_kernel<<<static_cast<unsigned>(p.B), kRowThreads, row_sample_smem(p.V), st>>>(p);
+    return cudaGetLastError();
   }
   const long long row_bytes = p.V * 4;
   int C = 1;

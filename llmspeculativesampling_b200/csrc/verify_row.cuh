@@ -1,0 +1,208 @@
+// Dense residual / resample step of kernel 2 for ONE request by ONE CTA, with the row staged in shared memory:
+//   p_n is brought in by 1-D TMA bulk copies (32 KB chunks, one mbarrier each), q_n is read from HBM exactly once
+//   straight into registers, the residual max(0, p_n - q_n) replaces p_n in place, and the two passes that follow
+//   (row maximum -> fixed-point scale; exact weight sums -> inverse-CDF position) never leave the SM.
+// Every warp owns one CONTIGUOUS range of the vocabulary, so the exact prefix sums of the sampler are a warp scan over
+// per-warp totals plus a walk of the owning warp's range; per-element weights are accumulated as two 20-bit limbs with
+// round-down float adds (no float -> u64 conversion per element, see norm_ring_kernel.cuh).
+//
+// Replaces /root/reference/sampling/speculative_sampling.py:2005-2023 (sample(max_fn(p - q)) with its fall-back to
+// sample(p), bonus sample) and sampling/utils.py:213-245; shared by sd_verify (dense path), sd_sample, sd_verify_multi
+// and sd_verify_bild whenever a row fits one CTA's shared memory (V <= ~57k fp32 probabilities).
+#pragma once
+
+#include "rowops.cuh"
+#include "specdec_internal.h"
+#include "verify_sparse.cuh"
+
+namespace sd {
+
+constexpr int kRowThreads = 512;
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kRowChunkBytes = 32768;
+constexpr int kRowMaxChunks = 8;
+
+struct alignas(16) RowSampleShared {
+  uint64_t bar[kRowMaxChunks];
+  unsigned long long wbest[kRowWarps];
+  unsigned long long wsum[kRowWarps];
+  int n_acc, aux;
+};
+
+// bytes of dynamic shared memory a CTA needs for a row of V probabilities
+static inline size_t row_sample_smem(long long V) {
+  return ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)) + sizeof(RowSampleShared);
+}
+
+// Samples request b's next token from max(0, prow - qrow) (qrow == nullptr: from prow), falling back to prow when the
+// residual is empty and `fallback` is set (reference :2009-2010).  All kRowThreads threads of the CTA must call it;
+// `row` is the CTA's staging area (>= V floats, 16-byte aligned), `sh` its scratch (barriers NOT yet initialised).
+// On success exactly one thread gets a token >= 0 back (with the guard value for the < 1e-9 rule applied); the others -1.
+// Returns -2 in every thread when there is nothing to sample from (err_flag is set).
+__device__ __forceinline__ long long row_residual_sample(const float* __restrict__ prow, const float* __restrict__ qrow, int V,
+                                                         float u_final, bool fallback, float* row, RowSampleShared& sh,
+                                                         int* err_flag) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_vec = (V + 3) >> 2;
+  const bool vec_ok = (V & 3) == 0 && (reinterpret_cast<uintptr_t>(prow) & 15) == 0 &&
+                      (qrow == nullptr || (reinterpret_cast<uintptr_t>(qrow) & 15) == 0);
+  const uint32_t row_bytes = static_cast<uint32_t>(V) * 4u;
+  const int n_chunks = vec_ok ? static_cast<int>((row_bytes + kRowChunkBytes - 1) / kRowChunkBytes) : 0;
+  // warp w owns vectors [w * vpw, (w + 1) * vpw), lanes strided inside
+  const int vpw = (n_vec + kRowWarps - 1) / kRowWarps;
+  const int v_begin = warp * vpw, v_end = min(n_vec, v_begin + vpw);
+  float4* row4 = reinterpret_cast<float4*>(row);
+
+  if (vec_ok) {
+    if (tid == 0) {
+      for (int c = 0; c < n_chunks; ++c) mbar_init(&sh.bar[c], 1);
+      fence_barrier_init();
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t off = static_cast<uint32_t>(c) * kRowChunkBytes;
+        const uint32_t bytes = min(static_cast<uint32_t>(kRowChunkBytes), row_bytes - off);
+        mbar_expect_tx(&sh.bar[c], bytes);
+        tma_load_1d(reinterpret_cast<unsigned char*>(row) + off, reinterpret_cast<const unsigned char*>(prow) + off, bytes, &sh.bar[c]);
+      }
+    }
+    __syncthreads();                                            // barriers initialised before anyone waits on them
+  } else {
+    for (int i = tid; i < n_vec * 4; i += kRowThreads) row[i] = i < V ? prow[i] : 0.f;
+    __syncthreads();
+  }
+
+  bool use_q = qrow != nullptr;
+  unsigned long long best = 0ull;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // ---- pass 1: residual in place (own vectors only), row maximum as a packed (value key, ~index)
+    unsigned long long mine = 0ull;
+    bool bad = false;
+    constexpr int kAhead = 4;                                   // q vectors requested ahead of their use
+    uint4 qbuf[kAhead];
+    if (use_q && vec_ok) {
+#pragma unroll
+      for (int a = 0; a < kAhead; ++a) {
+        const int v = v_begin + lane + 32 * a;
+        qbuf[a] = v < v_end ? ld_nc_v4(reinterpret_cast<const uint4*>(qrow) + v) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    for (int v0 = v_begin; v0 < v_end; v0 += 32 * kAhead) {
+#pragma unroll
+      for (int a = 0; a < kAhead; ++a) {
+        const int v = v0 + 32 * a + lane;
+        uint4 qv = make_uint4(0u, 0u, 0u, 0u);
+        if (use_q && vec_ok) {
+          qv = qbuf[a];
+          const int vn = v + 32 * kAhead;
+          qbuf[a] = vn < v_end ? ld_nc_v4(reinterpret_cast<const uint4*>(qrow) + vn) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (v < v_end) {
+          if (attempt == 0 && vec_ok) mbar_wait(&sh.bar[(v * 16) / kRowChunkBytes], 0);
+          float4 a4 = row4[v];
+          float w[4] = {a4.x, a4.y, a4.z, a4.w};
+          if (use_q) {
+            float qq[4];
+            if (vec_ok) { qq[0] = __uint_as_float(qv.x); qq[1] = __uint_as_float(qv.y); qq[2] = __uint_as_float(qv.z); qq[3] = __uint_as_float(qv.w); }
+            else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) qq[j] = v * 4 + j < V ? qrow[v * 4 + j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = fmaxf(w[j] - qq[j], 0.f);           // utils.py:240
+            row4[v] = make_float4(w[0], w[1], w[2], w[3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            bad |= !(w[j] >= 0.f) || isinf(w[j]);
+            const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(v * 4 + j));
+            mine = (w[j] > 0.f && pk > mine) ? pk : mine;
+          }
+        }
+      }
+    }
+    if (bad) atomicOr(err_flag, kErrEmptyRow);                  // negative / NaN / inf weights: 'prob error'
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, mine, o); mine = t > mine ? t : mine; }
+    __syncthreads();                                            // (wbest of a previous attempt has been read by everyone)
+    if (lane == 0) sh.wbest[warp] = mine;
+    __syncthreads();
+    best = lane < kRowWarps ? sh.wbest[lane] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
+    if (best != 0ull || !use_q || !fallback) break;
+    // empty residual: resample from p_n itself (reference :2009-2010) — bring the row back (rare: plain loads)
+    use_q = false;
+    __syncthreads();
+    for (int i = tid; i < n_vec * 4; i += kRowThreads) row[i] = i < V ? prow[i] : 0.f;
+    __syncthreads();
+  }
+  if (best == 0ull) {
+    if (tid == 0) atomicOr(err_flag, kErrEmptyRow);
+    return -2;
+  }
+  const float rmax = key2f(static_cast<uint32_t>(best >> 32));
+  const int argmax = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffu));
+  const int e = frexp_exp(rmax);
+
+  // ---- pass 2: exact weight sum of this warp's range, w = floor(r * 2^(40 - e)) as two 20-bit limbs
+  const float scale = ldexpf(1.0f, kScaleBits - e);
+  const float scale_hi = scale * 9.5367431640625e-07f;          // 2^-20 * scale (exact)
+  uint32_t acc_hi = 0u, acc_lo = 0u;
+  unsigned long long carry = 0ull;                              // limb sums are folded every 2048 vectors (no 32-bit overflow)
+  int since = 0;
+  for (int v = v_begin + lane; v < v_end; v += 32) {
+    const float4 a4 = row4[v];
+    const float w[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t1f = __fmaf_rd(w[j], scale_hi, 8388608.0f);                // 2^23 + floor(W / 2^20), W = w * scale < 2^40
+      const float hf = t1f - 8388608.0f;
+      const float lo = fmaf(hf, -1048576.0f, w[j] * scale);                   // W - 2^20 * floor(W / 2^20)  in [0, 2^20)
+      const float t2f = __fadd_rd(lo, 8388608.0f);                            // 2^23 + floor(lo)
+      acc_hi += __float_as_uint(t1f) - 0x4B000000u;
+      acc_lo += __float_as_uint(t2f) - 0x4B000000u;
+    }
+    if (++since == 512) { carry += (static_cast<unsigned long long>(acc_hi) << 20) + acc_lo; acc_hi = acc_lo = 0u; since = 0; }
+  }
+  unsigned long long wsum = carry + (static_cast<unsigned long long>(acc_hi) << 20) + acc_lo;
+  wsum = warp_sum(wsum);
+  if (lane == 0) sh.wsum[warp] = wsum;
+  __syncthreads();
+  const unsigned long long mine_w = lane < kRowWarps ? sh.wsum[lane] : 0ull;
+  const unsigned long long incl = warp_scan_incl(mine_w, lane);
+  const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0ull) {
+    if (tid == 0) atomicOr(err_flag, kErrEmptyRow);
+    return -2;
+  }
+  const unsigned long long target = scale_target(total, u_to_int(u_final));
+  const unsigned ball = __ballot_sync(0xffffffffu, incl > target);
+  const int owner = __ffs(ball) - 1;                            // first warp whose range crosses the target
+  if (warp != owner) return -1;
+  unsigned long long run = __shfl_sync(0xffffffffu, incl - mine_w, owner);
+  // the owning warp walks its range, 32 vectors per step, in vocabulary order
+  for (int v0 = v_begin; v0 < v_end; v0 += 32) {
+    const int v = v0 + lane;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned long long wv[4], vs = 0ull;
+    if (v < v_end) { const float4 a4 = row4[v]; w[0] = a4.x; w[1] = a4.y; w[2] = a4.z; w[3] = a4.w; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { wv[j] = weight_of(w[j], e); vs += wv[j]; }
+    const unsigned long long inc2 = warp_scan_incl(vs, lane) + run;
+    const unsigned b2 = __ballot_sync(0xffffffffu, inc2 > target);
+    if (b2) {
+      if (lane != __ffs(b2) - 1) return -1;
+      unsigned long long c = inc2 - vs;
+      long long found = -1;
+      float psel = 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { c += wv[j]; if (found < 0 && c > target) { found = v * 4 + j; psel = w[j]; } }
+      float guard_val = psel;
+      if (use_q) guard_val = __fdiv_rn(psel, ldexpf(__ull2float_rn(total), e - kScaleBits) + 1e-6f);   // sample(max_fn(p - q)) sees the normalised value
+      return guard_val < kProbGuard ? argmax : found;
+    }
+    run = __shfl_sync(0xffffffffu, inc2, 31);
+  }
+  return -1;
+}
+
+}  // namespace sd

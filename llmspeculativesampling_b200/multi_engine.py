@@ -33,6 +33,7 @@ class MultiDraftEngine(SpecDecEngine):
                          strict=True, use_cuda_graph=use_cuda_graph, max_iterations=max_iterations)
         g, W, dev = gamma, self.W, self.device
         self.use_compact = False                                  # the multi-draft verify reads the dense rows
+        self._layer_tables = [ops.LayerTable(st.cache.k, st.cache.v) for st in (self.draft, self.target)]
         self.u_m = torch.zeros(batch, multi_block(g, W), dtype=torch.float32, device=dev)
         self.u_final_m = torch.zeros(batch, dtype=torch.float32, device=dev)
         self.choice = torch.zeros(batch, dtype=torch.int32, device=dev)
@@ -73,9 +74,9 @@ class MultiDraftEngine(SpecDecEngine):
                                       ratios=self.ratios_m, err=self.err)
         self.choice.copy_(ch); self.n_acc_m.copy_(na); self.next_tok_m.copy_(nt)
         # rollback(end_pos, choice): the winner's kept KV positions [L, L + n_acc) over the other rows, both models
-        for st in (self.draft, self.target):
-            for k, v in zip(st.cache.k, st.cache.v):
-                ops.kv_select(k, v, W, self.choice, self.seq_len, W, self.n_acc_m, g, active=self.active, active_stride=W)
+        # (one launch per model over all of its layers: device tables of the cache pointers)
+        for tab in self._layer_tables:
+            ops.kv_select_layers(tab, W, self.choice, self.seq_len, W, self.n_acc_m, g, active=self.active, active_stride=W)
         ops.multi_commit(self.tokens, self.seq_len, W, self.choice, self.n_acc_m, self.next_tok_m, active=self.active)
         # statistics + termination, all on the device (rows of a request are identical after the commit)
         it = self.it_dev

@@ -289,7 +289,8 @@ def verify_bild(p_probs: torch.Tensor, draft_tok: torch.Tensor, rollback_thres: 
                 q_probs: Optional[torch.Tensor] = None, fallback_thres: float = 0.0, n_drafted: Optional[torch.Tensor] = None,
                 tokens: Optional[torch.Tensor] = None, seq_len: Optional[torch.Tensor] = None,
                 limit: Optional[torch.Tensor] = None, active: Optional[torch.Tensor] = None,
-                n_accepted: Optional[torch.Tensor] = None, next_tok: Optional[torch.Tensor] = None):
+                n_accepted: Optional[torch.Tensor] = None, next_tok: Optional[torch.Tensor] = None, q_compact=None,
+                q_cmp_req_stride: int = 0, eos_token_id: int = -1):
     """Kernel 2, BiLD variant (sd_verify_bild).  p_probs (B, C+1, V) fp32 target rows of the C unchecked draft tokens
     draft_tok (B, C) int64 (+ the row after them); keeps tokens while -log p[token] <= rollback_thres and samples the
     target's own token from the first row it did not keep.  Engine mode: q_probs (B, C, V) + fallback_thres derive the
@@ -314,7 +315,8 @@ def verify_bild(p_probs: torch.Tensor, draft_tok: torch.Tensor, rollback_thres: 
         q_probs.stride(0) if q_probs is not None else 0, q_probs.stride(1) if q_probs is not None else 0,
         draft_tok.data_ptr(), draft_tok.stride(0), _ptr(n_check), C, float(fallback_thres), float(rollback_thres),
         u_final.data_ptr(), B, V, n_accepted.data_ptr(), next_tok.data_ptr(), _ptr(nll), _ptr(n_drafted), _ptr(tokens),
-        tokens.stride(0) if tokens is not None else 0, _ptr(seq_len), _ptr(limit), _ptr(active), err.ptr(), _stream())
+        tokens.stride(0) if tokens is not None else 0, _ptr(seq_len), _ptr(limit), _ptr(active), _cref(q_compact),
+        int(q_cmp_req_stride), int(eos_token_id), err.ptr(), _stream())
     _cabi.check(rc, "sd_verify_bild")
     return n_accepted, next_tok
 
@@ -390,6 +392,29 @@ def kv_select(k_cache: torch.Tensor, v_cache: torch.Tensor, W: int, choice: torc
                                    int(max_count), choice.data_ptr(), start.data_ptr(), int(start_stride), count.data_ptr(),
                                    _ptr(active), int(active_stride), _stream())
     _cabi.check(rc, "sd_kv_select")
+
+
+class LayerTable:
+    """Device arrays of the per-layer K / V cache pointers of one model (for sd_kv_select_layers)."""
+
+    def __init__(self, k_caches, v_caches):
+        self.k, self.v = list(k_caches), list(v_caches)            # keep the tensors alive
+        dev = self.k[0].device
+        self.shape, self.elem_size = tuple(self.k[0].shape), self.k[0].element_size()
+        assert all(tuple(t.shape) == self.shape and t.is_contiguous() for t in self.k + self.v)
+        self.k_ptrs = torch.tensor([t.data_ptr() for t in self.k], dtype=torch.int64, device=dev)
+        self.v_ptrs = torch.tensor([t.data_ptr() for t in self.v], dtype=torch.int64, device=dev)
+
+
+def kv_select_layers(table: LayerTable, W: int, choice: torch.Tensor, start: torch.Tensor, start_stride: int, count: torch.Tensor,
+                     max_count: int, active: Optional[torch.Tensor] = None, active_stride: int = 1) -> None:
+    """kv_select for every layer of a model in ONE launch (sd_kv_select_layers)."""
+    R, H, S, D = table.shape
+    assert R % W == 0
+    rc = _cabi.load().sd_kv_select_layers(table.k_ptrs.data_ptr(), table.v_ptrs.data_ptr(), len(table.k), R // W, W, H, S, D,
+                                          table.elem_size, int(max_count), choice.data_ptr(), start.data_ptr(), int(start_stride),
+                                          count.data_ptr(), _ptr(active), int(active_stride), _stream())
+    _cabi.check(rc, "sd_kv_select_layers")
 
 
 def multi_commit(tokens: torch.Tensor, seq_len: torch.Tensor, W: int, choice: torch.Tensor, n_acc: torch.Tensor,

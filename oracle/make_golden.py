@@ -67,6 +67,30 @@ def write_bild():
         json.dump(runs, f)
 
 
+BILD_EOS_CASES = [   # V, top_k, top_p, T, gamma, max_len, seed, noise, fallback_thres, rollback_thres, eos
+    (48, 0, 0.0, 1.0, 4, 60, 71, 0.5, 0.02, 6.0, 5), (64, 20, 0.9, 1.0, 4, 60, 72, 0.5, 0.05, 5.0, 7), (40, 0, 0.0, 1.3, 6, 60, 73, 0.3, 0.02, 6.0, 3),
+    (56, 10, 0.0, 1.0, 3, 60, 74, 0.8, 0.05, 4.0, 9),
+]
+
+
+def write_bild_eos():
+    """bild_eos_runs.json: BiLD_sampling with an EOS id that the (small-vocabulary) draft emits now and then — the
+    reference tests for EOS after every draft token (speculative_sampling.py:1826-1841), also between two checks."""
+    runs = []
+    for (V, k, p, T, gamma, max_len, seed, noise, fb, rb, eos) in BILD_EOS_CASES:
+        d, t = replay_model.make_pair(V, seed=seed, noise=noise)
+        prefix = torch.randint(10, V, (1, 7), generator=torch.Generator().manual_seed(seed))
+        tp = tape.make_tape(seed, max_len + 1, gamma)
+        out, det = ref_loader.run_reference_bild(prefix, d, t, max_len, gamma, fb, rb, T, k, p, tape=tp, eos_token_id=eos)
+        runs.append(dict(V=V, top_k=k, top_p=p, temperature=T, gamma=gamma, max_len=max_len, seed=seed, noise=noise,
+                         fallback_thres=fb, rollback_thres=rb, eos=eos, prefix=prefix[0].tolist(), tokens=out[0].tolist(),
+                         acc_len=[int(a) for a in det["acc_len"]], target_call_times=int(det["target_call_times"]),
+                         approx_call_times=int(det["approx_call_times"])))
+        print("bild-eos", V, gamma, "generated", out.shape[1] - 7, "of", max_len, "checks", det["target_call_times"], "drafted", det["approx_call_times"])
+    with open(os.path.join(OUT, "bild_eos_runs.json"), "w") as f:
+        json.dump(runs, f)
+
+
 MULTI_CASES = [   # V, top_k, top_p, T, gamma, width, max_len, seed, noise
     (1000, 20, 0.9, 1.0, 4, 3, 32, 41, 0.5), (32000, 20, 0.9, 0.8, 4, 4, 24, 42, 0.5), (500, 0, 0.0, 1.0, 4, 4, 32, 43, 0.8),
     (777, 0, 0.9, 1.3, 3, 2, 32, 44, 0.3), (900, 5, 0.0, 0.7, 5, 3, 32, 45, 1.5), (1000, 20, 0.9, 1.0, 2, 8, 24, 46, 2.0),
@@ -147,7 +171,7 @@ def main():
     torch.set_num_threads(1)
     only = set(sys.argv[1:])
     if only:
-        for name, fn in (("v2", write_v2), ("ar", write_ar), ("bild", write_bild), ("multi", write_multi)):
+        for name, fn in (("v2", write_v2), ("ar", write_ar), ("bild", write_bild), ("multi", write_multi), ("bild_eos", write_bild_eos)):
             if name in only:
                 fn()
         return
@@ -188,6 +212,7 @@ def main():
     write_multi()
     write_v2()
     write_ar()
+    write_bild_eos()
     print("wrote", os.listdir(OUT))
 
 

@@ -363,3 +363,20 @@ def test_union_of_shards_equals_single_batch(cuda_lib):
             for r, o in zip(ids, outs):
                 got[r] = o
         assert all(torch.equal(a, b) for a, b in zip(whole, got)), f"world={world}"
+
+
+def test_bild_eos_inside_a_draft_matches_reference_golden_runs(cuda_lib):
+    """The reference tests for EOS after EVERY draft token (speculative_sampling.py:1826-1841): an EOS drafted between two
+    checks ends generation with the drafted tokens kept unchecked.  Golden runs of the unmodified reference on small
+    vocabularies (tests/golden/bild_eos_runs.json) vs the batched engine (sd_verify_bild's eos rule) and the host loop."""
+    from llmspeculativesampling_b200.sampling import BiLD_sampling
+    runs = json.load(open(os.path.join(GOLD, "bild_eos_runs.json")))
+    assert any(len(r["tokens"]) < len(r["prefix"]) + r["max_len"] for r in runs)
+    for r in runs:
+        d, t = _pair(r["V"], r["seed"], r["noise"])
+        prefix = torch.tensor([r["prefix"]], device="cuda")
+        tp = tape.make_tape(r["seed"], r["max_len"] + 1, r["gamma"])
+        for use_engine in (True, False):
+            out, det = BiLD_sampling(prefix, d, t, r["gamma"], r["eos"], None, r["fallback_thres"], r["rollback_thres"], r["max_len"],
+                                     r["temperature"], r["top_k"], r["top_p"], details=True, uniforms=tp, use_engine=use_engine)
+            assert out[0].tolist() == r["tokens"], f"V={r['V']} gamma={r['gamma']} eos={r['eos']} engine={use_engine}"

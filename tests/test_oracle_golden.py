@@ -88,6 +88,18 @@ def test_bild_restatement_matches_reference_runs():
         assert (det["target_call_times"], det["approx_call_times"]) == (r["target_call_times"], r["approx_call_times"])
 
 
+def test_bild_restatement_matches_reference_runs_with_eos_inside_a_draft():
+    runs = json.load(open(os.path.join(GOLD, "bild_eos_runs.json")))
+    torch.set_num_threads(1)
+    for r in runs:
+        d, t = replay_model.make_pair(r["V"], seed=r["seed"], noise=r["noise"])
+        tp = tape.make_tape(r["seed"], r["max_len"] + 1, r["gamma"])
+        out, det = spec_loop.bild_sampling(torch.tensor([r["prefix"]]), d, t, r["max_len"], r["gamma"], r["fallback_thres"],
+                                           r["rollback_thres"], r["temperature"], r["top_k"], r["top_p"], eos_token_id=r["eos"], tape=tp)
+        assert out[0].tolist() == r["tokens"], r
+        assert (det["target_call_times"], det["approx_call_times"]) == (r["target_call_times"], r["approx_call_times"])
+
+
 @pytest.mark.parametrize("residual", ["normalised", "raw"])
 def test_v2_restatement_matches_reference_runs(residual):
     """The reference's speculative_sampling_v2 (speculative_sampling.py:2080-2194: no KV cache, strict accept test,

@@ -249,10 +249,12 @@ def main():
     ap.add_argument("--T", type=float, default=0.8)
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--once", action="store_true", help="one eager launch per input set, no timing (for ncu)")
+    ap.add_argument("--verify-cluster", type=int, default=0, help="cluster size of the dense verify kernel (0 = heuristic)")
     a = ap.parse_args()
     global ONCE
     ONCE = a.once
     build.build()
+    ops.set_tuning(0, 0, a.verify_cluster)
     modes = {"verify_dense": lambda: bench_verify(a, False), "verify_sparse": lambda: bench_verify(a, True),
              "verify_multi": lambda: bench_verify_multi(a), "verify_bild": lambda: bench_verify_bild(a),
              "sample": lambda: bench_sample(a), "max_fn": lambda: bench_max_fn(a), "kv_append": lambda: bench_kv(a),
