@@ -54,6 +54,7 @@ __device__ __forceinline__ float float_down(float f, uint32_t ulps) {
 template <typename T> struct Elem;
 template <> struct Elem<float> {
   static constexpr int kPerVec = 4;   // elements per 16-byte vector
+  static constexpr uint32_t kNegInfWord = 0xff800000u;   // a 32-bit word of -inf elements
   __device__ static __forceinline__ void unpack(const uint4& v, float (&o)[4]) {
     o[0] = __uint_as_float(v.x); o[1] = __uint_as_float(v.y);
     o[2] = __uint_as_float(v.z); o[3] = __uint_as_float(v.w);
@@ -63,6 +64,7 @@ template <> struct Elem<float> {
 };
 template <> struct Elem<__nv_bfloat16> {
   static constexpr int kPerVec = 8;
+  static constexpr uint32_t kNegInfWord = 0xff80ff80u;
   __device__ static __forceinline__ void unpack(const uint4& v, float (&o)[8]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -76,6 +78,7 @@ template <> struct Elem<__nv_bfloat16> {
 };
 template <> struct Elem<__half> {
   static constexpr int kPerVec = 8;
+  static constexpr uint32_t kNegInfWord = 0xfc00fc00u;
   __device__ static __forceinline__ void unpack(const uint4& v, float (&o)[8]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -264,6 +267,42 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ----------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 — one issue slot for two fp32 lanes, every IEEE rounding mode)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 fma2_rd(f32x2 a, f32x2 b, f32x2 c) {        // round towards -inf
+  f32x2 d;
+  asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -64,6 +64,7 @@ bool plan_ring(NormParams& p, int dtype, int rows) {
   const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
   if (mode == kRingTopK && slice_bytes + sizeof(NormShared<kRingThreads>) > shared_off + offsetof(RingShared, n_fail)) return false;
   { const char* ev = getenv("SD_RING_EARLY"); p.ring_early = ev != nullptr ? atoi(ev) : 0; }
+  { const char* ev = getenv("SD_RING_TRIGGER"); p.ring_trigger = ev != nullptr ? atoi(ev) : 1; }
   p.ring_mode = mode;
   p.ring_slots = slots;
   p.ring_shared_off = static_cast<int>(shared_off);

@@ -41,7 +41,7 @@ constexpr int kRingMaxPieces = kRingMaxSlots * kRingComputeWarps;   // (chunk, w
 constexpr int kRingEndDone = -1, kRingEndPause = -2;
 constexpr uint32_t kRingTieUlps = 8;
 
-enum : int { kRingTopK = 0, kRingDense = 1 };
+enum : int { kRingTopK = 0, kRingDense = 1, kRingDenseT1 = 2 };   // (DenseT1: temperature == 1, no logit / T arithmetic compiled in)
 
 struct alignas(16) RingShared {
   uint64_t full[kRingMaxSlots];        // chunk landed                       (TMA -> compute warps)
@@ -110,11 +110,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
   const uint32_t row_bytes = static_cast<uint32_t>(n_vec) * 16u;
   const float temp = p.temperature;
   const float r_temp = 1.0f / temp;
-  const bool t1 = temp == 1.0f;
+  const bool t1 = MODE == kRingDenseT1 ? true : (MODE == kRingDense ? false : temp == 1.0f);
   const int k_eff = min(p.top_k, V);
   const bool want_probs = p.probs != nullptr;
   const int static_rows = static_cast<int>(gridDim.x);         // first item of CTA b is row b
   auto slot_ptr = [&](int slot) { return smem_raw + static_cast<size_t>(slot) * kRingChunkBytes; };
+  // debug timeline, per CTA (after the per-item area): globaltimer at entry / after the dependency wait / at exit, clock64 at entry
+  long long* prof_cta = p.prof != nullptr ? p.prof + (static_cast<long long>(gridDim.x) * 8 * 16 + static_cast<long long>(blockIdx.x) * 4) : nullptr;
+  if (prof_cta != nullptr && tid == 0) { prof_cta[0] = static_cast<long long>(globaltimer_ns()); prof_cta[3] = clock64(); }
 
   if constexpr (MODE == kRingTopK) {
     for (int i = tid; i < kRingChunkBytes / 16; i += kRingThreads) reinterpret_cast<uint4*>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -142,6 +145,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
     }
     __syncthreads();
     if (round == 0) pdl_wait();                                // everything above overlapped the previous kernel's tail
+    // Dependents may be scheduled from here on: the next kernel's CTAs take over every SM as soon as this kernel's CTA on it
+    // exits and run their own prologue (barrier init, zero chunk) up to their dependency wait, instead of being launched only
+    // after the LAST CTA of this kernel has finished (measured: ~2.5 us per launch boundary)
+    if (round == 0 && p.ring_trigger) pdl_launch_dependents();
+    if (round == 0 && prof_cta != nullptr && tid == 0) prof_cta[1] = static_cast<long long>(globaltimer_ns());
 
     if (warp == CW) {
       // =========================================================================== loader
@@ -422,6 +430,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
     } else {
       // =========================================================================== compute warps
       int slot0 = 0, wraps0 = 0;                                // ring position of the current row's first chunk
+      // DENSE: pass A of row it + 1 runs inside pass B of row it (see below); its per-thread results are carried over
+      float car_m = -INFINITY, car_nan = -INFINITY, car_u = -1.f;
+      f32x2 car_s2 = 0ull;
+      bool carried = false;
       for (int it = 0;; ++it) {
         mbar_wait(&sh.rowfull[it % kRingItemRing], static_cast<uint32_t>(it / kRingItemRing) & 1u);
         const int row = *reinterpret_cast<volatile int*>(&sh.row_of[it % kRingItemRing]);
@@ -636,43 +648,88 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
         } else {
           // =================================================================== DENSE (top_k = 0, top_p = 0)
           // thread -> vectors: warp w owns vectors c * 1024 + w * 64 + {lane, 32 + lane} of chunk c: one contiguous
-          // "piece" of 64 vectors per (chunk, warp), the unit of the sampler's exact prefix sums
+          // "piece" of 64 vectors per (chunk, warp), the unit of the sampler's exact prefix sums.  A thread handles its
+          // 2 * PV elements of a chunk TOGETHER (one maximum, one rescale, independent exponentials) and the arithmetic
+          // runs on packed fp32 pairs (FFMA2 / FADD2 / FMUL2): the two passes are issue- and latency-lean enough for the
+          // row period to be set by HBM, not by the SM.
+          constexpr int E = 2 * PV;                              // elements of one thread per chunk
           // logit / T, correctly rounded; -inf (a masked token) is clamped to a huge negative number first so that no
           // inf - inf can appear (its probability is exactly 0 either way)
+          const f32x2 rt2 = pack2(r_temp, r_temp), nt2 = pack2(-temp, -temp);
           auto xof = [&](float l) {
             l = fmaxf(l, -1.0e30f);
             const float q0 = l * r_temp;
             return fmaf(fmaf(-q0, temp, l), r_temp, q0);
           };
+          auto xof2 = [&](float a, float b) {                    // the same on a pair
+            const f32x2 l2 = pack2(fmaxf(a, -1.0e30f), fmaxf(b, -1.0e30f));
+            const f32x2 q0 = mul2(l2, rt2);
+            return fma2(fma2(q0, nt2, l2), rt2, q0);
+          };
+          const f32x2 l2e2 = pack2(kLog2e, kLog2e);
           const int vl0 = warp * 64 + lane;
-          // ---- pass A: per-thread online (max, sum of exp2) in the log2 domain, as the chunks land
-          float m_t = -INFINITY, s_t = 0.f, nan_acc = -INFINITY;
-          for (int c = 0; c < NCH; ++c) {
-            wait_chunk(c);
-            const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot_of(c)));
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int vl = vl0 + h * 32;
-              if (c * kRingVecPerChunk + vl < n_vec) {
-                float o[PV];
-                Elem<T>::unpack(s4[vl], o);
-                float vm = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < PV; ++j) {
-                  if (!t1) o[j] = xof(o[j]);
-                  asm("max.NaN.f32 %0, %0, %1;" : "+f"(vm) : "f"(o[j]));
-                }
-                asm("max.NaN.f32 %0, %0, %1;" : "+f"(nan_acc) : "f"(vm));
-                if (vm > m_t) { s_t *= ex2_ftz((m_t - vm) * kLog2e); m_t = vm; }   // (m_t = -inf: s_t is 0, stays 0; a NaN vm changes nothing)
-                const float mm = m_t == -INFINITY ? 0.f : m_t;
-                float a = 0.f;
-#pragma unroll
-                for (int j = 0; j < PV; ++j) a += ex2_ftz((o[j] - mm) * kLog2e);
-                s_t += a;
-              }
+          // ---- pass A: per-thread online (max, sum of exp2) in the log2 domain, one chunk of a row whose first chunk sits in
+          //      ring slot s0 (wrap count w0).  For the CTA's first row it runs on its own, as the chunks land; for every
+          //      later row it is interleaved, chunk by chunk, with pass B of the row before (below) — the SM then reads and
+          //      writes HBM at the same time instead of in alternating phases.
+          float m_t = -INFINITY, nan_acc = -INFINITY;
+          f32x2 s2 = pack2(0.f, 0.f);
+          auto pass_a = [&](int c, int s0, int w0) {
+            int sl = s0 + c;
+            const bool wrapped = sl >= NS;
+            if (wrapped) sl -= NS;
+            mbar_wait(&sh.full[sl], static_cast<uint32_t>(w0 + (wrapped ? 1 : 0)) & 1u);
+            const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(sl));
+            uint4 r0 = s4[vl0], r1 = s4[vl0 + 32];
+            if (c == NCH - 1) {                                  // the row's last chunk may be partial
+              constexpr uint32_t ninf = Elem<T>::kNegInfWord;
+              if (c * kRingVecPerChunk + vl0 >= n_vec) r0 = make_uint4(ninf, ninf, ninf, ninf);
+              if (c * kRingVecPerChunk + vl0 + 32 >= n_vec) r1 = make_uint4(ninf, ninf, ninf, ninf);
             }
+            // maximum of the raw logits (logit -> logit / T is monotone), NaN-propagating
+            float vm_raw = vec_max_nan<T>(vec_max_nan<T>(-INFINITY, r0), r1);
+            asm("max.NaN.f32 %0, %0, %1;" : "+f"(nan_acc) : "f"(vm_raw));
+            const float vm = t1 ? vm_raw : xof(vm_raw);
+            const float m_new = fmaxf(m_t, vm);                  // (a NaN leaves m_t as it is; the row is flagged below)
+            const float mm = m_new == -INFINITY ? 0.f : m_new;
+            // (x - mm first, then * log2(e): the difference is exact near the maximum whatever the magnitude of the logits — a
+            //  fused x * log2(e) - mm * log2(e) loses |mm| * 2^-24 in the exponent, fatal for the -1e30 clamp of masked tokens)
+            const float resc = ex2_ftz((m_t - mm) * kLog2e);     // m_t = -inf: 0 (and s2 is 0)
+            m_t = m_new;
+            const f32x2 nm2 = pack2(-mm, -mm);
+            float o[E];
+            {
+              float a[PV], b[PV];
+              Elem<T>::unpack(r0, a);
+              Elem<T>::unpack(r1, b);
+#pragma unroll
+              for (int j = 0; j < PV; ++j) { o[j] = a[j]; o[PV + j] = b[j]; }
+            }
+            f32x2 acc[E / 2];
+#pragma unroll
+            for (int j = 0; j < E; j += 2) {
+              const f32x2 x2 = t1 ? pack2(o[j], o[j + 1]) : xof2(o[j], o[j + 1]);
+              float a0, a1;
+              unpack2(mul2(add2(x2, nm2), l2e2), a0, a1);
+              acc[j / 2] = pack2(ex2_ftz(a0), ex2_ftz(a1));
+            }
+#pragma unroll
+            for (int w = E / 4; w >= 1; w >>= 1) {
+#pragma unroll
+              for (int j = 0; j < w; ++j) acc[j] = add2(acc[j], acc[j + w]);
+            }
+            s2 = fma2(s2, pack2(resc, resc), acc[0]);
+          };
+          float u_row;
+          if (carried) {                                         // scanned while the previous row was written out
+            m_t = car_m; nan_acc = car_nan; s2 = car_s2; u_row = car_u;
+          } else {
+            u_row = p.u != nullptr ? __ldg(p.u + row) : -1.f;    // (requested now, needed after pass A)
+            for (int c = 0; c < NCH; ++c) pass_a(c, slot0, wraps0);
           }
           if (nan_acc != nan_acc || nan_acc == INFINITY) atomicOr(p.err_flag, kErrNanLogit);
+          float s_t;
+          { float sa, sb; unpack2(s2, sa, sb); s_t = sa + sb; }
           RING_PROF(1);
           // ---- combine: warp, then CTA (every thread folds the 16 warp results itself: one barrier)
           {
@@ -682,71 +739,98 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
             if (lane == 0) { sh.wm[warp] = Mw; sh.ws[warp] = Sw; }
           }
           ring_named_bar(1, CT);
-          float M = -INFINITY;
-#pragma unroll
-          for (int w = 0; w < CW; ++w) M = fmaxf(M, sh.wm[w]);
-          double z = 0.0;
-#pragma unroll
-          for (int w = 0; w < CW; ++w) {
-            const float mw = sh.wm[w];
-            if (mw > -INFINITY) z += sh.ws[w] * static_cast<double>(ex2_ftz((mw - M) * kLog2e));
-          }
+          // (lane w of every warp folds warp w's pair; the warp-wide butterflies have the same order in all warps, so M and z
+          //  are bit-identical across the CTA)
+          const float mw = lane < CW ? sh.wm[lane] : -INFINITY;
+          const float M = warp_max(mw);
+          const double zw = (lane < CW && mw > -INFINITY) ? sh.ws[lane] * static_cast<double>(ex2_ftz((mw - M) * kLog2e)) : 0.0;
+          const double z = warp_sum(zw);
           const float logz = logf(static_cast<float>(z));
           if (!(z > 0.0) || isinf(logz) || logz != logz) { if (tid == 0) atomicOr(p.err_flag, kErrNanLogit); }   // (uniform condition)
           const float c2 = -logz * kLog2e;
-          const bool do_sample = p.u != nullptr && p.u[row] >= 0.f;        // row-uniform
+          const bool do_sample = u_row >= 0.f;                   // row-uniform
           const int par = it & 1;
           if (it >= 2) mbar_wait(&sh.tfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);   // sampler is done with item it - 2
           if (warp == 0) sh.info_c2[par] = c2;                   // (whole warp, same value: no single-lane branch in front of the warp reductions below)
           // sampler weights  w = floor(p * 2^(40 - e)),  e = frexp exponent of the row maximum exp2(c2)
           const float scale = ldexpf(1.0f, kScaleBits - frexp_exp(ex2_ftz(c2)));
           const float scale_hi = scale * 9.5367431640625e-07f;              // 2^-20 * scale (exact)
+          const f32x2 nM2 = pack2(-M, -M), c22 = pack2(c2, c2), sh2 = pack2(scale_hi, scale_hi);
+          const f32x2 k23 = pack2(8388608.0f, 8388608.0f), m1 = pack2(-1.0f, -1.0f), k20 = pack2(1048576.0f, 1048576.0f);
           RING_PROF(2);
+          // the row after this one (the loader published it while it issued this row's loads): its pass A is interleaved below
+          mbar_wait(&sh.rowfull[(it + 1) % kRingItemRing], static_cast<uint32_t>((it + 1) / kRingItemRing) & 1u);
+          const int next_row = *reinterpret_cast<volatile int*>(&sh.row_of[(it + 1) % kRingItemRing]);
+          int slot0n = slot0 + NCH, wraps0n = wraps0;
+          if (slot0n >= NS) { slot0n -= NS; ++wraps0n; }
+          m_t = -INFINITY; nan_acc = -INFINITY; s2 = pack2(0.f, 0.f);
+          if (next_row >= 0) car_u = p.u != nullptr ? __ldg(p.u + next_row) : -1.f;
           // ---- pass B: probabilities out (16-byte streaming stores), exact weight sums per piece, slots released
           for (int c = 0; c < NCH; ++c) {
             const int slot = slot_of(c);
             const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot));
+            const int v0 = c * kRingVecPerChunk + vl0;
+            bool ok0 = true, ok1 = true;
+            uint4 r0 = s4[vl0], r1 = s4[vl0 + 32];
+            if (c == NCH - 1) {                                  // the row's last chunk may be partial: -inf -> probability 0, weight 0
+              constexpr uint32_t ninf = Elem<T>::kNegInfWord;
+              ok0 = v0 < n_vec; ok1 = v0 + 32 < n_vec;
+              if (!ok0) r0 = make_uint4(ninf, ninf, ninf, ninf);
+              if (!ok1) r1 = make_uint4(ninf, ninf, ninf, ninf);
+            }
+            float o[E];
+            {
+              float a[PV], b[PV];
+              Elem<T>::unpack(r0, a);
+              Elem<T>::unpack(r1, b);
+#pragma unroll
+              for (int j = 0; j < PV; ++j) { o[j] = a[j]; o[PV + j] = b[j]; }
+            }
             uint32_t acc_hi = 0u, acc_lo = 0u;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int vl = vl0 + h * 32;
-              const int v = c * kRingVecPerChunk + vl;
-              if (v < n_vec) {
-                float o[PV];
-                Elem<T>::unpack(s4[vl], o);
+            for (int j = 0; j < E; j += 2) {
+              const f32x2 x2 = t1 ? pack2(o[j], o[j + 1]) : xof2(o[j], o[j + 1]);
+              float a0, a1;
+              unpack2(fma2(add2(x2, nM2), l2e2, c22), a0, a1);   // exp((x - M) - logZ), utils.py:199
+              o[j] = ex2_ftz(a0);
+              o[j + 1] = ex2_ftz(a1);
+              if (do_sample) {
+                // floor(W), W = p * scale < 2^40, as two 20-bit limbs.  A round-down add of 2^23 leaves floor() of the
+                // other operand in the low mantissa bits; every operation below is exact (kernel 1)
+                const f32x2 p2 = pack2(o[j], o[j + 1]);
+                const f32x2 t1f = fma2_rd(p2, sh2, k23);         // 2^23 + H,  H = floor(W / 2^20)
+                const f32x2 nh = fma2(t1f, m1, k23);             // -H
+                const f32x2 fr = fma2(p2, sh2, nh);              // W / 2^20 - H  in [0, 1)  (exact)
+                const f32x2 t2f = fma2_rd(fr, k20, k23);         // 2^23 + floor(W - 2^20 H)
+                float h0, h1, l0, l1;
+                unpack2(t1f, h0, h1);
+                unpack2(t2f, l0, l1);
+                acc_hi += __float_as_uint(h0) + __float_as_uint(h1);
+                acc_lo += __float_as_uint(l0) + __float_as_uint(l1);
+              }
+            }
+            if (want_probs) {
 #pragma unroll
-                for (int j = 0; j < PV; ++j) {
-                  const float x = t1 ? o[j] : xof(o[j]);
-                  o[j] = ex2_ftz(fmaf(x - M, kLog2e, c2));                  // exp((x - M) - logZ), utils.py:199
-                }
-                if (want_probs) {
-#pragma unroll
-                  for (int j = 0; j < PV; j += 4) st_cs_v4(orow + static_cast<long long>(v) * PV + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
-                }
-                if (do_sample) {
-#pragma unroll
-                  for (int j = 0; j < PV; ++j) {
-                    // floor(W), W = p * scale < 2^40, as two 20-bit limbs.  A round-down add of 2^23 leaves floor() of the
-                    // other operand in the low mantissa bits; every operation below is exact (kernel 1)
-                    const float t1f = __fmaf_rd(o[j], scale_hi, 8388608.0f);          // 2^23 + floor(W / 2^20)
-                    const float hf = t1f - 8388608.0f;
-                    const float lo = fmaf(hf, -1048576.0f, o[j] * scale);             // W - 2^20 * floor(W / 2^20)  in [0, 2^20)
-                    const float t2f = fadd_rd(lo, 8388608.0f);                         // 2^23 + floor(lo)
-                    acc_hi += __float_as_uint(t1f) - 0x4B000000u;
-                    acc_lo += __float_as_uint(t2f) - 0x4B000000u;
-                  }
-                }
+              for (int j = 0; j < PV; j += 4) {
+                if (ok0) st_cs_v4(orow + static_cast<long long>(v0) * PV + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+                if (ok1) st_cs_v4(orow + static_cast<long long>(v0 + 32) * PV + j, o[PV + j], o[PV + j + 1], o[PV + j + 2], o[PV + j + 3]);
               }
             }
             if (do_sample) {
+              // (every element added 2^23's bit pattern to both limb sums: E * 0x4B000000 per thread, modulo 2^32)
+              acc_hi -= static_cast<uint32_t>(E) * 0x4B000000u;
+              acc_lo -= static_cast<uint32_t>(E) * 0x4B000000u;
               const uint32_t hs = __reduce_add_sync(0xffffffffu, acc_hi), ls = __reduce_add_sync(0xffffffffu, acc_lo);
               if (lane == 0) sh.piece[par][c * CW + warp] = (static_cast<unsigned long long>(hs) << 20) + ls;
             }
             __syncwarp();
             if (lane == 0) ring_arrive(&sh.empty[slot]);
+            if (next_row >= 0) pass_a(c, slot0n, wraps0n);
           }
           __syncwarp();
           if (lane == 0) ring_arrive(&sh.row_done[par]);       // (release: this warp's stores and piece sums first)
+          carried = next_row >= 0;
+          car_m = m_t; car_nan = nan_acc; car_s2 = s2;
           RING_PROF(7);
           if (p.cmp.cnt != nullptr && tid == 0) p.cmp.cnt[static_cast<long long>(row) * p.cmp.row_stride] = -1;   // no compact list
         }
@@ -782,7 +866,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
     if (reason == kRingEndDone) break;
   }  // rounds
 
-  pdl_launch_dependents();
+  if (!p.ring_trigger) pdl_launch_dependents();
+  if (prof_cta != nullptr && tid == 0) prof_cta[2] = static_cast<long long>(globaltimer_ns());
   // the last CTA to finish re-arms the row counter for the next launch that uses this scheduler block
   if (tid == 0) {
     __threadfence();
@@ -822,7 +907,8 @@ static cudaError_t ring_launch(const NormParams& p, cudaStream_t st) {
 
 template <typename T>
 static cudaError_t ring_dispatch(const NormParams& p, cudaStream_t st) {
-  return p.ring_mode == kRingDense ? ring_launch<T, kRingDense>(p, st) : ring_launch<T, kRingTopK>(p, st);
+  if (p.ring_mode != kRingDense) return ring_launch<T, kRingTopK>(p, st);
+  return p.temperature == 1.0f ? ring_launch<T, kRingDenseT1>(p, st) : ring_launch<T, kRingDense>(p, st);
 }
 
 }  // namespace sd

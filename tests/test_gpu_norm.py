@@ -31,6 +31,13 @@ CASES = [  # V, rows, T, k, p, scale, dtype
     (262144, 2, 0.8, 20, 0.9, 3.8, torch.float32),
     (262144, 1, 1.0, 0, 0.0, 1.0, torch.float32),
     (151936, 2, 1.0, 50, 0.8, 3.0, torch.float32),
+    # dense rows (top_k = 0, top_p = 0) on the ring kernel: temperature != 1, 16-bit logits, rows shorter than one chunk
+    (32000, 3, 0.8, 0, 0.0, 3.8, torch.float32),
+    (32000, 5, 1.3, 0, 0.0, 2.0, torch.bfloat16),
+    (50272, 3, 0.7, 0, 0.0, 3.0, torch.bfloat16),
+    (48, 3, 1.0, 0, 0.0, 2.0, torch.float32),
+    (40, 1, 1.3, 0, 0.0, 2.0, torch.float32),
+    (4096, 300, 0.9, 0, 0.0, 3.0, torch.float32),      # more rows than SMs: several rows per persistent CTA
 ]
 
 
