@@ -76,7 +76,7 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
     // ---- pass 1: residual in place (own vectors only), row maximum as a packed (value key, ~index)
     unsigned long long mine = 0ull;
     bool bad = false;
-    constexpr int kAhead = 4;                                   // q vectors requested ahead of their use
+    constexpr int kAhead = 8;                                   // q vectors requested ahead of their use
     uint4 qbuf[kAhead];
     if (use_q && vec_ok) {
 #pragma unroll
@@ -143,28 +143,40 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
   const int argmax = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffu));
   const int e = frexp_exp(rmax);
 
-  // ---- pass 2: exact weight sum of this warp's range, w = floor(r * 2^(40 - e)) as two 20-bit limbs
+  // ---- pass 2: exact weight sums, w = floor(r * 2^(40 - e)) as two 20-bit limbs (packed fp32, round-down adds: no
+  //      float -> u64 conversion per element).  One "block" = the 32 vectors a warp reads in one step; lane k keeps the
+  //      sum of the warp's block k, so that the walk below is two warp scans instead of one per block.
   const float scale = ldexpf(1.0f, kScaleBits - e);
   const float scale_hi = scale * 9.5367431640625e-07f;          // 2^-20 * scale (exact)
-  uint32_t acc_hi = 0u, acc_lo = 0u;
-  unsigned long long carry = 0ull;                              // limb sums are folded every 2048 vectors (no 32-bit overflow)
-  int since = 0;
-  for (int v = v_begin + lane; v < v_end; v += 32) {
-    const float4 a4 = row4[v];
-    const float w[4] = {a4.x, a4.y, a4.z, a4.w};
+  const f32x2 sh2 = pack2(scale_hi, scale_hi), k23 = pack2(8388608.0f, 8388608.0f), m1 = pack2(-1.0f, -1.0f), k20 = pack2(1048576.0f, 1048576.0f);
+  unsigned long long blk = 0ull, wsum = 0ull;
+  {
+    int k = 0;
+    for (int v0 = v_begin; v0 < v_end; v0 += 32, ++k) {
+      const int v = v0 + lane;
+      uint32_t acc_hi = 0u, acc_lo = 0u;
+      if (v < v_end) {
+        const float4 a4 = row4[v];
+        const f32x2 pr[2] = {pack2(a4.x, a4.y), pack2(a4.z, a4.w)};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float t1f = __fmaf_rd(w[j], scale_hi, 8388608.0f);                // 2^23 + floor(W / 2^20), W = w * scale < 2^40
-      const float hf = t1f - 8388608.0f;
-      const float lo = fmaf(hf, -1048576.0f, w[j] * scale);                   // W - 2^20 * floor(W / 2^20)  in [0, 2^20)
-      const float t2f = __fadd_rd(lo, 8388608.0f);                            // 2^23 + floor(lo)
-      acc_hi += __float_as_uint(t1f) - 0x4B000000u;
-      acc_lo += __float_as_uint(t2f) - 0x4B000000u;
+        for (int j = 0; j < 2; ++j) {
+          const f32x2 t1f = fma2_rd(pr[j], sh2, k23);           // 2^23 + H,  H = floor(W / 2^20),  W = r * scale < 2^40
+          const f32x2 nh = fma2(t1f, m1, k23);                  // -H
+          const f32x2 fr = fma2(pr[j], sh2, nh);                // W / 2^20 - H  in [0, 1)  (exact)
+          const f32x2 t2f = fma2_rd(fr, k20, k23);              // 2^23 + floor(W - 2^20 H)
+          float h0, h1, l0, l1;
+          unpack2(t1f, h0, h1);
+          unpack2(t2f, l0, l1);
+          acc_hi += (__float_as_uint(h0) - 0x4B000000u) + (__float_as_uint(h1) - 0x4B000000u);
+          acc_lo += (__float_as_uint(l0) - 0x4B000000u) + (__float_as_uint(l1) - 0x4B000000u);
+        }
+      }
+      const uint32_t hs = __reduce_add_sync(0xffffffffu, acc_hi), ls = __reduce_add_sync(0xffffffffu, acc_lo);
+      const unsigned long long bs = (static_cast<unsigned long long>(hs) << 20) + ls;
+      if (lane == k) blk = bs;                                  // (at most 29 blocks per warp: the row fits shared memory)
+      wsum += bs;
     }
-    if (++since == 512) { carry += (static_cast<unsigned long long>(acc_hi) << 20) + acc_lo; acc_hi = acc_lo = 0u; since = 0; }
   }
-  unsigned long long wsum = carry + (static_cast<unsigned long long>(acc_hi) << 20) + acc_lo;
-  wsum = warp_sum(wsum);
   if (lane == 0) sh.wsum[warp] = wsum;
   __syncthreads();
   const unsigned long long mine_w = lane < kRowWarps ? sh.wsum[lane] : 0ull;
@@ -178,10 +190,14 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
   const unsigned ball = __ballot_sync(0xffffffffu, incl > target);
   const int owner = __ffs(ball) - 1;                            // first warp whose range crosses the target
   if (warp != owner) return -1;
-  unsigned long long run = __shfl_sync(0xffffffffu, incl - mine_w, owner);
-  // the owning warp walks its range, 32 vectors per step, in vocabulary order
-  for (int v0 = v_begin; v0 < v_end; v0 += 32) {
-    const int v = v0 + lane;
+  const unsigned long long base = __shfl_sync(0xffffffffu, incl - mine_w, owner);
+  // the owning warp: block that crosses the target, then the element inside it (vocabulary order)
+  const unsigned long long bincl = warp_scan_incl(blk, lane) + base;
+  const unsigned bb = __ballot_sync(0xffffffffu, bincl > target);
+  const int kb = __ffs(bb) - 1;
+  const unsigned long long run = __shfl_sync(0xffffffffu, bincl - blk, kb);
+  {
+    const int v = v_begin + kb * 32 + lane;
     float w[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned long long wv[4], vs = 0ull;
     if (v < v_end) { const float4 a4 = row4[v]; w[0] = a4.x; w[1] = a4.y; w[2] = a4.z; w[3] = a4.w; }
@@ -189,18 +205,15 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
     for (int j = 0; j < 4; ++j) { wv[j] = weight_of(w[j], e); vs += wv[j]; }
     const unsigned long long inc2 = warp_scan_incl(vs, lane) + run;
     const unsigned b2 = __ballot_sync(0xffffffffu, inc2 > target);
-    if (b2) {
-      if (lane != __ffs(b2) - 1) return -1;
-      unsigned long long c = inc2 - vs;
-      long long found = -1;
-      float psel = 1.f;
+    if (b2 == 0u || lane != __ffs(b2) - 1) return -1;
+    unsigned long long c = inc2 - vs;
+    long long found = -1;
+    float psel = 1.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { c += wv[j]; if (found < 0 && c > target) { found = v * 4 + j; psel = w[j]; } }
-      float guard_val = psel;
-      if (use_q) guard_val = __fdiv_rn(psel, ldexpf(__ull2float_rn(total), e - kScaleBits) + 1e-6f);   // sample(max_fn(p - q)) sees the normalised value
-      return guard_val < kProbGuard ? argmax : found;
-    }
-    run = __shfl_sync(0xffffffffu, inc2, 31);
+    for (int j = 0; j < 4; ++j) { c += wv[j]; if (found < 0 && c > target) { found = v * 4 + j; psel = w[j]; } }
+    float guard_val = psel;
+    if (use_q) guard_val = __fdiv_rn(psel, ldexpf(__ull2float_rn(total), e - kScaleBits) + 1e-6f);   // sample(max_fn(p - q)) sees the normalised value
+    return guard_val < kProbGuard ? argmax : found;
   }
   return -1;
 }

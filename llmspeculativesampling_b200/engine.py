@@ -175,6 +175,7 @@ class SpecDecEngine:
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self.graph_captured = False
+        self.phase_ns = None                                       # filled by run(profile_every=N)
 
     # ------------------------------------------------------------------ state
     def load_prompts(self, prompts: Sequence[torch.Tensor], max_new_tokens, eos_token_id: Optional[int] = None) -> None:
@@ -205,8 +206,16 @@ class SpecDecEngine:
         self.target.prefill(self.tokens, n_pre)
 
     # ------------------------------------------------------------------ one iteration (graph body)
-    def _iteration(self) -> None:
+    def _iteration(self, marks: Optional[list] = None) -> None:
+        """marks: a list that receives CUDA events at the phase boundaries (start, drafts done, target forward done,
+        target rows normalised, verified + bookkeeping) — the eager, event-timed twin of the captured graph."""
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
         g, B, V = self.gamma, self.B, self.V
+        mark()
         self.u_draft_t.copy_(self.u_rows[:, :g].t())
         self.u_final.copy_(self.u_rows[:, 2 * g + 1])
         for i in range(g):
@@ -218,10 +227,13 @@ class SpecDecEngine:
                             tok_out=self.cur_tok, err=self.err,
                             compact=self.q_cmp.view(i, g) if self.use_compact else None)
             self.draft_tok[:, i].copy_(self.cur_tok)
+        mark()
         logits = self.target.forward(self.tokens, self.seq_len, -1, g + 1, self.cur_tok)
+        mark()
         ops.norm_probs(logits.reshape(B * (g + 1), V), self.T, self.top_k, self.top_p,
                        out=self.p_probs.view(B * (g + 1), V), err=self.err,
                        compact=self.p_cmp.view() if self.use_compact else None)
+        mark()
         ops.verify(self.p_probs, self.q_probs, self.draft_tok, self.u_rows[:, g + 1:2 * g + 1], self.u_final,
                    strict=self.strict, n_accepted=self.n_acc, next_tok=self.next_tok, ratios=self.ratios,
                    tie_count=self.ties, tokens=self.tokens, seq_len=self.seq_len, active=self.active, err=self.err,
@@ -235,6 +247,7 @@ class SpecDecEngine:
         gen = (self._cols >= self.prompt_len.unsqueeze(1)) & (self._cols < self.seq_len.unsqueeze(1))
         hit_eos = ((self.tokens == self.eos) & gen).any(dim=1)
         self.active.copy_(((self.seq_len < self.limit) & ~hit_eos & (self.active > 0)).to(torch.int32))
+        mark()
 
     def _capture(self) -> None:
         """Warm up on a side stream and capture one iteration into a CUDA graph."""
@@ -266,15 +279,24 @@ class SpecDecEngine:
             self.err.t.zero_()
 
     # ------------------------------------------------------------------ driver
-    def run(self, tape_dev: torch.Tensor, check_every: int = 1) -> int:
-        """tape_dev: (iterations, B, 2*gamma+2) uniforms on the device.  Returns iterations executed."""
+    def run(self, tape_dev: torch.Tensor, check_every: int = 1, profile_every: int = 0) -> int:
+        """tape_dev: (iterations, B, 2*gamma+2) uniforms on the device.  Returns iterations executed.
+        profile_every = N > 0: every N-th iteration (the first included) runs as the eager twin of the graph with CUDA
+        events at its phase boundaries; self.phase_ns then holds the phase times of the whole run, scaled from the timed
+        iterations (keys as the reference's `details`, sampling/speculative_sampling.py:2062-2073)."""
         if self.use_cuda_graph and self._graph is None and not self.graph_captured:
             self._capture()
         it = 0
         n_max = min(tape_dev.shape[0], self.max_iterations)
+        timed: List[list] = []
+        can_time = profile_every > 0 and type(self)._iteration is SpecDecEngine._iteration
         while it < n_max:
             self.u_rows.copy_(tape_dev[it])
-            if self._graph is not None:
+            if can_time and it % profile_every == 0:
+                marks: list = []
+                self._iteration(marks)
+                timed.append(marks)
+            elif self._graph is not None:
                 self._graph.replay()
             else:
                 self._iteration()
@@ -282,6 +304,17 @@ class SpecDecEngine:
             if it % check_every == 0 and int(self.active.sum().item()) == 0:
                 break
         self.err.check()
+        self.phase_ns = None
+        if timed:
+            torch.cuda.synchronize(self.device)
+            tot = [0.0, 0.0, 0.0, 0.0]
+            for m in timed:
+                for j in range(4):
+                    tot[j] += m[j].elapsed_time(m[j + 1]) * 1e6          # ms -> ns
+            k = it / len(timed)
+            self.phase_ns = {"approx_time": int(tot[0] * k), "target_model_time": int(tot[1] * k),
+                             "target_post_prob_time": int(tot[2] * k), "target_time": int((tot[1] + tot[2]) * k),
+                             "other_time": int(tot[3] * k), "target_pre_cache_time": 0, "timed_iterations": len(timed)}
         return it
 
     def results(self, eos_token_id: Optional[int] = None) -> List[torch.Tensor]:

@@ -19,6 +19,7 @@ from .. import uniform_tape
 
 _ENGINES: "OrderedDict[tuple, SpecDecEngine]" = OrderedDict()
 _MAX_ENGINES = 4
+_PROFILE_EVERY = 8          # details=True: every 8th iteration runs eagerly with CUDA events at the phase boundaries
 
 
 def _engine_for(approx_model, target_model, batch, total_len, gamma, temperature, top_k, top_p, device, strict,
@@ -70,7 +71,7 @@ def _run(prefix, approx_model, target_model, eos_token_id, max_len, gamma, tempe
     t0 = time.perf_counter_ns()
     try:
         eng.load_prompts(prompts, int(max_len), eos_token_id)
-        iters = eng.run(tape_dev)
+        iters = eng.run(tape_dev, profile_every=_PROFILE_EVERY if details else 0)
         outs = eng.results(eos_token_id)
     except RuntimeError as e:
         if str(e) in ("norm logits error", "prob error", "s"):
@@ -91,14 +92,21 @@ def _run(prefix, approx_model, target_model, eos_token_id, max_len, gamma, tempe
         rates = np.minimum(1.0, rat.astype(np.float64))[live[:, :, None] & tested]
     else:
         rates = np.minimum(1.0, rat.astype(np.float64))[live]              # every drafted token (:1966-1971)
+    # phase times (ns, as the reference's process_time_ns sums, :2062-2073): CUDA-event times of the eager twin of the graph,
+    # every _PROFILE_EVERY-th iteration, scaled to the run.  approx_time = the gamma draft steps (forward + kernel 1b),
+    # target_time = target forward + kernel 1, other_time = kernel 2 + bookkeeping; the static caches need no per-call
+    # cache preparation (target_pre_cache_time = 0).
+    ph = eng.phase_ns or {}
     d = {
-        "approx_time": 0, "target_time": 0, "other_time": elapsed,          # one fused graph: no per-phase split
+        "approx_time": ph.get("approx_time", 0), "target_time": ph.get("target_time", 0),
+        "other_time": ph.get("other_time", 0),
         "acc_len": acc_len[0] if B == 1 else acc_len,
         "acc_rate": float(rates.mean()) if rates.size else 0.0,
         "target_call_times": iters, "approx_call_times": iters,
-        "target_model_time": 0, "target_pre_cache_time": 0, "target_post_prob_time": 0,
+        "target_model_time": ph.get("target_model_time", 0), "target_pre_cache_time": 0,
+        "target_post_prob_time": ph.get("target_post_prob_time", 0),
         "total_time_ns": elapsed, "iterations": iters, "cuda_graph": eng.graph_captured,
-        "exact_ties": int(eng.ties.item()),
+        "exact_ties": int(eng.ties.item()), "timed_iterations": ph.get("timed_iterations", 0),
     }
     return out, d
 

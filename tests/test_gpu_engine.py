@@ -99,6 +99,15 @@ def test_drop_in_matches_reference_golden_runs(cuda_lib):
         assert out[0].tolist() == r["tokens"], f"V={r['V']} k={r['top_k']} p={r['top_p']} gamma={r['gamma']}"
         assert det["acc_len"] == r["acc_len"]
         assert abs(det["acc_rate"] - r["acc_rate"]) < 1e-5
+        # the reference's timing keys (speculative_sampling.py:2062-2073) carry CUDA-event times of the run's phases
+        assert det["timed_iterations"] >= 1 and det["target_pre_cache_time"] == 0
+        for key in ("approx_time", "target_time", "other_time", "target_model_time", "target_post_prob_time"):
+            assert isinstance(det[key], int) and det[key] > 0, key
+        assert det["target_time"] >= det["target_model_time"]
+        # ... and timing a run does not change it
+        plain = speculative_sampling(prefix, d, t, None, None, r["max_len"], r["gamma"], r["temperature"], r["top_k"], r["top_p"],
+                                     uniforms=tp)
+        assert plain[0].tolist() == r["tokens"]
 
 
 @pytest.mark.parametrize("use_graph", [True, False])

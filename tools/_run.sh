@@ -1,9 +1,10 @@
-mkdir -p gpurun_out/r2p
-o=gpurun_out/r2p
-python -m pytest tests -m gpu -x -q > $o/pytest.log 2>&1; tail -3 $o/pytest.log
-for dt in f32 bf16; do for V in 32000 50272; do
-  python tools/microbench.py --mode dense --rows 576 --V $V --dtype $dt --sample --iters 200 >> $o/mb.log 2>&1
-done; done
-python tools/microbench.py --mode dense --rows 2368 --sample --iters 100 >> $o/mb.log 2>&1
-python tools/microbench.py --mode dense --rows 576 --sample --iters 200 >> $o/mb.log 2>&1
-cat $o/mb.log
+mkdir -p gpurun_out/r2r
+o=gpurun_out/r2r
+python -m pytest tests -m gpu -x -q > $o/pytest.log 2>&1; tail -4 $o/pytest.log
+python tools/kernel_bench.py --mode verify_dense > $o/kb.jsonl 2> $o/kb.err
+python tools/kernel_bench.py --mode verify_dense --V 50272 >> $o/kb.jsonl 2>> $o/kb.err
+python tools/kernel_bench.py --mode verify_dense --B 256 >> $o/kb.jsonl 2>> $o/kb.err
+python tools/kernel_bench.py --mode verify_multi >> $o/kb.jsonl 2>> $o/kb.err
+python tools/kernel_bench.py --mode verify_bild >> $o/kb.jsonl 2>> $o/kb.err
+python tools/kernel_bench.py --mode sample >> $o/kb.jsonl 2>> $o/kb.err
+cut -c1-230 $o/kb.jsonl
