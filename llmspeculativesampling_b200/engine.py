@@ -317,8 +317,9 @@ class SpecDecEngine:
                              "other_time": int(tot[3] * k), "target_pre_cache_time": 0, "timed_iterations": len(timed)}
         return it
 
-    def results(self, eos_token_id: Optional[int] = None) -> List[torch.Tensor]:
-        """Per-request token tensors (1, n) with the reference's EOS cut (speculative_sampling.py:2033-2041)."""
+    def results(self, eos_token_id: Optional[int] = None, device=None) -> List[torch.Tensor]:
+        """Per-request token tensors (1, n) with the reference's EOS cut (speculative_sampling.py:2033-2041); on `device`
+        if given (the reference returns its output on the prefix's device), else on the host."""
         toks = self.tokens.cpu()
         lens = self.seq_len.cpu().tolist()
         plen = self.prompt_len.cpu().tolist()
@@ -330,4 +331,6 @@ class SpecDecEngine:
                 if new.numel() > 0:
                     row = row[:plen[b] + int(new[0]) + 1]
             outs.append(row.unsqueeze(0))
+        if device is not None:
+            outs = [o.to(device, non_blocking=True) for o in outs]
         return outs

@@ -100,9 +100,13 @@ class KVCacheModel:
             s1, e1 = self.forward_time_dict.span("norm_prob_time")
             s1.record()
             first = self._n + done
-            for b in range(B):                                    # rows of one request are contiguous in the buffer
-                ops.norm_probs(logits[b], self._temperature, self._top_k or 0, self._top_p or 0.0,
-                               out=self._prob_buf[b, first:first + q])
+            if q == 1:                                            # a generation step: ONE launch for all B rows (strided rows)
+                ops.norm_probs(logits[:, 0], self._temperature, self._top_k or 0, self._top_p or 0.0,
+                               out=self._prob_buf[:, first])
+            else:                                                 # prefill: the q rows of one request are contiguous in the buffer
+                for b in range(B):
+                    ops.norm_probs(logits[b], self._temperature, self._top_k or 0, self._top_p or 0.0,
+                                   out=self._prob_buf[b, first:first + q])
             e1.record()
             done += q
         self._n = cur

@@ -72,7 +72,7 @@ def _run(prefix, approx_model, target_model, eos_token_id, max_len, gamma, tempe
     try:
         eng.load_prompts(prompts, int(max_len), eos_token_id)
         iters = eng.run(tape_dev, profile_every=_PROFILE_EVERY if details else 0)
-        outs = eng.results(eos_token_id)
+        outs = eng.results(eos_token_id, device)
     except RuntimeError as e:
         if str(e) in ("norm logits error", "prob error", "s"):
             print(e)

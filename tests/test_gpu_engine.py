@@ -389,3 +389,34 @@ def test_bild_eos_inside_a_draft_matches_reference_golden_runs(cuda_lib):
             out, det = BiLD_sampling(prefix, d, t, r["gamma"], r["eos"], None, r["fallback_thres"], r["rollback_thres"], r["max_len"],
                                      r["temperature"], r["top_k"], r["top_p"], details=True, uniforms=tp, use_engine=use_engine)
             assert out[0].tolist() == r["tokens"], f"V={r['V']} gamma={r['gamma']} eos={r['eos']} engine={use_engine}"
+
+
+def test_evaluation_loop_statistics_and_batched_get_score(cuda_lib):
+    """Engine side of the reference's evaluation driver (evaluation.py:109-132, :515-583): the batched
+    request loop gives, per request, the tokens of a one-request call with the same request id; its sums are the sums of the
+    per-request details; get_score over a ragged batch (one target forward) equals the reference's formula per output."""
+    from llmspeculativesampling_b200.evaluation import evaluate_speculative, evaluate_autoregressive, get_score
+    from llmspeculativesampling_b200.sampling import speculative_sampling
+    V, N = 2000, 20
+    d, t = _pair(V, 9, 0.5)
+    g = torch.Generator().manual_seed(4)
+    ds = [torch.randint(3, V, (1, int(n)), generator=g).cuda() for n in (5, 9, 7, 12, 6, 3, 8)]
+    outs, st = evaluate_speculative(ds, d, t, N, gamma=4, temperature=1.0, top_k=20, top_p=0.9, random_seed=13, batch=3)
+    assert len(outs) == len(ds) and st.requests == len(ds)
+    tot_acc = tot_calls = tot_tok = 0
+    for i, x in enumerate(ds):
+        want, det = speculative_sampling(x, d, t, None, None, N, 4, 1.0, 20, 0.9, False, 13, True, request_ids=[i])
+        assert torch.equal(outs[i].reshape(-1), want.reshape(-1)), f"request {i}"
+        tot_acc += sum(det["acc_len"]); tot_calls += det["target_call_times"]; tot_tok += want.numel() - x.numel()
+        # evaluation.py:109-122 on this output alone
+        lg = torch.log_softmax(t(want).logits[:, :-1, :].float(), dim=-1)
+        ref = torch.gather(lg, -1, want[:, 1:, None])[:, x.shape[1] - 1:, :].mean()
+        assert abs(float(st.scores[i]) - float(ref)) < 1e-5
+        assert abs(float(get_score(want, t, x.shape[1])) - float(ref)) < 1e-6
+    s = st.summary()
+    assert st.total_acc_len == tot_acc and st.target_times == tot_calls and st.total_token == tot_tok
+    assert abs(s["average_accepted_len"] - tot_acc / tot_calls) < 1e-12 and s["tokens_per_s"] > 0
+    assert st.approx_time > 0 and st.target_time >= st.target_model_time > 0 and st.target_post_prob_time > 0
+    assert len(st.lines()) == 5 and "average accepted len" in st.lines()[2]
+    outs_ar, st_ar = evaluate_autoregressive(ds[:3], t, 8, temperature=1.0, top_k=20, top_p=0.9, random_seed=5)
+    assert st_ar.total_token == 24 and len(st_ar.scores) == 3 and all(o.shape[1] == x.shape[1] + 8 for o, x in zip(outs_ar, ds))

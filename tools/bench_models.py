@@ -125,7 +125,7 @@ def main():
                 h = 1469598103934665603
                 for t in [ids[j]] + row:
                     h = ((h ^ int(t)) * 1099511628211) & 0xFFFFFFFFFFFF
-                checksum = (checksum + h) % (1 << 52)
+                checksum = (checksum + (h & 0xFFFFFFFFFF)) % (1 << 48)      # (< 2^48: the float64 all-reduce below stays exact)
         stats = torch.tensor([elapsed, float(tot_emit), float(tot_acc), float(tot_iter_req), float(checksum)], dtype=torch.float64, device=dev)
         if world > 1:
             mx = stats[:1].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -135,7 +135,7 @@ def main():
         results.append({"setting": setting, "top_k": top_k, "top_p": top_p, "emitted_tokens_per_s": emit / el,
                         "accepted_tokens_per_s": acc_n / el, "mean_accepted_per_iteration": acc_n / max(itreq, 1),
                         "request_iterations_per_s": itreq / el, "seconds": el, "cuda_graph": captured,
-                        "emitted_tokens": int(emit), "tokens_checksum": int(csum) % (1 << 52)})
+                        "emitted_tokens": int(emit), "tokens_checksum": int(csum) % (1 << 48)})
         del eng
         torch.cuda.empty_cache()
     if rank == 0:
