@@ -14,16 +14,20 @@ Metric: accepted tokens/s (whole job, all GPUs); emitted tokens/s and the accept
 
 value     inputs resident in HBM, steps replayed from CUDA graphs, timed with CUDA events around exactly K steps (barrier +
           synchronize on both sides, max over ranks).  Inputs rotate over distinct sets whose total exceeds 2x the 126 MB
-          L2.  By default the steps are software-pipelined (--pipeline 1): a 16-step graph launches kernel 1 of batch i+1
-          right behind kernel 1 of batch i while kernel 2 of batch i runs beside it on a second stream — two independent
-          batches in flight, as a serving loop with more than one batch would run them; `serial_ms_per_step` is the same
-          step with its kernels strictly one after the other.
+          L2.  By default the steps are software-pipelined (--pipeline 2): a 16-step graph keeps independent batches in
+          flight, as a serving loop with more than one batch would run them — kernel 2 of batch i runs on a second stream
+          beside kernel 1 of batch i+1, and kernel 1 of consecutive batches alternates between two streams (own scheduler
+          workspace each), so the persistent CTAs of batch i+1 take over every SM as soon as batch i's CTA on it has exited:
+          one launch's drain (selection latency of its last rows, slowest CTA, grid completion) overlaps the next
+          launch's ramp instead of leaving HBM idle.  `serial_ms_per_step` is the same step with its kernels strictly one
+          after the other (the latency of ONE batch); --pipeline 1 / 0 select the older schedules.
 e2e       same steps through the public tensor API with HOST buffers: every step copies its logits and uniforms from
           pinned host memory to the device (double-buffered on a copy stream) and reads accept counts and tokens back.
 roofline  dominant kernel (norm, 1 launch per step): algorithmic bytes (rows * V * (4 read + 4 written)) / its average
-          launch duration from back-to-back graph replays (>= 240 launches whatever --steps is); peak =
-          MEASURED_PEAKS.json hbm_gbs.  `roofline.step` is the same for the whole step, `roofline.verify_dense` kernel 2's
-          dense path (top_k = 0) at V = 32000 / 50272.
+          launch duration from back-to-back graph replays ON ONE STREAM (>= 240 launches whatever --steps is); peak =
+          MEASURED_PEAKS.json hbm_gbs.  `roofline.overlapped` is the time per launch when the same launches alternate
+          between two streams, `roofline.step` the whole step (both kernels) over the timed ms_per_step,
+          `roofline.verify_dense` kernel 2's dense path (top_k = 0) at V = 32000 / 50272.
 gpu_aten_baseline   the reference's ATen op chain on the same B200, batch 1 as the reference runs (oracle/aten_gpu.py).
 cpu_baseline / --impl reference   the oracle port of the reference's CPU path (oracle/ref_ops.py: the same
           ATen op chain, one row at a time, host syncs included) on a bounded sample of the same workload.
@@ -401,9 +405,10 @@ def main():
     ap.add_argument("--fused", type=int, default=0,
                     help="0: sd_norm_sample + sd_verify (two launches per step); "
                          "1: sd_norm_sample_verify (one launch per step, requests verified inside the cluster-pipeline norm kernel)")
-    ap.add_argument("--pipeline", type=int, default=1,
+    ap.add_argument("--pipeline", type=int, default=2,
                     help="1: software-pipelined steps (kernel 2 of batch i runs on a second stream while kernel 1 of batch i+1 streams); "
-                         "0: the two kernels of every step strictly one after the other")
+                         "2 (default): kernel 1 of consecutive steps additionally alternates between two streams, so one launch's drain "
+                         "overlaps the next launch's ramp; 0: the two kernels of every step strictly one after the other")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("SD_PDL", "1")), help="programmatic dependent launch on/off")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -454,10 +459,12 @@ def main():
     err = ops.ErrFlag(dev)
     req_cnt = torch.zeros(B, dtype=torch.int32, device=dev)       # fused launch: finished-row counters (left zeroed)
 
-    def norm(i: int, lg=None, ur=None, pr=None):
+    err_b = ops.ErrFlag(dev)                                      # second error flag + scheduler workspace (second kernel-1 stream)
+
+    def norm(i: int, lg=None, ur=None, pr=None, ef=None):
         ops.norm_sample((logits[i] if lg is None else lg).view(B * R, V), TEMP, TOP_K, TOP_P, u_rows[i] if ur is None else ur,
-                        probs_out=(probs[i] if pr is None else pr).view(B * R, V), tok_out=tok_rows[i].view(-1), err=err,
-                        compact=cmp_rows[i].view())
+                        probs_out=(probs[i] if pr is None else pr).view(B * R, V), tok_out=tok_rows[i].view(-1),
+                        err=err if ef is None else ef, compact=cmp_rows[i].view())
 
     def verify(i: int, count: bool = True, pr=None, ua=None, uf=None):
         p_ = probs[i] if pr is None else pr
@@ -492,19 +499,36 @@ def main():
 
     g_serial = [capture(lambda i=i: step(i)) for i in range(n_sets)]       # one step, its kernels strictly in order
 
+    side3 = torch.cuda.Stream()
+
     def pipelined():
-        """PIPE_STEPS steps on two streams: kernel 1 of step j+1 is launched right behind kernel 1 of step j, kernel 2 of
-        step j runs beside it on the second stream (it needs a few KB of compact lists and a handful of thread blocks).
+        """PIPE_STEPS steps, independent batches in flight.  --pipeline 1: kernel 1 of step j+1 is launched right behind
+        kernel 1 of step j on one stream, kernel 2 of step j runs beside it on a second stream (it needs a few KB of
+        compact lists and a handful of thread blocks).  --pipeline 2 (default): kernel 1 of consecutive steps additionally
+        alternates between TWO streams (each with its own scheduler workspace): the persistent CTAs of step j+1 take over
+        every SM as soon as step j's CTA on it has exited, so the drain of one launch (selection latency of the last rows,
+        slowest CTA, grid completion) overlaps the ramp of the next instead of leaving HBM idle.
         A step's buffers are reused n_sets steps later: kernel 1 of step j waits for kernel 2 of step j - n_sets."""
         main_s = torch.cuda.current_stream()
+        two = args.pipeline >= 2
+        if two:
+            side3.wait_stream(main_s)
         ev_v = {}
         for j in range(PIPE_STEPS):
             i = j % n_sets
+            s_n = side3 if (two and j % 2 == 1) else main_s
             if j - n_sets in ev_v:
-                main_s.wait_event(ev_v[j - n_sets])
-            norm(i)
-            ev_n = torch.cuda.Event()
-            ev_n.record(main_s)
+                s_n.wait_event(ev_v[j - n_sets])
+            with torch.cuda.stream(s_n):
+                norm(i, ef=err_b if (two and j % 2 == 1) else None)
+                ev_n = torch.cuda.Event()
+                ev_n.record(s_n)
+            if args.pipeline >= 3:                                  # two independent serial chains: kernel 2 stays on its kernel 1's stream
+                with torch.cuda.stream(s_n):
+                    verify(i)
+                    ev_v[j] = torch.cuda.Event()
+                    ev_v[j].record(s_n)
+                continue
             side2.wait_event(ev_n)
             with torch.cuda.stream(side2):
                 verify(i)
@@ -512,6 +536,8 @@ def main():
                 ev_v[j].record(side2)
         for j in range(PIPE_STEPS - n_sets, PIPE_STEPS):
             main_s.wait_event(ev_v[j])
+        if two:
+            main_s.wait_stream(side3)
 
     use_pipe = bool(args.pipeline) and not args.fused
     g_pipe = capture(pipelined) if use_pipe else None
@@ -564,6 +590,15 @@ def main():
 
     serial_ms = timed(capture(lambda: [step(i, False) for i in range(n_sets)]), n_sets)
     norm_ms = timed(capture(lambda: [norm(i) for i in range(n_sets)]), n_sets)
+
+    def norm_two_streams():                                 # kernel 1 only, launches alternating between two streams
+        main_s = torch.cuda.current_stream()
+        side3.wait_stream(main_s)
+        for j in range(2 * n_sets):
+            with torch.cuda.stream(side3 if j % 2 else main_s):
+                norm(j % n_sets, ef=err_b if j % 2 else None)
+        main_s.wait_stream(side3)
+    norm_overlap_ms = timed(capture(norm_two_streams), 2 * n_sets)
     verify_ms = timed(capture(lambda: [verify(i, False) for i in range(n_sets)]), n_sets)
     clock_info = clocks.stop()
     norm_bytes = B * R * V * 8                              # logits read once (4 B) + probs written once (4 B)
@@ -666,9 +701,11 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2_policy": f"inputs and outputs rotate over {n_sets} sets "
                    f"({n_sets * norm_bytes / 1e6:.0f} MB > 2 x 126 MB L2), identical on every rank", "cuda_graph": True,
-                   "pipeline": (f"software-pipelined: {pipelined_steps} of the {args.steps} timed steps ran from a {PIPE_STEPS}-step CUDA graph in which "
-                                "kernel 2 of batch i runs on a second stream beside kernel 1 of batch i+1 (two independent batches in "
-                                "flight; results identical); the rest strictly serial") if use_pipe else "strictly serial steps",
+                   "pipeline": (f"software-pipelined (--pipeline {args.pipeline}): {pipelined_steps} of the {args.steps} timed steps ran from a "
+                                f"{PIPE_STEPS}-step CUDA graph in which kernel 2 of batch i runs on a second stream beside kernel 1 of batch i+1"
+                                + (", and kernel 1 of consecutive batches alternates between two streams (the next launch's persistent CTAs "
+                                   "take over each SM as the previous launch's CTA on it exits)" if args.pipeline >= 2 else "")
+                                + " — independent batches in flight, results identical; the rest strictly serial") if use_pipe else "strictly serial steps",
                    "kernels_per_step": (["sd_norm_sample_verify (ONE launch: kernel 1 over the B*(2*gamma+1) rows — dense probs + "
                                          "compact lists — and kernel 2's verify of each request inside it)"] if args.fused else
                                         ["sd_norm_sample (ring kernel: B*(2*gamma+1) rows, one launch; dense probs + compact lists)",
@@ -690,6 +727,11 @@ def main():
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "timing": "CUDA events around back-to-back graph replays of the launch (4 rotating input sets, >= 240 launches)",
                      "kernel_ms_graph_back_to_back": {"norm": norm_ms, "verify": verify_ms},
+                     "overlapped": {"ms_per_launch": norm_overlap_ms, "achieved": norm_bytes / (norm_overlap_ms * 1e-3) / 1e9,
+                                    "frac": norm_bytes / (norm_overlap_ms * 1e-3) / 1e9 / peak,
+                                    "note": "the same launches alternating between two streams (independent batches): time per launch when one "
+                                            "launch's drain overlaps the next launch's ramp; `achieved` / `frac` above are the strict "
+                                            "single-stream figures"},
                      "step": {"algorithmic_bytes": step_bytes, "ms": step_ms, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
                               "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "serial_ms": serial_ms,
                               "serial_frac": step_bytes / (serial_ms * 1e-3) / 1e9 / peak,

@@ -145,9 +145,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
     }
     __syncthreads();
     if (round == 0) pdl_wait();                                // everything above overlapped the previous kernel's tail
-    // Dependents may be scheduled from here on: the next kernel's CTAs take over every SM as soon as this kernel's CTA on it
-    // exits and run their own prologue (barrier init, zero chunk) up to their dependency wait, instead of being launched only
-    // after the LAST CTA of this kernel has finished (measured: ~2.5 us per launch boundary)
+    // SD_RING_TRIGGER=1: dependents may be scheduled from here on (the next kernel's CTAs then take over every SM as soon as
+    // this kernel's CTA on it exits and run their prologue up to their dependency wait).  Measured: 0.5 us per boundary in
+    // eager back-to-back launches, nothing inside CUDA graphs, and early-launched dependents can hold SMs that a concurrent
+    // independent launch on another stream could use — off by default (the trigger then comes after all work of the CTA).
     if (round == 0 && p.ring_trigger) pdl_launch_dependents();
     if (round == 0 && prof_cta != nullptr && tid == 0) prof_cta[1] = static_cast<long long>(globaltimer_ns());
 
