@@ -6,7 +6,7 @@
 //     TOPK   0 < top_k <= 128, any top_p
 //     DENSE  top_k = 0, top_p = 0
 // whenever a row fits the shared-memory ring of one CTA (V * sizeof(logit) <= slots * 16 KB: every vocabulary of the
-// named models in fp32 up to V = 53248, in bf16 / fp16 up to V = 106496), rows are 16-byte aligned and a scheduler
+// named models: top-k 12 chunks = fp32 up to V = 49152, dense 13 chunks = fp32 up to V = 53248; bf16 / fp16 twice that), rows are 16-byte aligned and a scheduler
 // workspace is given.  Everything else keeps using the cluster kernels (norm_pipe.cu, norm.cu).
 #include "norm_ring_kernel.cuh"
 
@@ -52,7 +52,7 @@ bool plan_ring(NormParams& p, int dtype, int rows) {
   const bool aligned_out = p.probs == nullptr || (reinterpret_cast<uintptr_t>(p.probs) % 16 == 0 && p.ld_out % 4 == 0 && p.V % 4 == 0);
   if (!aligned_in || !aligned_out) return false;
   const int smem_max = device_max_smem_optin();
-  const size_t fixed = (sizeof(RingShared) + 127) & ~static_cast<size_t>(127);
+  const size_t fixed = ((mode == kRingDense ? kRingSharedDenseBytes : sizeof(RingShared)) + 127) & ~static_cast<size_t>(127);
   const int extra = mode == kRingTopK ? 1 : 0;               // TOPK: one more chunk holds the zeros of the output rows' zero fill
   int slots = static_cast<int>((static_cast<size_t>(smem_max) - fixed) / kRingChunkBytes) - extra;
   if (slots > kRingMaxSlots) slots = kRingMaxSlots;
@@ -62,7 +62,7 @@ bool plan_ring(NormParams& p, int dtype, int rows) {
   // in-kernel general-path fallback (norm_row with the whole row in this CTA) must fit in front of the deferred-row list
   const long long slice = (p.V + 127) & ~127LL;
   const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
-  if (mode == kRingTopK && slice_bytes + sizeof(NormShared<kRingThreads>) > shared_off + offsetof(RingShared, n_fail)) return false;
+  if (mode == kRingTopK && slice_bytes + sizeof(NormShared<kRingThreads>) > shared_off + offsetof(RingShared, fail_rows)) return false;
   // pivot taken while the row's last chunks are still in flight: pays for rows of >= 7 chunks (measured: 8 chunks 31.9 -> 31.2 us,
   // 7 chunks 36.1 -> 35.0 us at 576 rows; rows of 4 chunks lose: the early pivot is too weak there)
   { const char* ev = getenv("SD_RING_EARLY"); p.ring_early = ev != nullptr ? atoi(ev) : (n_chunks >= 7 ? 3 : 0); }

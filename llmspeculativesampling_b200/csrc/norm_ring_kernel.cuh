@@ -43,16 +43,9 @@ constexpr uint32_t kRingTieUlps = 8;
 
 enum : int { kRingTopK = 0, kRingDense = 1, kRingDenseT1 = 2 };   // (DenseT1: temperature == 1, no logit / T arithmetic compiled in)
 
-struct alignas(16) RingShared {
-  uint64_t full[kRingMaxSlots];        // chunk landed                       (TMA -> compute warps)
-  uint64_t empty[kRingMaxSlots];       // slot may be overwritten            (16 compute warps -> loader)
-  uint64_t rowfull[kRingItemRing];     // row of item it published           (loader -> everyone)
-  uint64_t sorted[2];                  // TOPK: candidates of item it complete (16 compute warps -> aux), by item parity
-  uint64_t sfree[2];                   // TOPK: that candidate array may be reused    (aux -> compute)
-  uint64_t row_done[2];                // DENSE: row written, piece sums ready (16 compute warps -> aux), by item parity
-  uint64_t tfree[2];                   // DENSE: piece table may be reused   (aux -> compute)
-  int row_of[kRingItemRing];
-  // ---- TOPK scratch
+// scratch of the two modes (a union inside RingShared: a dense launch needs 5 KB next to the ring instead of 19 KB, which
+// is one more 16 KB slot — fp32 rows of V = 50272 are 13 chunks)
+struct alignas(16) RingTopKScratch {
   alignas(16) float tm_in[128];        // maxima of the 128 thread quads
   float tm[128];                       // the same, sorted per warp (4 lists of 32)
   uint2 w_pair[kRingComputeWarps][kRingWarpCap];     // slow path only: a warp's candidates before they are allocated
@@ -63,15 +56,33 @@ struct alignas(16) RingShared {
   float s_val[2][kRingCap];            // sorted candidates (logit / T, descending), double buffered by item parity (compute -> aux)
   int s_idx[2][kRingCap];
   float f_val[kRingCap];               // ... and the final probabilities of the row it is finishing
-  // ---- DENSE scratch
+};
+struct alignas(16) RingDenseScratch {
   float wm[kRingComputeWarps];
   double ws[kRingComputeWarps];
   unsigned long long piece[2][kRingMaxPieces];
   float info_c2[2];
-  // ---- kept LAST (survives norm_row, which re-purposes everything in front of it)
-  int n_fail, end_reason;
+};
+
+struct alignas(16) RingShared {
+  uint64_t full[kRingMaxSlots];        // chunk landed                       (TMA -> compute warps)
+  uint64_t empty[kRingMaxSlots];       // slot may be overwritten            (16 compute warps -> loader)
+  uint64_t rowfull[kRingItemRing];     // row of item it published           (loader -> everyone)
+  uint64_t sorted[2];                  // TOPK: candidates of item it complete (16 compute warps -> aux), by item parity
+  uint64_t sfree[2];                   // TOPK: that candidate array may be reused    (aux -> compute)
+  uint64_t row_done[2];                // DENSE: row written, piece sums ready (16 compute warps -> aux), by item parity
+  uint64_t tfree[2];                   // DENSE: piece table may be reused   (aux -> compute)
+  int row_of[kRingItemRing];
+  int n_fail, end_reason;              // (read into registers before the general path re-purposes the memory)
+  union {
+    RingTopKScratch k;
+    RingDenseScratch d;
+  };
+  // ---- kept LAST (TOPK only; survives norm_row, which re-purposes everything in front of it)
   int fail_rows[kRingMaxFail];
 };
+// bytes of RingShared a dense launch touches
+constexpr size_t kRingSharedDenseBytes = offsetof(RingShared, d) + sizeof(RingDenseScratch);
 
 __device__ __forceinline__ void ring_named_bar(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
       }
       sh.n_fail = 0;
       sh.end_reason = kRingEndDone;
-      sh.cand_cnt = 0; sh.cand_over = 0;
+      if constexpr (MODE == kRingTopK) { sh.k.cand_cnt = 0; sh.k.cand_over = 0; }   // (a dense launch does not allocate the top-k scratch)
       fence_barrier_init();
     }
     if (round > 0) {
@@ -202,11 +213,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           const float u_row = p.u != nullptr ? __ldg(p.u + row) : -1.f;        // (requested now, needed after the softmax)
           const int par = it & 1;
           mbar_wait(&sh.sorted[par], static_cast<uint32_t>(it >> 1) & 1u);
-          const int n_tot = *reinterpret_cast<volatile int*>(&sh.n_sorted[par]);
+          const int n_tot = *reinterpret_cast<volatile int*>(&sh.k.n_sorted[par]);
           RING_PROF_AUX(8);
           if (n_tot >= 0) {                                        // (< 0: the row goes to the general path)
-            const float* sv = sh.s_val[par];
-            const int* si = sh.s_idx[par];
+            const float* sv = sh.k.s_val[par];
+            const int* si = sh.k.s_idx[par];
             int np_out = 0;
             int nk = 0;
             const float kth = sv[k_eff - 1];
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               const float logz = logf(static_cast<float>(z2));
               const float pr = in_p ? expf((x - M) - logz) : 0.f;
               if (in_p && (!(pr >= 0.f) || isinf(pr))) atomicOr(p.err_flag, kErrNanLogit);
-              if (in_p) sh.f_val[lane] = pr;
+              if (in_p) sh.k.f_val[lane] = pr;
               np_out = np;
               if (p.cmp.cnt != nullptr) {
                 const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
@@ -289,7 +300,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               for (int i = lane; i < np; i += 32) {
                 const float pr = expf((sv[i] - M) - logz);
                 badp |= !(pr >= 0.f) || isinf(pr);
-                sh.f_val[i] = pr;
+                sh.k.f_val[i] = pr;
               }
               if (badp) atomicOr(p.err_flag, kErrNanLogit);
               np_out = np;
@@ -297,14 +308,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               if (p.cmp.cnt != nullptr) {
                 const long long cr = static_cast<long long>(row) * p.cmp.row_stride;
                 if (np <= p.cmp.cap) {
-                  for (int i = lane; i < np; i += 32) { p.cmp.idx[cr * p.cmp.cap + i] = si[i]; p.cmp.val[cr * p.cmp.cap + i] = sh.f_val[i]; }
+                  for (int i = lane; i < np; i += 32) { p.cmp.idx[cr * p.cmp.cap + i] = si[i]; p.cmp.val[cr * p.cmp.cap + i] = sh.k.f_val[i]; }
                   if (lane == 0) p.cmp.cnt[cr] = np;
                 } else if (lane == 0) p.cmp.cnt[cr] = -1;
               }
               if (p.u != nullptr && u_row >= 0.f) {
-                const int e = frexp_exp(sh.f_val[0]);
+                const int e = frexp_exp(sh.k.f_val[0]);
                 unsigned long long tot = 0ull;
-                for (int i = lane; i < np; i += 32) tot += weight_of(sh.f_val[i], e);
+                for (int i = lane; i < np; i += 32) tot += weight_of(sh.k.f_val[i], e);
                 tot = warp_sum(tot);
                 if (tot == 0ull) {
                   if (lane == 0) { atomicOr(p.err_flag, kErrEmptyRow); p.tok_out[row] = 0; }
@@ -312,11 +323,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
                   const unsigned long long target = scale_target(tot, u_to_int(u_row));
                   for (int i = lane; i < np; i += 32) {
                     const int id = si[i];
-                    const unsigned long long wi = weight_of(sh.f_val[i], e);
+                    const unsigned long long wi = weight_of(sh.k.f_val[i], e);
                     unsigned long long before = 0ull;
-                    for (int j = 0; j < np; ++j) before += (si[j] < id) ? weight_of(sh.f_val[j], e) : 0ull;
+                    for (int j = 0; j < np; ++j) before += (si[j] < id) ? weight_of(sh.k.f_val[j], e) : 0ull;
                     if (wi > 0ull && target >= before && target < before + wi)
-                      p.tok_out[row] = (sh.f_val[i] < kProbGuard) ? si[0] : id;
+                      p.tok_out[row] = (sh.k.f_val[i] < kProbGuard) ? si[0] : id;
                   }
                 }
               }
@@ -326,7 +337,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
             if (want_probs) {                                     // scatter the non-zeros over the zero-filled row
               if (lane == 0) tma_store_wait_all();                // the zeros of this row are in place
               __syncwarp();
-              for (int i = lane; i < np_out; i += 32) orow[si[i]] = sh.f_val[i];
+              for (int i = lane; i < np_out; i += 32) orow[si[i]] = sh.k.f_val[i];
             }
           } else if (lane == 0) {
             sh.fail_rows[atomicAdd(&sh.n_fail, 1)] = row;         // deferred to the general path (runs after the ring has drained)
@@ -347,8 +358,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           mbar_wait(&sh.row_done[par], static_cast<uint32_t>(it >> 1) & 1u);
           const bool do_sample = p.u != nullptr && p.u[row] >= 0.f;
           if (do_sample) {
-            const volatile unsigned long long* tab = sh.piece[par];
-            const float c2 = *reinterpret_cast<volatile float*>(&sh.info_c2[par]);
+            const volatile unsigned long long* tab = sh.d.piece[par];
+            const float c2 = *reinterpret_cast<volatile float*>(&sh.d.info_c2[par]);
             const int e = frexp_exp(ex2_ftz(c2));
             const int ppl = (n_pieces + 31) / 32;               // pieces per lane (contiguous range)
             unsigned long long mine = 0ull;
@@ -488,20 +499,20 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           {
             float q = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
             q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 2));
-            if ((lane & 3) == 0) sh.tm_in[warp * 8 + (lane >> 2)] = q;
+            if ((lane & 3) == 0) sh.k.tm_in[warp * 8 + (lane >> 2)] = q;
           }
           ring_named_bar(1, CT);
           // (every thread has read the previous row's count by now.  Done by a thread of a warp that does NOT sort below: a
           //  single-lane branch in front of the shuffles made warp 0 diverge there — measured 5k cycles for a 0.5k sort)
-          if (tid == CT - 1) { sh.cand_cnt = 0; sh.cand_over = 0; }
+          if (tid == CT - 1) { sh.k.cand_cnt = 0; sh.k.cand_over = 0; }
           if (warp < 4) {
-            const float sv = warp_sort_desc(sh.tm_in[warp * 32 + lane], lane);
-            sh.tm[warp * 32 + lane] = sv;
+            const float sv = warp_sort_desc(sh.k.tm_in[warp * 32 + lane], lane);
+            sh.k.tm[warp * 32 + lane] = sv;
             ring_named_bar(2, 128);
             const int kk = min(k_eff, 32);
             if (tid < 4 * kk) {                                  // element (list ew, position ej), one per thread
               const int ew = tid / kk, ej = tid - ew * kk;
-              const float ev = sh.tm[ew * 32 + ej];
+              const float ev = sh.k.tm[ew * 32 + ej];
               int lo[4], hi[4];
 #pragma unroll
               for (int w = 0; w < 4; ++w) { lo[w] = 0; hi[w] = 32; }
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
                   const int mid = (lo[w] + hi[w]) >> 1;
-                  const float y = sh.tm[w * 32 + min(mid, 31)];
+                  const float y = sh.k.tm[w * 32 + min(mid, 31)];
                   const bool before = mid < 32 && ((y > ev) || (y == ev && w < ew));
                   lo[w] = before ? mid + 1 : lo[w];
                   hi[w] = before ? hi[w] : mid;
@@ -519,14 +530,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               int rank = ej;
 #pragma unroll
               for (int w = 0; w < 4; ++w) rank += (w == ew) ? 0 : lo[w];
-              if (rank == k_eff - 1) sh.tau = ev;                // (exactly one value has this rank: k_eff <= 128)
+              if (rank == k_eff - 1) sh.k.tau = ev;                // (exactly one value has this rank: k_eff <= 128)
             }
           }
           RING_PROF(4);
           for (int c = c_piv + 1; c < NCH; ++c) scan_chunk(c);    // the rest of pass 1 while the pivot settles
           if (nan_acc != nan_acc || tmax == INFINITY) { atomicOr(p.err_flag, kErrNanLogit); tmax = INFINITY; }
           ring_named_bar(1, CT);
-          const float tau = float_down(sh.tau, t1 ? 0u : kRingTieUlps);
+          const float tau = float_down(sh.k.tau, t1 ? 0u : kRingTieUlps);
           RING_PROF(2);
 
           // ---- pass 2: every element >= pivot of the threads whose maximum reaches it goes straight into the row's candidate
@@ -582,7 +593,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
                     const float val = __shfl_sync(0xffffffffu, o[j], src);
                     const int idx = __shfl_sync(0xffffffffu, v, src) * PV + j;
                     if (val >= tau) {
-                      if (lane == 0 && ws < kRingWarpCap) sh.w_pair[warp][ws] = make_uint2(__float_as_uint(val), static_cast<uint32_t>(idx));
+                      if (lane == 0 && ws < kRingWarpCap) sh.k.w_pair[warp][ws] = make_uint2(__float_as_uint(val), static_cast<uint32_t>(idx));
                       ++ws;
                     }
                   }
@@ -592,23 +603,23 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
             __syncwarp();
             int base = 0;
             if (lane == 0 && wq + ws > 0) {
-              base = atomicAdd(&sh.cand_cnt, wq + ws);
-              if (ws > kRingWarpCap) sh.cand_over = 1;
+              base = atomicAdd(&sh.k.cand_cnt, wq + ws);
+              if (ws > kRingWarpCap) sh.k.cand_over = 1;
             }
             base = __shfl_sync(0xffffffffu, base, 0);
             if (c > 0) {
               int w = base + incl - c;
 #pragma unroll
               for (int j = 0; j < PV; ++j)
-                if (o1[j] >= tau) { if (w < kRingCap) sh.a_key[w] = key_of(o1[j], i1 * PV + j); ++w; }
+                if (o1[j] >= tau) { if (w < kRingCap) sh.k.a_key[w] = key_of(o1[j], i1 * PV + j); ++w; }
               if (two) {
 #pragma unroll
                 for (int j = 0; j < PV; ++j)
-                  if (o2[j] >= tau) { if (w < kRingCap) sh.a_key[w] = key_of(o2[j], i2 * PV + j); ++w; }
+                  if (o2[j] >= tau) { if (w < kRingCap) sh.k.a_key[w] = key_of(o2[j], i2 * PV + j); ++w; }
               }
             }
             for (int i = lane; i < min(ws, kRingWarpCap); i += 32)
-              if (base + wq + i < kRingCap) sh.a_key[base + wq + i] = key_of(__uint_as_float(sh.w_pair[warp][i].x), static_cast<int>(sh.w_pair[warp][i].y));
+              if (base + wq + i < kRingCap) sh.k.a_key[base + wq + i] = key_of(__uint_as_float(sh.k.w_pair[warp][i].x), static_cast<int>(sh.k.w_pair[warp][i].y));
           }
           // the row's logits are no longer needed: hand the ring slots back to the loader
           __syncwarp();
@@ -618,31 +629,31 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           if (it >= 2) mbar_wait(&sh.sfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);
           ring_named_bar(1, CT);
           RING_PROF(12);
-          const int n_tot = sh.cand_cnt;
+          const int n_tot = sh.k.cand_cnt;
           // self-check: every element >= pivot collected (no overflow), at least k of them; else the general path
-          const bool ok = sh.cand_over == 0 && n_tot <= kRingCap && n_tot >= k_eff;
+          const bool ok = sh.k.cand_over == 0 && n_tot <= kRingCap && n_tot >= k_eff;
           if (ok) {
             // ---- rank sort on the 64-bit keys (value descending, then vocabulary index ascending): four threads per candidate
             for (int b0 = 0; b0 < n_tot; b0 += CT / 4) {
               const int i = b0 + (tid >> 2);
               const bool live = i < n_tot;
-              const unsigned long long ki = live ? sh.a_key[i] : 0ull;
+              const unsigned long long ki = live ? sh.k.a_key[i] : 0ull;
               int r = 0;
               if (live) {
 #pragma unroll 4
-                for (int j = tid & 3; j < n_tot; j += 4) r += sh.a_key[j] > ki ? 1 : 0;
+                for (int j = tid & 3; j < n_tot; j += 4) r += sh.k.a_key[j] > ki ? 1 : 0;
               }
               r += __shfl_xor_sync(0xffffffffu, r, 1);
               r += __shfl_xor_sync(0xffffffffu, r, 2);
               if (live && (tid & 3) == 0) {
-                sh.s_val[par][r] = key2f(static_cast<uint32_t>(ki >> 32));
-                sh.s_idx[par][r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(ki & 0xffffffffull));
+                sh.k.s_val[par][r] = key2f(static_cast<uint32_t>(ki >> 32));
+                sh.k.s_idx[par][r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(ki & 0xffffffffull));
               }
             }
           }
           ring_named_bar(1, CT);                                // sorted list complete
           if (tid == 0) {
-            sh.n_sorted[par] = ok ? n_tot : -1;
+            sh.k.n_sorted[par] = ok ? n_tot : -1;
             ring_arrive(&sh.sorted[par]);                        // hand the row over to the aux warp and go on
           }
           RING_PROF(7);
@@ -737,14 +748,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
             const float Mw = warp_max(m_t);
             const float sc = (m_t == -INFINITY) ? 0.f : s_t * ex2_ftz((m_t - Mw) * kLog2e);
             const double Sw = warp_sum(static_cast<double>(sc));
-            if (lane == 0) { sh.wm[warp] = Mw; sh.ws[warp] = Sw; }
+            if (lane == 0) { sh.d.wm[warp] = Mw; sh.d.ws[warp] = Sw; }
           }
           ring_named_bar(1, CT);
           // (lane w of every warp folds warp w's pair; the warp-wide butterflies have the same order in all warps, so M and z
           //  are bit-identical across the CTA)
-          const float mw = lane < CW ? sh.wm[lane] : -INFINITY;
+          const float mw = lane < CW ? sh.d.wm[lane] : -INFINITY;
           const float M = warp_max(mw);
-          const double zw = (lane < CW && mw > -INFINITY) ? sh.ws[lane] * static_cast<double>(ex2_ftz((mw - M) * kLog2e)) : 0.0;
+          const double zw = (lane < CW && mw > -INFINITY) ? sh.d.ws[lane] * static_cast<double>(ex2_ftz((mw - M) * kLog2e)) : 0.0;
           const double z = warp_sum(zw);
           const float logz = logf(static_cast<float>(z));
           if (!(z > 0.0) || isinf(logz) || logz != logz) { if (tid == 0) atomicOr(p.err_flag, kErrNanLogit); }   // (uniform condition)
@@ -752,7 +763,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           const bool do_sample = u_row >= 0.f;                   // row-uniform
           const int par = it & 1;
           if (it >= 2) mbar_wait(&sh.tfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);   // sampler is done with item it - 2
-          if (warp == 0) sh.info_c2[par] = c2;                   // (whole warp, same value: no single-lane branch in front of the warp reductions below)
+          if (warp == 0) sh.d.info_c2[par] = c2;                   // (whole warp, same value: no single-lane branch in front of the warp reductions below)
           // sampler weights  w = floor(p * 2^(40 - e)),  e = frexp exponent of the row maximum exp2(c2)
           const float scale = ldexpf(1.0f, kScaleBits - frexp_exp(ex2_ftz(c2)));
           const float scale_hi = scale * 9.5367431640625e-07f;              // 2^-20 * scale (exact)
@@ -766,7 +777,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           if (slot0n >= NS) { slot0n -= NS; ++wraps0n; }
           m_t = -INFINITY; nan_acc = -INFINITY; s2 = pack2(0.f, 0.f);
           if (next_row >= 0) car_u = p.u != nullptr ? __ldg(p.u + next_row) : -1.f;
-          // ---- pass B: probabilities out (16-byte streaming stores), exact weight sums per piece, slots released
+          // ---- pass B: probabilities out (16-byte streaming stores), exact weight sums per piece, slots released.
+          //      With fewer than 3 spare ring slots next to a row (fp32 V = 50272: none) the next row's chunk c can only be
+          //      requested once this row's chunk c + NCH - NS has been released: its pass A then lags `lag` chunks behind
+          //      pass B, so that a load has `lag` chunk-steps to land instead of being waited for right after its issue
+          const int lag = min(NCH, max(0, 3 - (NS - NCH)));
           for (int c = 0; c < NCH; ++c) {
             const int slot = slot_of(c);
             const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot));
@@ -822,12 +837,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               acc_hi -= static_cast<uint32_t>(E) * 0x4B000000u;
               acc_lo -= static_cast<uint32_t>(E) * 0x4B000000u;
               const uint32_t hs = __reduce_add_sync(0xffffffffu, acc_hi), ls = __reduce_add_sync(0xffffffffu, acc_lo);
-              if (lane == 0) sh.piece[par][c * CW + warp] = (static_cast<unsigned long long>(hs) << 20) + ls;
+              if (lane == 0) sh.d.piece[par][c * CW + warp] = (static_cast<unsigned long long>(hs) << 20) + ls;
             }
             __syncwarp();
             if (lane == 0) ring_arrive(&sh.empty[slot]);
-            if (next_row >= 0) pass_a(c, slot0n, wraps0n);
+            if (next_row >= 0 && c >= lag) pass_a(c - lag, slot0n, wraps0n);
           }
+          if (next_row >= 0)
+            for (int c = NCH - lag; c < NCH; ++c) pass_a(c, slot0n, wraps0n);
           __syncwarp();
           if (lane == 0) ring_arrive(&sh.row_done[par]);       // (release: this warp's stores and piece sums first)
           carried = next_row >= 0;

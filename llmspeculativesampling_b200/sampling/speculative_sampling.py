@@ -51,14 +51,17 @@ def _as_prompts(prefix) -> List[torch.Tensor]:
 
 
 def _run(prefix, approx_model, target_model, eos_token_id, max_len, gamma, temperature, top_k, top_p, random_seed,
-         details, uniforms, strict, use_cuda_graph, request_ids):
+         details, uniforms, strict, use_cuda_graph, request_ids, pad_batch=False):
     prompts = _as_prompts(prefix)
     B = len(prompts)
     device = prompts[0].device
     if device.type != "cuda":
         raise RuntimeError("speculative_sampling needs CUDA tensors/models: there is no CPU path")
     total = max(int(p.numel()) for p in prompts) + int(max_len)
-    eng = _engine_for(approx_model, target_model, B, total, gamma, temperature, top_k, top_p, device, strict,
+    # pad_batch (serving): the engine (static KV caches, probability buffers, captured graph) is keyed on the batch size, so
+    # arbitrary sizes from a request queue are rounded up to a power of two with dummy requests that may generate nothing
+    B_eng = 1 << (B - 1).bit_length() if pad_batch else B
+    eng = _engine_for(approx_model, target_model, B_eng, total, gamma, temperature, top_k, top_p, device, strict,
                       use_cuda_graph)
     if uniforms is None:
         if random_seed is not None:
@@ -68,11 +71,16 @@ def _run(prefix, approx_model, target_model, eos_token_id, max_len, gamma, tempe
             uniforms = torch.rand(int(max_len) + 1, B, uniform_tape.block(gamma))
     assert uniforms.shape[1] == B and uniforms.shape[2] == uniform_tape.block(gamma)
     tape_dev = uniforms.to(device=device, dtype=torch.float32)
+    new_tokens = [int(max_len)] * B
+    if B_eng > B:
+        tape_dev = torch.cat([tape_dev, tape_dev.new_zeros(tape_dev.shape[0], B_eng - B, tape_dev.shape[2])], dim=1)
+        prompts = prompts + [prompts[0][:2]] * (B_eng - B)
+        new_tokens = new_tokens + [0] * (B_eng - B)
     t0 = time.perf_counter_ns()
     try:
-        eng.load_prompts(prompts, int(max_len), eos_token_id)
+        eng.load_prompts(prompts, new_tokens, eos_token_id)
         iters = eng.run(tape_dev, profile_every=_PROFILE_EVERY if details else 0)
-        outs = eng.results(eos_token_id, device)
+        outs = eng.results(eos_token_id, device)[:B]
     except RuntimeError as e:
         if str(e) in ("norm logits error", "prob error", "s"):
             print(e)
@@ -82,8 +90,8 @@ def _run(prefix, approx_model, target_model, eos_token_id, max_len, gamma, tempe
     out = outs[0] if B == 1 else outs
     if not details:
         return out
-    acc = eng.acc_hist[:iters].cpu().numpy()                                # (iters, B), -1 where the request was idle
-    rat = eng.ratio_hist[:iters].cpu().numpy()
+    acc = eng.acc_hist[:iters, :B].cpu().numpy()                            # (iters, B), -1 where the request was idle
+    rat = eng.ratio_hist[:iters, :B].cpu().numpy()
     acc_len = [[int(a) for a in acc[:, b] if a >= 0] for b in range(B)]
     live = acc >= 0
     if strict:
@@ -117,7 +125,7 @@ def speculative_sampling(prefix: Union[torch.Tensor, Sequence[torch.Tensor]], ap
                          gamma: int = 4, temperature: float = 1, top_k: int = 0, top_p: float = 0,
                          verbose: bool = False, random_seed: int = None, details: bool = False, *,
                          uniforms: Optional[torch.Tensor] = None, use_cuda_graph: bool = True,
-                         request_ids: Optional[Sequence[int]] = None):
+                         request_ids: Optional[Sequence[int]] = None, pad_batch: bool = False):
     """Google / Leviathan speculative sampling with KV caches (reference :1877-2076).
 
     Positional order is the reference's: (prefix, approx_model, target_model, eos_token_id,
@@ -126,7 +134,7 @@ def speculative_sampling(prefix: Union[torch.Tensor, Sequence[torch.Tensor]], ap
     (the reference re-seeds torch before every accept draw, :1976-1977, which makes all its accept
     uniforms equal — that quirk is not reproduced)."""
     return _run(prefix, approx_model, target_model, eos_token_id, max_len, gamma, temperature, top_k, top_p,
-                random_seed, details, uniforms, False, use_cuda_graph, request_ids)
+                random_seed, details, uniforms, False, use_cuda_graph, request_ids, pad_batch)
 
 
 @torch.no_grad()

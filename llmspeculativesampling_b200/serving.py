@@ -54,7 +54,7 @@ class Server:
         self._served += len(prompts)
         outs = speculative_sampling(prompts, self._small_model, self._large_model, self.eos_token_id, self.pad_token_id,
                                     self.num_tokens, gamma=self.gamma, temperature=self.temperature, top_k=self.top_k,
-                                    top_p=self.top_p, random_seed=self.random_seed, request_ids=ids)
+                                    top_p=self.top_p, random_seed=self.random_seed, request_ids=ids, pad_batch=True)
         res = []
         for r, o in zip(requests, outs):
             o = o.reshape(-1)
