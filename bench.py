@@ -392,6 +392,31 @@ def config1_side_report():
             "leading_tokens_identical_to_cpu_run": agree, "of": same}
 
 
+def pin_to_gpu_numa_node(local: int):
+    """The e2e leg streams 73.7 MB of pinned host memory per step to the GPU; with N ranks on one box the pinned buffers of
+    a rank should live on the NUMA node its GPU hangs off (first touch), or all ranks pull through one socket's memory
+    controllers.  Restricts this process to the CPUs local to its GPU (sysfs `local_cpulist` of the PCI device); returns
+    a short description for the JSON line, None if the topology is not visible."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0"
+        cpus = open(os.path.join(path, "local_cpulist")).read().strip()
+        node = open(os.path.join(path, "numa_node")).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return {"numa_node": int(node), "cpus": cpus, "bound": len(ids)}
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,6 +453,8 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device (the B200 arm has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # (N > 1 only: at N = 1 the CPU baseline leg of this process must keep every host core)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None  # before any pinned allocation: first touch decides the node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -718,6 +745,7 @@ def main():
         "gpu_launches": (1 if args.fused else 2) * args.steps,
         "e2e": {"value": e2e_acc / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "h2d_GBs_per_gpu": h2d / (e2e_s / e2e_steps) / 1e9,
+                "host_affinity": numa,
                 "note": "double-buffered pinned-host -> device copies on a copy stream, results read back with events; "
                         "bound by the host link (73.7 MB of fp32 logits per step)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -1,3 +1,2 @@
-mkdir -p gpurun_out/r2z
-o=gpurun_out/r2z
-python -m pytest tests -m gpu -x -q > $o/pytest.log 2>&1; tail -4 $o/pytest.log
+mkdir -p gpurun_out/r2sw
+python tools/sweep.py > gpurun_out/r2sw/sweep_n1.jsonl 2> gpurun_out/r2sw/sweep_n1.err; wc -l gpurun_out/r2sw/sweep_n1.jsonl; tail -3 gpurun_out/r2sw/sweep_n1.err

@@ -1,9 +1,10 @@
 """BASELINE.json config 5: sweep of V x gamma x batch on synthetic logits, HBM roofline fraction per point.
 
     python tools/sweep.py [--full] > sweep.jsonl
+    torchrun --nproc-per-node 8 tools/sweep.py --subset headline > sweep_n8.jsonl     (replicas: slowest rank per point)
 
 Each point runs kernel 1 (sd_norm_sample: filter + softmax + draft token) over the B*(2*gamma+1) rows of one batch,
-T=0.8, top_k=20, top_p=0.9, inputs/outputs rotating over > 2x L2, CUDA-graph replays timed with CUDA events.
+T=0.8, top_k=20, top_p=0.9 (mode topk) or T=1, top_k=0, top_p=0 (mode dense, the API default), inputs/outputs rotating over > 2x L2, CUDA-graph replays timed with CUDA events.
 Algorithmic bytes = rows * V * (sizeof(logit) + 4).  Peak = MEASURED_PEAKS.json hbm_gbs.
 """
 import argparse
@@ -64,31 +65,62 @@ def point(V, gamma, B, dtype, peak, mode):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--subset", default="all", choices=["all", "headline"],
+                    help="headline: the B >= 64 points of V = 32000 / 50272 only (the multi-GPU run)")
     a = ap.parse_args()
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:                                             # N GPUs: every rank runs the same points (replicas, no collective
+        import torch.distributed as dist                      # in the path); a point reports its slowest rank
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build()
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except OSError:
         peak = 6650.0
     pts = []
-    for dtype in (torch.float32, torch.bfloat16):
-        for V in (32000, 50272, 65536, 131072, 262144):
-            for B in (1, 8, 64, 256, 512):
-                pts.append((V, 4, B, dtype, "topk"))
-        for gamma in (1, 2, 8, 16):
-            for B in ((1, 8, 64, 256, 512) if a.full else (64, 256)):
-                pts.append((32000, gamma, B, dtype, "topk"))
-    for B in (64, 256):
-        pts.append((32000, 4, B, torch.float32, "dense"))
-        pts.append((50272, 4, B, torch.bfloat16, "dense"))
+    if a.subset == "headline":
+        for dtype in (torch.float32, torch.bfloat16):
+            for mode in ("topk", "dense"):
+                for V in (32000, 50272):
+                    for B in (64, 256):
+                        pts.append((V, 4, B, dtype, mode))
+    else:
+        for dtype in (torch.float32, torch.bfloat16):
+            for V in (32000, 50272, 65536, 131072, 262144):
+                for B in (1, 8, 64, 256, 512):
+                    pts.append((V, 4, B, dtype, "topk"))
+            for V in (32000, 50272):
+                for gamma in (1, 2, 8, 16):
+                    for B in ((1, 8, 64, 256, 512) if a.full else (64, 256)):
+                        pts.append((V, gamma, B, dtype, "topk"))
+            for V in (32000, 50272, 131072):
+                for B in (8, 64, 256):
+                    pts.append((V, 4, B, dtype, "dense"))
+            for gamma in (1, 16):
+                pts.append((32000, gamma, 64, dtype, "dense"))
     for pt in pts:
         try:
             r = point(*pt[:4], peak, pt[4])
         except Exception as e:  # noqa: BLE001
             r = dict(V=pt[0], gamma=pt[1], batch=pt[2], dtype=str(pt[3]), mode=pt[4], error=str(e)[:100])
-        if r is not None:
+        if world > 1:
+            t = torch.tensor([r["ms"] if r is not None and "ms" in r else -1.0], dtype=torch.float64, device="cuda")
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            if r is not None and "ms" in r:
+                ms_all = [float(x) for x in allt]
+                worst = max(ms_all)
+                per_set = r["rows"] * r["V"] * ((4 if r["dtype"] == "float32" else 2) + 4)
+                r.update(n_gpus=world, ms_per_rank=[round(x, 4) for x in ms_all], ms=round(worst, 4), GBs=round(per_set / worst / 1e6, 1),
+                         frac_of_measured=round(per_set / worst / 1e6 / peak, 3), frac_of_8TBs=round(per_set / worst / 1e6 / 8000, 3),
+                         aggregate_GBs=round(world * per_set / worst / 1e6, 1))
+        if r is not None and rank == 0:
             print(json.dumps(r), flush=True)
         torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
