@@ -782,6 +782,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           //      requested once this row's chunk c + NCH - NS has been released: its pass A then lags `lag` chunks behind
           //      pass B, so that a load has `lag` chunk-steps to land instead of being waited for right after its issue
           const int lag = min(NCH, max(0, 3 - (NS - NCH)));
+          const bool out32 = want_probs && (reinterpret_cast<uintptr_t>(orow) & 31) == 0;
           for (int c = 0; c < NCH; ++c) {
             const int slot = slot_of(c);
             const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot));
@@ -826,10 +827,15 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               }
             }
             if (want_probs) {
+              if (PV == 8 && out32) {                            // 16-bit logits: 8 floats per vector = one 32-byte sector per thread
+                if (ok0) st_cs_v8(orow + static_cast<long long>(v0) * PV, o);
+                if (ok1) st_cs_v8(orow + static_cast<long long>(v0 + 32) * PV, o + PV);
+              } else {
 #pragma unroll
-              for (int j = 0; j < PV; j += 4) {
-                if (ok0) st_cs_v4(orow + static_cast<long long>(v0) * PV + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
-                if (ok1) st_cs_v4(orow + static_cast<long long>(v0 + 32) * PV + j, o[PV + j], o[PV + j + 1], o[PV + j + 2], o[PV + j + 3]);
+                for (int j = 0; j < PV; j += 4) {
+                  if (ok0) st_cs_v4(orow + static_cast<long long>(v0) * PV + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+                  if (ok1) st_cs_v4(orow + static_cast<long long>(v0 + 32) * PV + j, o[PV + j], o[PV + j + 1], o[PV + j + 2], o[PV + j + 3]);
+                }
               }
             }
             if (do_sample) {

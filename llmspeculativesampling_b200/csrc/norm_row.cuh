@@ -492,8 +492,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
         for (int v = tid; v < nfull; v += THREADS) {
           float pr[PV];
           vec_probs(v, pr);
-#pragma unroll
-          for (int j = 0; j < PV; j += 4) st_cs_v4(o + v * PV + j, pr[j], pr[j + 1], pr[j + 2], pr[j + 3]);
+          st_cs_vec<PV>(o + v * PV, pr);
         }
         for (int v = nfull + tid; v < n_vec; v += THREADS) {
           float pr[PV];
@@ -517,8 +516,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
 #pragma unroll
         for (int j = 0; j < PV; ++j) lane_w += weight_of(pr[j], e);
         if (v < nfull) {
-#pragma unroll
-          for (int j = 0; j < PV; j += 4) st_cs_v4(o + v * PV + j, pr[j], pr[j + 1], pr[j + 2], pr[j + 3]);
+          st_cs_vec<PV>(o + v * PV, pr);
         } else if (want_probs) {
           for (int j = 0; j < PV; ++j) if (v * PV + j < n) o[v * PV + j] = pr[j];
         }
@@ -629,8 +627,7 @@ __device__ __forceinline__ void norm_row(const NormParams& p, const int row) {
       for (int v = tid; v < nfull; v += THREADS) {
         float pr[PV];
         vec_probs(v, pr);
-#pragma unroll
-        for (int j = 0; j < PV; j += 4) st_cs_v4(o + v * PV + j, pr[j], pr[j + 1], pr[j + 2], pr[j + 3]);
+        st_cs_vec<PV>(o + v * PV, pr);
       }
       for (int v = nfull + tid; v < n_vec; v += THREADS) {
         float pr[PV];

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) verify_row_kernel(const Verify
   float* row = reinterpret_cast<float*>(smem_raw);
   RowSampleShared& sh = *reinterpret_cast<RowSampleShared*>(smem_raw + ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)));
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();                                                   // (launched with programmatic stream serialization)
   if (p.active != nullptr && p.active[b] == 0) return;
   const bool has_q = p.q != nullptr;
   // ---- accept scan: lane i tests drafted token i (speculative_sampling.py:1975-1990)
@@ -638,8 +639,16 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
     static bool attr_dev[64] = {};
     cudaError_t e = set_row_smem(verify_row_kernel, attr_dev);
     if (e != cudaSuccess) return e;
-    verify_row_kernel<<<static_cast<unsigned>(p.B), kRowThreads, row_sample_smem(p.V), st>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t rcfg = {};
+    rcfg.gridDim = dim3(static_cast<unsigned>(p.B));
+    rcfg.blockDim = dim3(kRowThreads);
+    rcfg.dynamicSmemBytes = row_sample_smem(p.V);
+    rcfg.stream = st;
+    cudaLaunchAttribute rat[1];
+    rat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    rat[0].val.programmaticStreamSerializationAllowed = 1;
+    rcfg.attrs = rat; rcfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&rcfg, verify_row_kernel, p);
   }
   const long long row_bytes = p.V * 4;
   int C = 1;

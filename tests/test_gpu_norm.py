@@ -120,6 +120,20 @@ def test_minus_inf_and_strided_rows(cuda_lib):
         assert float(got[:, 100:2000].abs().sum()) == 0.0
 
 
+def test_dense_16bit_rows_with_output_rows_not_32_byte_aligned(cuda_lib):
+    """16-bit logits on the dense ring kernel write 8 floats per thread with one 32-byte store when the output row is
+    32-byte aligned and with two 16-byte stores otherwise: both give the same rows."""
+    from llmspeculativesampling_b200 import ops
+    V, rows = 4096, 7
+    x = make_logits(rows, V, 2.0, 3, dtype=torch.bfloat16).cuda()
+    want = ops.norm_probs(x, 0.9, 0, 0.0)
+    wide = torch.full((rows, V + 4), -1.0, device="cuda")        # row stride 4100 floats: rows 1, 3, 5 are only 16-byte aligned
+    got = ops.norm_probs(x, 0.9, 0, 0.0, out=wide[:, :V])
+    ops.default_flag("cuda").check()
+    assert torch.equal(got, want) and bool((wide[:, V:] == -1.0).all())
+    assert compare_probs(got, oracle_probs(x.cpu(), 0.9, 0, 0.0), "bf16 dense, strided output") == 0
+
+
 def test_nan_logit_raises_like_reference(cuda_lib):
     from llmspeculativesampling_b200 import ops
     x = make_logits(2, 1000, 1.0, 1)

@@ -1,2 +1,5 @@
-mkdir -p gpurun_out/r2sw
-python tools/sweep.py > gpurun_out/r2sw/sweep_n1.jsonl 2> gpurun_out/r2sw/sweep_n1.err; wc -l gpurun_out/r2sw/sweep_n1.jsonl; tail -3 gpurun_out/r2sw/sweep_n1.err
+mkdir -p gpurun_out/r3c
+o=gpurun_out/r3c
+python -m pytest tests -m gpu -x -q > $o/pytest.log 2>&1; tail -3 $o/pytest.log
+python tools/sweep.py > $o/sweep_n1.jsonl 2> $o/sweep.err; grep -c . $o/sweep_n1.jsonl
+grep '"dense"' $o/sweep_n1.jsonl | cut -c1-170
