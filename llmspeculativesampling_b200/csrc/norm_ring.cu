@@ -57,7 +57,10 @@ bool plan_ring(NormParams& p, int dtype, int rows) {
   int slots = static_cast<int>((static_cast<size_t>(smem_max) - fixed) / kRingChunkBytes) - extra;
   if (slots > kRingMaxSlots) slots = kRingMaxSlots;
   const int n_chunks = static_cast<int>((row_bytes + kRingChunkBytes - 1) / kRingChunkBytes);
-  if (slots < 2 || n_chunks > slots) return false;
+  // DENSE rows longer than the ring are streamed through it twice (max / sum pass, write pass; the second read is an L2 hit)
+  const bool long_rows = mode == kRingDense && n_chunks > slots;
+  if (slots < 2 || (n_chunks > slots && !long_rows) || n_chunks > kRingMaxLongChunks) return false;
+  p.ring_long = long_rows ? 1 : 0;
   const size_t shared_off = static_cast<size_t>(slots + extra) * kRingChunkBytes;
   // in-kernel general-path fallback (norm_row with the whole row in this CTA) must fit in front of the deferred-row list
   const long long slice = (p.V + 127) & ~127LL;

@@ -37,7 +37,8 @@ constexpr int kRingCap = 256;                               // merged candidates
 constexpr int kRingWarpCap = 48;                            // candidates one warp may collect per row
 constexpr int kRingMaxFail = 192;                           // rows per round that may be deferred to the general path
 constexpr int kRingFailSlack = 40;
-constexpr int kRingMaxPieces = kRingMaxSlots * kRingComputeWarps;   // (chunk, warp) pieces of 64 vectors
+constexpr int kRingMaxLongChunks = 64;                      // DENSE rows longer than the ring (streamed twice): up to 1 MB per row
+constexpr int kRingMaxPieces = kRingMaxLongChunks * kRingComputeWarps;   // (chunk, warp) pieces of 64 vectors
 constexpr int kRingEndDone = -1, kRingEndPause = -2;
 constexpr uint32_t kRingTieUlps = 8;
 
@@ -179,7 +180,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           if (row < 0) { sh.end_reason = row; break; }
           const int next = draw();                             // (latency hidden behind this row's loads)
           const unsigned char* src = reinterpret_cast<const unsigned char*>(p.logits) + static_cast<size_t>(row) * p.ld_in * sizeof(T);
-          for (int c = 0; c < NCH; ++c) {
+          // (a DENSE row longer than the ring is streamed twice: once for the max / sum pass, once for the write pass — the
+          //  second read of the 148 rows in flight comes from the 126 MB L2)
+          for (int cc = 0; cc < (p.ring_long ? 2 * NCH : NCH); ++cc) {
+            const int c = cc >= NCH ? cc - NCH : cc;
             if (wraps > 0) mbar_wait(&sh.empty[slot], static_cast<uint32_t>(wraps - 1) & 1u);
             const uint32_t off = static_cast<uint32_t>(c) * kRingChunkBytes;
             const uint32_t bytes = min(static_cast<uint32_t>(kRingChunkBytes), row_bytes - off);
@@ -443,6 +447,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
       // =========================================================================== compute warps
       int slot0 = 0, wraps0 = 0;                                // ring position of the current row's first chunk
       // DENSE: pass A of row it + 1 runs inside pass B of row it (see below); its per-thread results are carried over
+      int cur_slot = 0, cur_wraps = 0;                          // DENSE long rows: ring cursor (chunks are consumed strictly in ring order)
+      const bool long_rows = MODE != kRingTopK && p.ring_long != 0;
       float car_m = -INFINITY, car_nan = -INFINITY, car_u = -1.f;
       f32x2 car_s2 = 0ull;
       bool carried = false;
@@ -686,7 +692,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           //      writes HBM at the same time instead of in alternating phases.
           float m_t = -INFINITY, nan_acc = -INFINITY;
           f32x2 s2 = pack2(0.f, 0.f);
-          auto pass_a = [&](int c, int s0, int w0) {
+          auto pass_a = [&](int c, int s0, int w0, bool release) {
             int sl = s0 + c;
             const bool wrapped = sl >= NS;
             if (wrapped) sl -= NS;
@@ -731,13 +737,24 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               for (int j = 0; j < w; ++j) acc[j] = add2(acc[j], acc[j + w]);
             }
             s2 = fma2(s2, pack2(resc, resc), acc[0]);
+            if (release) {                                       // long rows: the chunk comes back for pass B in a later slot
+              __syncwarp();
+              if (lane == 0) ring_arrive(&sh.empty[sl]);
+            }
           };
           float u_row;
           if (carried) {                                         // scanned while the previous row was written out
             m_t = car_m; nan_acc = car_nan; s2 = car_s2; u_row = car_u;
           } else {
             u_row = p.u != nullptr ? __ldg(p.u + row) : -1.f;    // (requested now, needed after pass A)
-            for (int c = 0; c < NCH; ++c) pass_a(c, slot0, wraps0);
+            if (long_rows) {
+              for (int c = 0; c < NCH; ++c) {
+                pass_a(c, cur_slot - c, cur_wraps, true);        // (slot = cursor, no wrap arithmetic inside)
+                if (++cur_slot == NS) { cur_slot = 0; ++cur_wraps; }
+              }
+            } else {
+              for (int c = 0; c < NCH; ++c) pass_a(c, slot0, wraps0, false);
+            }
           }
           if (nan_acc != nan_acc || nan_acc == INFINITY) atomicOr(p.err_flag, kErrNanLogit);
           float s_t;
@@ -771,8 +788,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           const f32x2 k23 = pack2(8388608.0f, 8388608.0f), m1 = pack2(-1.0f, -1.0f), k20 = pack2(1048576.0f, 1048576.0f);
           RING_PROF(2);
           // the row after this one (the loader published it while it issued this row's loads): its pass A is interleaved below
-          mbar_wait(&sh.rowfull[(it + 1) % kRingItemRing], static_cast<uint32_t>((it + 1) / kRingItemRing) & 1u);
-          const int next_row = *reinterpret_cast<volatile int*>(&sh.row_of[(it + 1) % kRingItemRing]);
+          int next_row = -1;
+          if (!long_rows) {
+            mbar_wait(&sh.rowfull[(it + 1) % kRingItemRing], static_cast<uint32_t>((it + 1) / kRingItemRing) & 1u);
+            next_row = *reinterpret_cast<volatile int*>(&sh.row_of[(it + 1) % kRingItemRing]);
+          }
           int slot0n = slot0 + NCH, wraps0n = wraps0;
           if (slot0n >= NS) { slot0n -= NS; ++wraps0n; }
           m_t = -INFINITY; nan_acc = -INFINITY; s2 = pack2(0.f, 0.f);
@@ -784,7 +804,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           const int lag = min(NCH, max(0, 3 - (NS - NCH)));
           const bool out32 = want_probs && (reinterpret_cast<uintptr_t>(orow) & 31) == 0;
           for (int c = 0; c < NCH; ++c) {
-            const int slot = slot_of(c);
+            int slot;
+            if (long_rows) {                                     // second trip of the chunk through the ring
+              slot = cur_slot;
+              mbar_wait(&sh.full[slot], static_cast<uint32_t>(cur_wraps) & 1u);
+              if (++cur_slot == NS) { cur_slot = 0; ++cur_wraps; }
+            } else {
+              slot = slot_of(c);
+            }
             const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot));
             const int v0 = c * kRingVecPerChunk + vl0;
             bool ok0 = true, ok1 = true;
@@ -847,10 +874,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
             }
             __syncwarp();
             if (lane == 0) ring_arrive(&sh.empty[slot]);
-            if (next_row >= 0 && c >= lag) pass_a(c - lag, slot0n, wraps0n);
+            if (next_row >= 0 && c >= lag) pass_a(c - lag, slot0n, wraps0n, false);
           }
           if (next_row >= 0)
-            for (int c = NCH - lag; c < NCH; ++c) pass_a(c, slot0n, wraps0n);
+            for (int c = NCH - lag; c < NCH; ++c) pass_a(c, slot0n, wraps0n, false);
           __syncwarp();
           if (lane == 0) ring_arrive(&sh.row_done[par]);       // (release: this warp's stores and piece sums first)
           carried = next_row >= 0;

@@ -47,7 +47,7 @@ struct NormParams {
   int pipe_buffers, pipe_cap, pipe_clusters;             // ... merged-candidate capacity, clusters in the persistent grid
   // ring kernel (norm_ring.cu): one persistent CTA per SM, whole rows streamed through a ring of 16 KB chunks
   int no_ring;                             // caller asked for the older kernels (SD_NORM_NO_RING)
-  int ring_mode, ring_slots, ring_smem_bytes, ring_ctas, ring_shared_off, ring_early, ring_trigger;
+  int ring_mode, ring_slots, ring_smem_bytes, ring_ctas, ring_shared_off, ring_early, ring_trigger, ring_long;
   int ring_row_elems, ring_row_smem_bytes; // geometry of the in-kernel general-path fallback (whole row in one CTA)
   const int* row_filter;                   // norm_probs_kernel: process only rows with row_filter[row] != 0
   // pipelined kernel, optional: verify request b as soon as its fv_rows rows (b * fv_rows ..) are all normalised

@@ -233,7 +233,10 @@ def test_pipeline_kernel_dynamic_rows_and_deferred_rows(cuda_lib, V, rows, n_tie
 
 
 @pytest.mark.parametrize("V,dtype,rows,T", [(32000, torch.float32, 576, 1.0), (50272, torch.bfloat16, 300, 0.8), (32000, torch.float16, 149, 1.3),
-                                            (50272, torch.float32, 160, 1.0), (4096, torch.float32, 5000, 0.7), (1000, torch.bfloat16, 40, 1.0)])
+                                            (50272, torch.float32, 160, 1.0), (4096, torch.float32, 5000, 0.7), (1000, torch.bfloat16, 40, 1.0),
+                                            # rows longer than the ring: streamed through it twice
+                                            (65536, torch.float32, 200, 0.9), (131072, torch.bfloat16, 160, 1.0),
+                                            (151936, torch.float32, 20, 1.0), (262144, torch.float32, 5, 0.8)])
 def test_ring_kernel_dense_rows_with_sampling(cuda_lib, V, dtype, rows, T):
     """Dense rows (top_k = 0, top_p = 0 — the reference API's default, speculative_sampling.py:1879-1880) on the ring
     kernel: probabilities against the oracle, the sampled token bit-exact against the inverse-CDF rule applied to the
