@@ -297,22 +297,26 @@ def run_variants(args):
                 "b200": {"seconds": gpu_s, "emitted_tokens_per_s": (tok.shape[1] - 16) / gpu_s, "target_calls": d["target_call_times"],
                          "draft_tokens": d["approx_call_times"]},
                 "leading_tokens_identical_to_cpu_run": a, "of": n})
-    # ---- the same two rows with 16 requests in flight (ragged prompts, one CUDA graph per iteration / check cycle)
-    Bq = 16
-    gq = torch.Generator().manual_seed(11)
-    prompts = [torch.randint(3, 32000, (int(n),), generator=gq).cuda() for n in torch.randint(8, 24, (Bq,), generator=gq)]
-    tape_m = torch.rand(N + 1, Bq, spec_loop.multi_block(GAMMA, W), generator=gq)
-    tape_b = uniform_tape.batch_tape(5, list(range(Bq)), N + 1, GAMMA)
+    # ---- the same two rows with 16 and 64 requests in flight (ragged prompts, one CUDA graph per iteration / check cycle)
     batched = []
-    for name, fn in (("N2 multi_speculative_sampling(strategy='iid'), width 4", lambda: multi_speculative_sampling(
-                          prompts, dg, tg, None, None, N, GAMMA, W, None, "iid", None, 0.4, 1.0, k, p, uniforms=tape_m)),
-                     ("N3 BiLD_sampling", lambda: BiLD_sampling(prompts, dg, tg, GAMMA, None, None, fb, rb, N, 1.0, k, p, uniforms=tape_b))):
-        fn()                                                   # engine construction + graph capture
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        outs = fn()
-        torch.cuda.synchronize(); dt = time.perf_counter() - t0
-        emitted = sum(o.shape[1] - pr.numel() for o, pr in zip(outs, prompts))
-        batched.append({"row": name, "requests_in_flight": Bq, "seconds": dt, "emitted_tokens_per_s": emitted / dt})
+    for Bq in (16, 64):
+        gq = torch.Generator().manual_seed(11)
+        prompts = [torch.randint(3, 32000, (int(n),), generator=gq).cuda() for n in torch.randint(8, 24, (Bq,), generator=gq)]
+        tape_m = torch.rand(N + 1, Bq, spec_loop.multi_block(GAMMA, W), generator=gq)
+        tape_b = uniform_tape.batch_tape(5, list(range(Bq)), N + 1, GAMMA)
+        for name, fn in (("N2 multi_speculative_sampling(strategy='iid'), width 4", lambda: multi_speculative_sampling(
+                              prompts, dg, tg, None, None, N, GAMMA, W, None, "iid", None, 0.4, 1.0, k, p, uniforms=tape_m, details=True)),
+                         ("N3 BiLD_sampling", lambda: BiLD_sampling(prompts, dg, tg, GAMMA, None, None, fb, rb, N, 1.0, k, p, uniforms=tape_b,
+                                                                    details=True))):
+            fn()                                                   # engine construction + graph capture
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            outs, det = fn()
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            emitted = sum(o.shape[1] - pr.numel() for o, pr in zip(outs, prompts))
+            its = det.get("iterations", det.get("target_call_times"))
+            its = max(its) if isinstance(its, (list, tuple)) else its
+            batched.append({"row": name, "requests_in_flight": Bq, "seconds": dt, "emitted_tokens_per_s": emitted / dt,
+                            "graph_iterations": its, "ms_per_iteration": dt / max(int(its or 1), 1) * 1e3})
     print(json.dumps({"workload": "SURVEY 8f next rows on the config-1 models (llama-68m shapes, identical weights, fp32, batch 1, 64 new tokens)",
                       "note": "both run on their batched CUDA-graph engines (multi_engine.MultiDraftEngine, bild_engine.BiLDEngine), batch 1 here",
                       "results": out, "batched": batched}))
