@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SD_VERSION 200
+#define SD_VERSION 210
 #define SD_OK 0
 #define SD_EINVAL (-1)
 
@@ -96,11 +96,14 @@ int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_
                   void* workspace, void* stream);
 
 /* `workspace` of the two norm entry points: SD_NORM_WORKSPACE_BYTES of device memory, zeroed ONCE by the caller.  The
- * persistent kernel hands rows to its clusters through a ticket counter that lives there (SMs run at visibly different
- * speeds under full HBM load; a static split waits for the slowest) and leaves it zeroed when it ends, so the same
- * block serves any number of launches that are ordered after one another (one stream, one CUDA graph).  Launches that
- * may run CONCURRENTLY must use different blocks.  NULL is always safe: it selects the one-cluster-per-row kernel. */
-#define SD_NORM_WORKSPACE_BYTES 16
+ * persistent kernels hand rows to their CTAs through a ticket counter that lives in its first 16 bytes (SMs run at
+ * visibly different speeds under full HBM load; a static split waits for the slowest); the rest is one bit per row
+ * (up to 65536 rows per call) in which the ring kernel flags the top-k rows LONGER than its shared-memory ring that its
+ * fast selection cannot serve (massive ties) for the follow-up launch of the general path.  Every launch leaves the
+ * block zeroed when it ends, so the same block serves any number of launches that are ordered after one another (one
+ * stream, one CUDA graph).  Launches that may run CONCURRENTLY must use different blocks.  NULL is always safe: it
+ * selects the one-cluster-per-row kernel. */
+#define SD_NORM_WORKSPACE_BYTES (16 + 65536 / 8)
 
 /* `flags` of the two norm entry points.  By default, for 0 < top_k <= 128 and 16-byte aligned rows the persistent,
  * warp-specialised pipeline kernel runs if a `workspace` is given (one CTA per SM: a memory warp streams slices in by TMA and zero-fills the

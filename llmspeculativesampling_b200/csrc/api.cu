@@ -66,6 +66,8 @@ static int fill_norm(const void* logits, int dtype, int64_t rows, int64_t V, int
   p.no_pipeline = ((flags & SD_NORM_NO_PIPELINE) || workspace == nullptr) ? 1 : 0;
   p.no_ring = (flags & SD_NORM_NO_RING) ? 1 : 0;
   p.sched = static_cast<unsigned int*>(workspace);
+  p.defer_bitmap = workspace != nullptr ? static_cast<unsigned int*>(workspace) + 4 : nullptr;   // (SD_NORM_WORKSPACE_BYTES = 16 + bitmap)
+  p.use_defer_bitmap = 0;
   return SD_OK;
 }
 

@@ -34,9 +34,14 @@ __global__ void __launch_bounds__(THREADS, MINB) norm_probs_kernel(const NormPar
   bool first = true;
   for (int row = cid; row < p.rows; row += n_cl) {
     if (p.row_filter != nullptr && p.row_filter[row] == 0) continue;     // uniform across the cluster
+    if (p.use_defer_bitmap && ((p.defer_bitmap[row >> 5] >> (row & 31)) & 1u) == 0u) continue;   // (uniform as well)
     if (!first) __syncthreads();                                          // shared memory / mbarriers are reused
     first = false;
     norm_row<T, THREADS>(p, row);
+    if (p.use_defer_bitmap) {                                             // served: clear the flag for the next launch
+      if (C > 1) cg::this_cluster().sync(); else __syncthreads();         // (every CTA of the cluster has read the bit)
+      if (threadIdx.x == 0 && blockIdx.x % C == 0) atomicAnd(p.defer_bitmap + (row >> 5), ~(1u << (row & 31)));
+    }
   }
 }
 
@@ -66,7 +71,7 @@ static cudaError_t launch_cfg(const NormParams& p, size_t smem, int rows, cudaSt
   }
   cudaLaunchConfig_t cfg = {};
   int n_cl = rows;
-  if (p.row_filter != nullptr) n_cl = min(rows, max(1, device_sm_count() / p.cluster));   // follow-up mode: walk the rows
+  if (p.row_filter != nullptr || p.use_defer_bitmap) n_cl = min(rows, max(1, device_sm_count() / p.cluster));   // follow-up mode: walk the rows
   cfg.gridDim = dim3(static_cast<unsigned>(n_cl) * p.cluster);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem;
@@ -134,7 +139,19 @@ cudaError_t launch_norm(const NormParams& pin, int dtype, int rows, cudaStream_t
   p.fv_rows = 0;
   // ring kernel (one persistent CTA per SM, whole rows through a shared-memory ring) where a row fits one CTA;
   // else the persistent cluster pipeline where it applies (both fall back to the general path per row by themselves)
-  if (g_tune_threads == 0 && g_tune_cluster == 0 && plan_ring(p, dtype, rows)) return launch_norm_ring(p, dtype, st);
+  if (g_tune_threads == 0 && g_tune_cluster == 0 && plan_ring(p, dtype, rows)) {
+    cudaError_t e = launch_norm_ring(p, dtype, st);
+    if (e != cudaSuccess || !(p.ring_long && p.ring_mode == 0)) return e;
+    // top-k rows longer than the ring: the rows the ring kernel flagged (massive ties) are re-run on the general path by a
+    // small persistent grid of the one-cluster-per-row kernel that walks the bitmap (no host round trip: always launched)
+    NormParams f = pin;
+    f.prof = nullptr;
+    f.row_filter = nullptr;
+    f.fv_rows = 0;
+    f.use_defer_bitmap = 1;
+    f.force_general = 1;
+    return launch_classic(f, dtype, rows, st);
+  }
   if (g_tune_threads == 0 && !p.no_pipeline && plan_pipe(p, dtype, rows, g_tune_cluster)) return launch_norm_pipe(p, dtype, rows, st);
   return launch_classic(p, dtype, rows, st);
 }

@@ -58,14 +58,20 @@ bool plan_ring(NormParams& p, int dtype, int rows) {
   if (slots > kRingMaxSlots) slots = kRingMaxSlots;
   const int n_chunks = static_cast<int>((row_bytes + kRingChunkBytes - 1) / kRingChunkBytes);
   // DENSE rows longer than the ring are streamed through it twice (max / sum pass, write pass; the second read is an L2 hit)
-  const bool long_rows = mode == kRingDense && n_chunks > slots;
+  // TOPK rows longer than the ring: pass 1 releases every chunk at once, pass 2 fetches a thread's one or two hot vectors
+  // from global memory (L2); rows the fast selection cannot serve are flagged in the workspace bitmap and re-run by a
+  // follow-up launch of the one-cluster-per-row kernel (launch_norm) — needs one bit per row in the workspace
+  // (measured at 576 rows: up to 16 chunks the cluster pipeline is as fast or faster — 45.5 vs 53.5 us at fp32 V = 50272,
+  //  82.7 vs 85.4 us at bf16 V = 131072 —, from 32 chunks on the ring wins: 113 vs 151 us at fp32 V = 131072, 212 vs 654 us
+  //  at fp32 V = 262144)
+  const bool long_rows = n_chunks > slots && (mode == kRingDense || (rows <= kDeferBitmapRows && n_chunks >= 24));
   if (slots < 2 || (n_chunks > slots && !long_rows) || n_chunks > kRingMaxLongChunks) return false;
   p.ring_long = long_rows ? 1 : 0;
   const size_t shared_off = static_cast<size_t>(slots + extra) * kRingChunkBytes;
   // in-kernel general-path fallback (norm_row with the whole row in this CTA) must fit in front of the deferred-row list
   const long long slice = (p.V + 127) & ~127LL;
   const size_t slice_bytes = (static_cast<size_t>(slice) * es + 127) & ~static_cast<size_t>(127);
-  if (mode == kRingTopK && slice_bytes + sizeof(NormShared<kRingThreads>) > shared_off + offsetof(RingShared, fail_rows)) return false;
+  if (mode == kRingTopK && !long_rows && slice_bytes + sizeof(NormShared<kRingThreads>) > shared_off + offsetof(RingShared, fail_rows)) return false;
   // pivot taken while the row's last chunks are still in flight: pays for rows of >= 7 chunks (measured: 8 chunks 31.9 -> 31.2 us,
   // 7 chunks 36.1 -> 35.0 us at 576 rows; rows of 4 chunks lose: the early pivot is too weak there)
   { const char* ev = getenv("SD_RING_EARLY"); p.ring_early = ev != nullptr ? atoi(ev) : (n_chunks >= 7 ? 3 : 0); }

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           const unsigned char* src = reinterpret_cast<const unsigned char*>(p.logits) + static_cast<size_t>(row) * p.ld_in * sizeof(T);
           // (a DENSE row longer than the ring is streamed twice: once for the max / sum pass, once for the write pass — the
           //  second read of the 148 rows in flight comes from the 126 MB L2)
-          for (int cc = 0; cc < (p.ring_long ? 2 * NCH : NCH); ++cc) {
+          for (int cc = 0; cc < ((MODE != kRingTopK && p.ring_long) ? 2 * NCH : NCH); ++cc) {
             const int c = cc >= NCH ? cc - NCH : cc;
             if (wraps > 0) mbar_wait(&sh.empty[slot], static_cast<uint32_t>(wraps - 1) & 1u);
             const uint32_t off = static_cast<uint32_t>(c) * kRingChunkBytes;
@@ -344,7 +344,13 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               for (int i = lane; i < np_out; i += 32) orow[si[i]] = sh.k.f_val[i];
             }
           } else if (lane == 0) {
-            sh.fail_rows[atomicAdd(&sh.n_fail, 1)] = row;         // deferred to the general path (runs after the ring has drained)
+            if (p.ring_long) {
+              // a row longer than the ring cannot be re-run by this CTA: flag it in the caller's workspace; the follow-up
+              // launch of the one-cluster-per-row kernel (general path) serves the flagged rows
+              atomicOr(p.defer_bitmap + (row >> 5), 1u << (row & 31));
+            } else {
+              sh.fail_rows[atomicAdd(&sh.n_fail, 1)] = row;       // deferred to the general path (runs after the ring has drained)
+            }
             if (want_probs) tma_store_wait_all();                 // its zero fill must not land after the general path's writes
           }
           __syncwarp();
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
       int slot0 = 0, wraps0 = 0;                                // ring position of the current row's first chunk
       // DENSE: pass A of row it + 1 runs inside pass B of row it (see below); its per-thread results are carried over
       int cur_slot = 0, cur_wraps = 0;                          // DENSE long rows: ring cursor (chunks are consumed strictly in ring order)
-      const bool long_rows = MODE != kRingTopK && p.ring_long != 0;
+      const bool long_rows = p.ring_long != 0;                   // rows longer than the ring (DENSE: streamed twice; TOPK: pass 2 from L2)
       float car_m = -INFINITY, car_nan = -INFINITY, car_u = -1.f;
       f32x2 car_s2 = 0ull;
       bool carried = false;
@@ -472,8 +478,16 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           int i1 = 0, i2 = 0;
           float nan_acc = -INFINITY;
           auto scan_chunk = [&](int c) {
-            wait_chunk(c);
-            const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(slot_of(c)));
+            int sl;
+            if (long_rows) {                                     // chunks are consumed strictly in ring order
+              sl = cur_slot;
+              mbar_wait(&sh.full[sl], static_cast<uint32_t>(cur_wraps) & 1u);
+              if (++cur_slot == NS) { cur_slot = 0; ++cur_wraps; }
+            } else {
+              wait_chunk(c);
+              sl = slot_of(c);
+            }
+            const uint4* s4 = reinterpret_cast<const uint4*>(slot_ptr(sl));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int vl = h * CT + tid;
@@ -489,6 +503,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               m2 = fmaxf(m2, lo1);
               i2 = c1 ? i1 : (c2 ? v : i2);
               i1 = c1 ? v : i1;
+            }
+            if (long_rows) {                                     // the row does not stay resident: pass 2 re-reads its few hot
+              __syncwarp();                                      // vectors from global memory (L2)
+              if (lane == 0) ring_arrive(&sh.empty[sl]);
             }
           };
           // The pivot is taken EARLY, from the chunks that have landed when about a quarter of the row is still in flight:
@@ -549,7 +567,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           // ---- pass 2: every element >= pivot of the threads whose maximum reaches it goes straight into the row's candidate
           //      array (sort keys: value key << 32 | ~index); a warp allocates its slots with one shared-memory atomic
           const int par = it & 1;
-          auto vec_at = [&](int v) { return reinterpret_cast<const uint4*>(slot_ptr(slot_of(v >> 10)))[v & (kRingVecPerChunk - 1)]; };
+          const uint4* grow = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.logits) +
+                                                             static_cast<size_t>(row) * p.ld_in * sizeof(T));
+          auto vec_at = [&](int v) {
+            return long_rows ? ld_nc_v4(grow + v)
+                             : reinterpret_cast<const uint4*>(slot_ptr(slot_of(v >> 10)))[v & (kRingVecPerChunk - 1)];
+          };
           static_assert(kRingVecPerChunk == 1024, "vec_at assumes 1024 vectors per chunk");
           auto key_of = [&](float logit, int idx) {
             const float xv = __fdiv_rn(logit, temp) + 0.0f;        // logit / T;  -0 -> +0: equal values tie on the index
@@ -629,7 +652,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           }
           // the row's logits are no longer needed: hand the ring slots back to the loader
           __syncwarp();
-          if (lane == 0)
+          if (lane == 0 && !long_rows)
             for (int c = 0; c < NCH; ++c) ring_arrive(&sh.empty[slot_of(c)]);
           // the aux warp must be done with the sorted list of item it - 2 before the rank sort below overwrites it
           if (it >= 2) mbar_wait(&sh.sfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);

@@ -50,6 +50,8 @@ struct NormParams {
   int ring_mode, ring_slots, ring_smem_bytes, ring_ctas, ring_shared_off, ring_early, ring_trigger, ring_long;
   int ring_row_elems, ring_row_smem_bytes; // geometry of the in-kernel general-path fallback (whole row in one CTA)
   const int* row_filter;                   // norm_probs_kernel: process only rows with row_filter[row] != 0
+  unsigned int* defer_bitmap;              // workspace + 16: one bit per row the ring kernel could not serve (rows longer than the ring);
+  int use_defer_bitmap;                    // norm_probs_kernel: process (and clear) only the flagged rows
   // pipelined kernel, optional: verify request b as soon as its fv_rows rows (b * fv_rows ..) are all normalised
   int fv_rows;                             // 0: disabled
   int* fv_cnt;                             // (B,) finished-row counters, zero between launches
@@ -63,6 +65,7 @@ void set_norm_prof(long long* ptr);
 void set_pdl(int enable);
 int pdl_enabled();
 bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster);
+constexpr int kDeferBitmapRows = 65536;  // rows the workspace bitmap covers (SD_NORM_WORKSPACE_BYTES = 16 + kDeferBitmapRows / 8)
 bool plan_ring(NormParams& p, int dtype, int rows);
 cudaError_t launch_norm_ring(const NormParams& p, int dtype, cudaStream_t st);
 int device_sm_count();                    // multiprocessors of the current device (cached per device)

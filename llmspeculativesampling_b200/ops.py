@@ -31,6 +31,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+NORM_WORKSPACE_BYTES = 16 + 65536 // 8        # SD_NORM_WORKSPACE_BYTES (include/specdec_b200.h)
+
+
 class ErrFlag:
     """Device int32 word the kernels OR error bits into, plus the norm kernels' scheduler workspace
     (SD_NORM_WORKSPACE_BYTES, include/specdec_b200.h).  One object serves launches that are ordered after one another
@@ -38,7 +41,7 @@ class ErrFlag:
 
     def __init__(self, device, shared: bool = False):
         self.t = torch.zeros(1, dtype=torch.int32, device=device)
-        self.ws = torch.zeros(4, dtype=torch.int32, device=device)
+        self.ws = torch.zeros(NORM_WORKSPACE_BYTES // 4, dtype=torch.int32, device=device)
         self.shared = shared          # per-device default flag: any stream may use it, so its workspace is not used
 
     def ptr(self) -> int:
@@ -83,7 +86,7 @@ def _default_workspace(device) -> int:
     if ws is None:
         if torch.cuda.is_current_stream_capturing():
             return 0
-        ws = _workspaces[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+        ws = _workspaces[key] = torch.zeros(NORM_WORKSPACE_BYTES // 4, dtype=torch.int32, device=dev)
     return ws.data_ptr()
 
 

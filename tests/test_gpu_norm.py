@@ -206,7 +206,9 @@ def test_pipeline_kernel_many_rows_with_sampling(cuda_lib, V, dtype, rows, kerne
     assert compare_probs(pa[sel], want, "pipeline vs oracle") == 0
 
 
-@pytest.mark.parametrize("V,rows,n_tied", [(4096, 9000, 3), (32000, 2400, 40), (2048, 40000, 40000), (4096, 30000, 15000)])
+@pytest.mark.parametrize("V,rows,n_tied", [(4096, 9000, 3), (32000, 2400, 40), (2048, 40000, 40000), (4096, 30000, 15000),
+                                           # top-k rows longer than the ring (pass 2 from L2): tied rows go to the follow-up launch
+                                           (131072, 400, 7), (131072, 300, 300), (262144, 150, 1)])
 @pytest.mark.parametrize("kernel", [True, "cluster"])
 def test_pipeline_kernel_dynamic_rows_and_deferred_rows(cuda_lib, V, rows, n_tied, kernel):
     """Rows are handed to the clusters through a ticket counter (tens of items per cluster: the row-index ring wraps), and

@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_cabi.SIGNATURES), (declared ^ set(_cabi.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sd_version() == 200
+    assert lib.sd_version() == 210
 
 
 def test_no_cpu_fallback():
