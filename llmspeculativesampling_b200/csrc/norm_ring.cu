@@ -64,7 +64,7 @@ bool plan_ring(NormParams& p, int dtype, int rows) {
   // (measured at 576 rows: up to 16 chunks the cluster pipeline is as fast or faster — 45.5 vs 53.5 us at fp32 V = 50272,
   //  82.7 vs 85.4 us at bf16 V = 131072 —, from 32 chunks on the ring wins: 113 vs 151 us at fp32 V = 131072, 212 vs 654 us
   //  at fp32 V = 262144)
-  const bool long_rows = n_chunks > slots && (mode == kRingDense || (rows <= kDeferBitmapRows && n_chunks >= 24));
+  const bool long_rows = n_chunks > slots && (mode == kRingDense || (rows <= kDeferBitmapRows && n_chunks >= 24 && rows * 4 >= device_sm_count()));   // (a handful of rows: one CTA per row starves, clusters split them)
   if (slots < 2 || (n_chunks > slots && !long_rows) || n_chunks > kRingMaxLongChunks) return false;
   p.ring_long = long_rows ? 1 : 0;
   const size_t shared_off = static_cast<size_t>(slots + extra) * kRingChunkBytes;
