@@ -236,6 +236,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   while (!mbar_try_wait(bar, phase)) {
   }

@@ -54,6 +54,7 @@ void set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
 int pdl_enabled() { return g_pdl; }
 
 void set_norm_prof(long long* ptr) { g_prof = ptr; }
+long long* get_norm_prof() { return g_prof; }
 
 void set_norm_tuning(int cluster, int threads) { g_tune_cluster = cluster; g_tune_threads = threads; }
 

@@ -28,6 +28,8 @@ struct VerifyParams {
   Compact pc, qc; long long pc_req_stride, qc_req_stride;
   // filled by the launcher
   int cluster, slice_elems, use_tma;
+  long long* prof;                                          // debug: clock64 timestamps, 8 per request (verify_row_kernel), nullable
+  int q_slots;                                              // verify_row_kernel: 16 KB slots of the q ring behind the staged p row (0: per-thread loads)
 };
 struct NormParams {
   const void* logits; long long ld_in; long long V;
@@ -62,6 +64,7 @@ cudaError_t launch_norm(const NormParams& p, int dtype, int rows, cudaStream_t s
 cudaError_t launch_norm_verify(const NormParams& p, int dtype, int rows, cudaStream_t st);
 void set_norm_tuning(int cluster, int threads);
 void set_norm_prof(long long* ptr);
+long long* get_norm_prof();
 void set_pdl(int enable);
 int pdl_enabled();
 bool plan_pipe(NormParams& p, int dtype, int rows, int tune_cluster);

@@ -173,9 +173,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) verify_row_kernel(const Verify
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int V = static_cast<int>(p.V), gamma = p.gamma;
   float* row = reinterpret_cast<float*>(smem_raw);
-  RowSampleShared& sh = *reinterpret_cast<RowSampleShared*>(smem_raw + ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)));
+  const size_t row_al = (static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127);
+  unsigned char* qring = smem_raw + row_al;                      // p.q_slots x 16 KB behind the staged row
+  RowSampleShared& sh = *reinterpret_cast<RowSampleShared*>(smem_raw + row_al + static_cast<size_t>(p.q_slots) * kRowQChunkBytes);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();                                                   // (launched with programmatic stream serialization)
+  long long* prof = p.prof != nullptr ? p.prof + static_cast<long long>(b) * 8 : nullptr;
+  if (prof != nullptr && tid == 0) prof[0] = clock64();
   if (p.active != nullptr && p.active[b] == 0) return;
   const bool has_q = p.q != nullptr;
   // ---- accept scan: lane i tests drafted token i (speculative_sampling.py:1975-1990)
@@ -203,11 +207,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) verify_row_kernel(const Verify
     if (lane == 0) sh.n_acc = n_acc;
   }
   __syncthreads();
+  if (prof != nullptr && tid == 0) prof[1] = clock64();          // accept scan done
   const int n_acc = sh.n_acc;
   const bool use_q = has_q && n_acc < gamma;
   const float* prow = p.p + b * p.p_req_stride + (has_q ? n_acc : 0) * p.p_row_stride;
   const float* qrow = use_q ? p.q + b * p.q_req_stride + n_acc * p.q_row_stride : nullptr;
-  const long long tok = row_residual_sample(prow, qrow, V, p.u_final[b], !p.strict, row, sh, p.err_flag);
+  const long long tok = row_residual_sample(prow, qrow, V, p.u_final[b], !p.strict, row, sh, p.err_flag, prof, qring, p.q_slots);
+  if (prof != nullptr && tok >= 0) prof[5] = clock64();          // token found (the one thread that holds it)
   if (tok == -2) {
     if (tid == 0) { p.next_tok[b] = 0; if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc; }
   } else if (tok >= 0) {
@@ -639,15 +645,22 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
     static bool attr_dev[64] = {};
     cudaError_t e = set_row_smem(verify_row_kernel, attr_dev);
     if (e != cudaSuccess) return e;
+    // q ring: as many 16 KB slots (up to 4) as fit behind the staged p row; fewer than 2: q through per-thread loads
+    {
+      const long long room = static_cast<long long>(device_max_smem_optin()) - kRowStaticReserve - static_cast<long long>(row_sample_smem(p.V));
+      const int qs = p.q != nullptr ? static_cast<int>(room / kRowQChunkBytes) : 0;
+      p.q_slots = qs >= 2 ? (qs > kRowQMaxSlots ? kRowQMaxSlots : qs) : 0;
+    }
     cudaLaunchConfig_t rcfg = {};
     rcfg.gridDim = dim3(static_cast<unsigned>(p.B));
     rcfg.blockDim = dim3(kRowThreads);
-    rcfg.dynamicSmemBytes = row_sample_smem(p.V);
+    rcfg.dynamicSmemBytes = row_sample_smem(p.V, p.q_slots);
     rcfg.stream = st;
     cudaLaunchAttribute rat[1];
     rat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     rat[0].val.programmaticStreamSerializationAllowed = 1;
     rcfg.attrs = rat; rcfg.numAttrs = pdl_enabled() ? 1 : 0;
+    p.prof = get_norm_prof();
     return cudaLaunchKernelEx(&rcfg, verify_row_kernel, p);
   }
   const long long row_bytes = p.V * 4;

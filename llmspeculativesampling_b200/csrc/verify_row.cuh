@@ -22,16 +22,20 @@ constexpr int kRowWarps = kRowThreads / 32;
 constexpr int kRowChunkBytes = 32768;
 constexpr int kRowMaxChunks = 8;
 
+constexpr int kRowQChunkBytes = 16384;                          // q row: streamed through a small ring of TMA chunks
+constexpr int kRowQMaxSlots = 4;
+
 struct alignas(16) RowSampleShared {
   uint64_t bar[kRowMaxChunks];
+  uint64_t qfull[kRowQMaxSlots], qempty[kRowQMaxSlots];
   unsigned long long wbest[kRowWarps];
   unsigned long long wsum[kRowWarps];
   int n_acc, aux;
 };
 
 // bytes of dynamic shared memory a CTA needs for a row of V probabilities
-static inline size_t row_sample_smem(long long V) {
-  return ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)) + sizeof(RowSampleShared);
+static inline size_t row_sample_smem(long long V, int q_slots = 0) {
+  return ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)) + static_cast<size_t>(q_slots) * kRowQChunkBytes + sizeof(RowSampleShared);
 }
 
 // Samples request b's next token from max(0, prow - qrow) (qrow == nullptr: from prow), falling back to prow when the
@@ -41,13 +45,16 @@ static inline size_t row_sample_smem(long long V) {
 // Returns -2 in every thread when there is nothing to sample from (err_flag is set).
 __device__ __forceinline__ long long row_residual_sample(const float* __restrict__ prow, const float* __restrict__ qrow, int V,
                                                          float u_final, bool fallback, float* row, RowSampleShared& sh,
-                                                         int* err_flag) {
+                                                         int* err_flag, long long* prof = nullptr, unsigned char* qring = nullptr,
+                                                         int q_slots = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_vec = (V + 3) >> 2;
   const bool vec_ok = (V & 3) == 0 && (reinterpret_cast<uintptr_t>(prow) & 15) == 0 &&
                       (qrow == nullptr || (reinterpret_cast<uintptr_t>(qrow) & 15) == 0);
   const uint32_t row_bytes = static_cast<uint32_t>(V) * 4u;
   const int n_chunks = vec_ok ? static_cast<int>((row_bytes + kRowChunkBytes - 1) / kRowChunkBytes) : 0;
+  const int n_qchunks = static_cast<int>((row_bytes + kRowQChunkBytes - 1) / kRowQChunkBytes);
+  const bool q_ring = vec_ok && qrow != nullptr && qring != nullptr && q_slots >= 2;   // q streamed by TMA instead of per-thread loads
   // warp w owns vectors [w * vpw, (w + 1) * vpw), lanes strided inside
   const int vpw = (n_vec + kRowWarps - 1) / kRowWarps;
   const int v_begin = warp * vpw, v_end = min(n_vec, v_begin + vpw);
@@ -56,12 +63,21 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
   if (vec_ok) {
     if (tid == 0) {
       for (int c = 0; c < n_chunks; ++c) mbar_init(&sh.bar[c], 1);
+      if (q_ring) for (int c = 0; c < q_slots; ++c) { mbar_init(&sh.qfull[c], 1); mbar_init(&sh.qempty[c], kRowWarps); }
       fence_barrier_init();
       for (int c = 0; c < n_chunks; ++c) {
         const uint32_t off = static_cast<uint32_t>(c) * kRowChunkBytes;
         const uint32_t bytes = min(static_cast<uint32_t>(kRowChunkBytes), row_bytes - off);
         mbar_expect_tx(&sh.bar[c], bytes);
         tma_load_1d(reinterpret_cast<unsigned char*>(row) + off, reinterpret_cast<const unsigned char*>(prow) + off, bytes, &sh.bar[c]);
+        // the q chunks of the same range right behind it (two 16 KB chunks per 32 KB of p), as far as the ring reaches
+        if (q_ring)
+          for (int cq = 2 * c; cq < min(2 * c + 2, min(q_slots, n_qchunks)); ++cq) {
+            const uint32_t qoff = static_cast<uint32_t>(cq) * kRowQChunkBytes;
+            const uint32_t qb = min(static_cast<uint32_t>(kRowQChunkBytes), row_bytes - qoff);
+            mbar_expect_tx(&sh.qfull[cq], qb);
+            tma_load_1d(qring + static_cast<size_t>(cq) * kRowQChunkBytes, reinterpret_cast<const unsigned char*>(qrow) + qoff, qb, &sh.qfull[cq]);
+          }
       }
     }
     __syncthreads();                                            // barriers initialised before anyone waits on them
@@ -70,12 +86,51 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
     __syncthreads();
   }
 
+  if (prof != nullptr && threadIdx.x == 0) prof[2] = clock64();   // loads issued
   bool use_q = qrow != nullptr;
   unsigned long long best = 0ull;
   for (int attempt = 0; attempt < 2; ++attempt) {
     // ---- pass 1: residual in place (own vectors only), row maximum as a packed (value key, ~index)
     unsigned long long mine = 0ull;
     bool bad = false;
+    if (attempt == 0 && q_ring) {
+      // q arrives chunk by chunk in a small ring (the SM keeps p: V * 4 bytes + q: q_slots * 16 KB in flight through TMA);
+      // chunk c holds vectors c * 1024 ..: thread t takes vectors t and t + 512 of it
+      int slot = 0;
+      uint32_t par = 0u;
+      for (int c = 0; c < n_qchunks; ++c) {
+        mbar_wait(&sh.qfull[slot], par);
+        mbar_wait(&sh.bar[(c * kRowQChunkBytes) / kRowChunkBytes], 0);
+        const uint4* q4 = reinterpret_cast<const uint4*>(qring + static_cast<size_t>(slot) * kRowQChunkBytes);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int vl = h * kRowThreads + tid, v = c * (kRowQChunkBytes / 16) + vl;
+          if (v < n_vec) {
+            const float4 a4 = row4[v];
+            const uint4 qv = q4[vl];
+            float w[4] = {fmaxf(a4.x - __uint_as_float(qv.x), 0.f), fmaxf(a4.y - __uint_as_float(qv.y), 0.f),
+                          fmaxf(a4.z - __uint_as_float(qv.z), 0.f), fmaxf(a4.w - __uint_as_float(qv.w), 0.f)};   // utils.py:240
+            row4[v] = make_float4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              bad |= !(w[j] >= 0.f) || isinf(w[j]);
+              const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(v * 4 + j));
+              mine = (w[j] > 0.f && pk > mine) ? pk : mine;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.qempty[slot]);
+        if (tid == 0 && c + q_slots < n_qchunks) {               // refill the slot with chunk c + q_slots once all 16 warps released it
+          mbar_wait(&sh.qempty[slot], par);
+          const uint32_t qoff = static_cast<uint32_t>(c + q_slots) * kRowQChunkBytes;
+          const uint32_t qb = min(static_cast<uint32_t>(kRowQChunkBytes), row_bytes - qoff);
+          mbar_expect_tx(&sh.qfull[slot], qb);
+          tma_load_1d(qring + static_cast<size_t>(slot) * kRowQChunkBytes, reinterpret_cast<const unsigned char*>(qrow) + qoff, qb, &sh.qfull[slot]);
+        }
+        if (++slot == q_slots) { slot = 0; par ^= 1u; }
+      }
+    } else {
     constexpr int kAhead = 8;                                   // q vectors requested ahead of their use
     uint4 qbuf[kAhead];
     if (use_q && vec_ok) {
@@ -119,6 +174,7 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
         }
       }
     }
+    }
     if (bad) atomicOr(err_flag, kErrEmptyRow);                  // negative / NaN / inf weights: 'prob error'
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, mine, o); mine = t > mine ? t : mine; }
@@ -139,6 +195,7 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
     if (tid == 0) atomicOr(err_flag, kErrEmptyRow);
     return -2;
   }
+  if (prof != nullptr && threadIdx.x == 0) prof[3] = clock64();   // pass 1 done, maximum known
   const float rmax = key2f(static_cast<uint32_t>(best >> 32));
   const int argmax = static_cast<int>(0xffffffffu - static_cast<uint32_t>(best & 0xffffffffu));
   const int e = frexp_exp(rmax);
@@ -151,34 +208,44 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
   const f32x2 sh2 = pack2(scale_hi, scale_hi), k23 = pack2(8388608.0f, 8388608.0f), m1 = pack2(-1.0f, -1.0f), k20 = pack2(1048576.0f, 1048576.0f);
   unsigned long long blk = 0ull, wsum = 0ull;
   {
-    int k = 0;
-    for (int v0 = v_begin; v0 < v_end; v0 += 32, ++k) {
-      const int v = v0 + lane;
-      uint32_t acc_hi = 0u, acc_lo = 0u;
-      if (v < v_end) {
-        const float4 a4 = row4[v];
-        const f32x2 pr[2] = {pack2(a4.x, a4.y), pack2(a4.z, a4.w)};
+    // four blocks per trip: their loads and limb arithmetic are independent, and the eight warp reductions that follow
+    // are issued back to back instead of one dependent pair per block
+    constexpr int kU = 4;
+    for (int v0 = v_begin, k = 0; v0 < v_end; v0 += 32 * kU, k += kU) {
+      uint32_t acc_hi[kU], acc_lo[kU];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const f32x2 t1f = fma2_rd(pr[j], sh2, k23);           // 2^23 + H,  H = floor(W / 2^20),  W = r * scale < 2^40
-          const f32x2 nh = fma2(t1f, m1, k23);                  // -H
-          const f32x2 fr = fma2(pr[j], sh2, nh);                // W / 2^20 - H  in [0, 1)  (exact)
-          const f32x2 t2f = fma2_rd(fr, k20, k23);              // 2^23 + floor(W - 2^20 H)
-          float h0, h1, l0, l1;
-          unpack2(t1f, h0, h1);
-          unpack2(t2f, l0, l1);
-          acc_hi += (__float_as_uint(h0) - 0x4B000000u) + (__float_as_uint(h1) - 0x4B000000u);
-          acc_lo += (__float_as_uint(l0) - 0x4B000000u) + (__float_as_uint(l1) - 0x4B000000u);
+      for (int t = 0; t < kU; ++t) {
+        const int v = v0 + 32 * t + lane;
+        acc_hi[t] = 0u; acc_lo[t] = 0u;
+        if (v < v_end) {
+          const float4 a4 = row4[v];
+          const f32x2 pr[2] = {pack2(a4.x, a4.y), pack2(a4.z, a4.w)};
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const f32x2 t1f = fma2_rd(pr[j], sh2, k23);         // 2^23 + H,  H = floor(W / 2^20),  W = r * scale < 2^40
+            const f32x2 nh = fma2(t1f, m1, k23);                // -H
+            const f32x2 fr = fma2(pr[j], sh2, nh);              // W / 2^20 - H  in [0, 1)  (exact)
+            const f32x2 t2f = fma2_rd(fr, k20, k23);            // 2^23 + floor(W - 2^20 H)
+            float h0, h1, l0, l1;
+            unpack2(t1f, h0, h1);
+            unpack2(t2f, l0, l1);
+            acc_hi[t] += (__float_as_uint(h0) - 0x4B000000u) + (__float_as_uint(h1) - 0x4B000000u);
+            acc_lo[t] += (__float_as_uint(l0) - 0x4B000000u) + (__float_as_uint(l1) - 0x4B000000u);
+          }
         }
       }
-      const uint32_t hs = __reduce_add_sync(0xffffffffu, acc_hi), ls = __reduce_add_sync(0xffffffffu, acc_lo);
-      const unsigned long long bs = (static_cast<unsigned long long>(hs) << 20) + ls;
-      if (lane == k) blk = bs;                                  // (at most 29 blocks per warp: the row fits shared memory)
-      wsum += bs;
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+        const uint32_t hs = __reduce_add_sync(0xffffffffu, acc_hi[t]), ls = __reduce_add_sync(0xffffffffu, acc_lo[t]);
+        const unsigned long long bs = (static_cast<unsigned long long>(hs) << 20) + ls;
+        if (lane == k + t) blk = bs;                            // (at most 29 blocks per warp: the row fits shared memory)
+        wsum += bs;
+      }
     }
   }
   if (lane == 0) sh.wsum[warp] = wsum;
   __syncthreads();
+  if (prof != nullptr && threadIdx.x == 0) prof[4] = clock64();   // pass 2 done
   const unsigned long long mine_w = lane < kRowWarps ? sh.wsum[lane] : 0ull;
   const unsigned long long incl = warp_scan_incl(mine_w, lane);
   const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);

@@ -1,4 +1,11 @@
-mkdir -p gpurun_out/r3g
-o=gpurun_out/r3g
-timeout 1200 python -m pytest tests -m gpu -x -q > $o/pytest.log 2>&1; tail -5 $o/pytest.log
-python tools/sweep.py > $o/sweep_n1.jsonl 2> $o/sweep.err; grep -c . $o/sweep_n1.jsonl
+mkdir -p gpurun_out/r3i
+o=gpurun_out/r3i
+timeout 900 python -m pytest tests/test_gpu_verify.py tests/test_gpu_engine.py tests/test_gpu_dropins.py -x -q > $o/pytest.log 2>&1; tail -3 $o/pytest.log
+python tools/verify_prof.py > $o/vprof.log 2>&1; cat $o/vprof.log
+python tools/kernel_bench.py --mode verify_dense > $o/kb.jsonl 2> $o/kb.err
+python tools/kernel_bench.py --mode verify_dense --V 50272 >> $o/kb.jsonl 2>> $o/kb.err
+python tools/kernel_bench.py --mode verify_dense --B 256 >> $o/kb.jsonl 2>> $o/kb.err
+python tools/kernel_bench.py --mode sample >> $o/kb.jsonl 2>> $o/kb.err
+python tools/kernel_bench.py --mode verify_multi >> $o/kb.jsonl 2>> $o/kb.err
+python tools/kernel_bench.py --mode verify_bild >> $o/kb.jsonl 2>> $o/kb.err
+cut -c1-160 $o/kb.jsonl
