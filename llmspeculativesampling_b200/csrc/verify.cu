@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) verify_row_kernel(const Verify
   if (prof != nullptr && tid == 0) prof[0] = clock64();
   if (p.active != nullptr && p.active[b] == 0) return;
   const bool has_q = p.q != nullptr;
+  const bool vec_rows = (V & 3) == 0;                            // (the sampler's TMA path; misaligned pointers re-check inside)
+  if (tid == 32 && vec_rows) row_sample_init_barriers(sh, p.q_slots);   // while warp 0 runs the accept scan
   // ---- accept scan: lane i tests drafted token i (speculative_sampling.py:1975-1990)
   if (warp == 0) {
     int n_acc = 0;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) verify_row_kernel(const Verify
   const bool use_q = has_q && n_acc < gamma;
   const float* prow = p.p + b * p.p_req_stride + (has_q ? n_acc : 0) * p.p_row_stride;
   const float* qrow = use_q ? p.q + b * p.q_req_stride + n_acc * p.q_row_stride : nullptr;
-  const long long tok = row_residual_sample(prow, qrow, V, p.u_final[b], !p.strict, row, sh, p.err_flag, prof, qring, p.q_slots);
+  const long long tok = row_residual_sample(prow, qrow, V, p.u_final[b], !p.strict, row, sh, p.err_flag, prof, qring, p.q_slots, vec_rows);
   if (prof != nullptr && tok >= 0) prof[5] = clock64();          // token found (the one thread that holds it)
   if (tok == -2) {
     if (tid == 0) { p.next_tok[b] = 0; if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc; }

@@ -38,6 +38,14 @@ static inline size_t row_sample_smem(long long V, int q_slots = 0) {
   return ((static_cast<size_t>(V) * 4 + 127) & ~static_cast<size_t>(127)) + static_cast<size_t>(q_slots) * kRowQChunkBytes + sizeof(RowSampleShared);
 }
 
+// The barriers of row_residual_sample, initialised by ONE thread ahead of time (e.g. while another warp runs the accept scan);
+// a CTA-wide barrier must follow before row_residual_sample(..., barriers_ready = true) is called.
+__device__ __forceinline__ void row_sample_init_barriers(RowSampleShared& sh, int q_slots) {
+  for (int c = 0; c < kRowMaxChunks; ++c) mbar_init(&sh.bar[c], 1);
+  for (int c = 0; c < q_slots; ++c) { mbar_init(&sh.qfull[c], 1); mbar_init(&sh.qempty[c], kRowWarps); }
+  fence_barrier_init();
+}
+
 // Samples request b's next token from max(0, prow - qrow) (qrow == nullptr: from prow), falling back to prow when the
 // residual is empty and `fallback` is set (reference :2009-2010).  All kRowThreads threads of the CTA must call it;
 // `row` is the CTA's staging area (>= V floats, 16-byte aligned), `sh` its scratch (barriers NOT yet initialised).
@@ -46,7 +54,7 @@ static inline size_t row_sample_smem(long long V, int q_slots = 0) {
 __device__ __forceinline__ long long row_residual_sample(const float* __restrict__ prow, const float* __restrict__ qrow, int V,
                                                          float u_final, bool fallback, float* row, RowSampleShared& sh,
                                                          int* err_flag, long long* prof = nullptr, unsigned char* qring = nullptr,
-                                                         int q_slots = 0) {
+                                                         int q_slots = 0, bool barriers_ready = false) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_vec = (V + 3) >> 2;
   const bool vec_ok = (V & 3) == 0 && (reinterpret_cast<uintptr_t>(prow) & 15) == 0 &&
@@ -62,25 +70,28 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
 
   if (vec_ok) {
     if (tid == 0) {
-      for (int c = 0; c < n_chunks; ++c) mbar_init(&sh.bar[c], 1);
-      if (q_ring) for (int c = 0; c < q_slots; ++c) { mbar_init(&sh.qfull[c], 1); mbar_init(&sh.qempty[c], kRowWarps); }
-      fence_barrier_init();
-      for (int c = 0; c < n_chunks; ++c) {
-        const uint32_t off = static_cast<uint32_t>(c) * kRowChunkBytes;
-        const uint32_t bytes = min(static_cast<uint32_t>(kRowChunkBytes), row_bytes - off);
-        mbar_expect_tx(&sh.bar[c], bytes);
-        tma_load_1d(reinterpret_cast<unsigned char*>(row) + off, reinterpret_cast<const unsigned char*>(prow) + off, bytes, &sh.bar[c]);
-        // the q chunks of the same range right behind it (two 16 KB chunks per 32 KB of p), as far as the ring reaches
-        if (q_ring)
-          for (int cq = 2 * c; cq < min(2 * c + 2, min(q_slots, n_qchunks)); ++cq) {
-            const uint32_t qoff = static_cast<uint32_t>(cq) * kRowQChunkBytes;
-            const uint32_t qb = min(static_cast<uint32_t>(kRowQChunkBytes), row_bytes - qoff);
-            mbar_expect_tx(&sh.qfull[cq], qb);
-            tma_load_1d(qring + static_cast<size_t>(cq) * kRowQChunkBytes, reinterpret_cast<const unsigned char*>(qrow) + qoff, qb, &sh.qfull[cq]);
-          }
+      if (!barriers_ready) {                                    // (else: row_sample_init_barriers ran before a CTA-wide barrier)
+        for (int c = 0; c < n_chunks; ++c) mbar_init(&sh.bar[c], 1);
+        if (q_ring) for (int c = 0; c < q_slots; ++c) { mbar_init(&sh.qfull[c], 1); mbar_init(&sh.qempty[c], kRowWarps); }
+        fence_barrier_init();
       }
     }
-    __syncthreads();                                            // barriers initialised before anyone waits on them
+    if (!barriers_ready) __syncthreads();                       // barriers initialised before anyone waits on them
+    // one bulk copy per thread (a single thread needs ~200 cycles per issue: 8 copies in a row were 1.7k cycles of the
+    // request's critical path): lanes 0.. of warp 0 the p chunks, lanes 0.. of warp 1 the first q chunks
+    if (tid < n_chunks) {
+      const uint32_t off = static_cast<uint32_t>(tid) * kRowChunkBytes;
+      const uint32_t bytes = min(static_cast<uint32_t>(kRowChunkBytes), row_bytes - off);
+      mbar_expect_tx(&sh.bar[tid], bytes);
+      tma_load_1d(reinterpret_cast<unsigned char*>(row) + off, reinterpret_cast<const unsigned char*>(prow) + off, bytes, &sh.bar[tid]);
+    }
+    if (q_ring && tid >= 32 && tid - 32 < min(q_slots, n_qchunks)) {
+      const int cq = tid - 32;
+      const uint32_t qoff = static_cast<uint32_t>(cq) * kRowQChunkBytes;
+      const uint32_t qb = min(static_cast<uint32_t>(kRowQChunkBytes), row_bytes - qoff);
+      mbar_expect_tx(&sh.qfull[cq], qb);
+      tma_load_1d(qring + static_cast<size_t>(cq) * kRowQChunkBytes, reinterpret_cast<const unsigned char*>(qrow) + qoff, qb, &sh.qfull[cq]);
+    }
   } else {
     for (int i = tid; i < n_vec * 4; i += kRowThreads) row[i] = i < V ? prow[i] : 0.f;
     __syncthreads();
