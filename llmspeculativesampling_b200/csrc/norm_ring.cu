@@ -54,7 +54,12 @@ bool plan_ring(NormParams& p, int dtype, int rows) {
   const int smem_max = device_max_smem_optin();
   const size_t fixed = ((mode == kRingDense ? kRingSharedDenseBytes : sizeof(RingShared)) + 127) & ~static_cast<size_t>(127);
   const int extra = mode == kRingTopK ? 1 : 0;               // TOPK: one more chunk holds the zeros of the output rows' zero fill
-  int slots = static_cast<int>((static_cast<size_t>(smem_max) - fixed) / kRingChunkBytes) - extra;
+  // SD_RING_SPARE=<bytes> leaves part of the SM's shared memory unallocated, so that a small kernel of another stream (the
+  // sparse verify: 12.7 KB static, 128 threads) can run BESIDE the ring CTAs instead of waiting for an SM to drain.
+  // Measured on the software-pipelined bench step: no gain (31.4 vs 31.0 us) — off by default.
+  size_t spare = 0;
+  { const char* ev = getenv("SD_RING_SPARE"); if (ev != nullptr) spare = static_cast<size_t>(atoi(ev)); }
+  int slots = static_cast<int>((static_cast<size_t>(smem_max) - fixed - spare) / kRingChunkBytes) - extra;
   if (slots > kRingMaxSlots) slots = kRingMaxSlots;
   const int n_chunks = static_cast<int>((row_bytes + kRingChunkBytes - 1) / kRingChunkBytes);
   // DENSE rows longer than the ring are streamed through it twice (max / sum pass, write pass; the second read is an L2 hit)

@@ -42,7 +42,9 @@ constexpr int kRingMaxPieces = kRingMaxLongChunks * kRingComputeWarps;   // (chu
 constexpr int kRingEndDone = -1, kRingEndPause = -2;
 constexpr uint32_t kRingTieUlps = 8;
 
-enum : int { kRingTopK = 0, kRingDense = 1, kRingDenseT1 = 2 };   // (DenseT1: temperature == 1, no logit / T arithmetic compiled in)
+enum : int { kRingTopK = 0, kRingDense = 1, kRingDenseT1 = 2, kRingTopKLong = 3 };
+// (DenseT1: temperature == 1, no logit / T arithmetic compiled in; TopKLong: top-k rows longer than the ring — a separate
+//  instantiation: its branches in pass 1 / pass 2 cost the resident-row kernel 4 % when they were run-time)
 
 // scratch of the two modes (a union inside RingShared: a dense launch needs 5 KB next to the ring instead of 19 KB, which
 // is one more 16 KB slot — fp32 rows of V = 50272 are 13 chunks)
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
   const uint32_t row_bytes = static_cast<uint32_t>(n_vec) * 16u;
   const float temp = p.temperature;
   const float r_temp = 1.0f / temp;
+  constexpr bool kTopK = MODE == kRingTopK || MODE == kRingTopKLong;
   const bool t1 = MODE == kRingDenseT1 ? true : (MODE == kRingDense ? false : temp == 1.0f);
   const int k_eff = min(p.top_k, V);
   const bool want_probs = p.probs != nullptr;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
   long long* prof_cta = p.prof != nullptr ? p.prof + (static_cast<long long>(gridDim.x) * 8 * 16 + static_cast<long long>(blockIdx.x) * 4) : nullptr;
   if (prof_cta != nullptr && tid == 0) { prof_cta[0] = static_cast<long long>(globaltimer_ns()); prof_cta[3] = clock64(); }
 
-  if constexpr (MODE == kRingTopK) {
+  if constexpr (kTopK) {
     for (int i = tid; i < kRingChunkBytes / 16; i += kRingThreads) reinterpret_cast<uint4*>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();                                       // generic writes above -> bulk-copy (async proxy) reads below
   }
@@ -145,13 +148,13 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
       }
       sh.n_fail = 0;
       sh.end_reason = kRingEndDone;
-      if constexpr (MODE == kRingTopK) { sh.k.cand_cnt = 0; sh.k.cand_over = 0; }   // (a dense launch does not allocate the top-k scratch)
+      if constexpr (kTopK) { sh.k.cand_cnt = 0; sh.k.cand_over = 0; }   // (a dense launch does not allocate the top-k scratch)
       fence_barrier_init();
     }
     if (round > 0) {
       // the general path used the ring (and the zero chunk) through the generic proxy: restore the zeros, then order
       // everything before the bulk copies of the new round
-      if constexpr (MODE == kRingTopK)
+      if constexpr (kTopK)
         for (int i = tid; i < kRingChunkBytes / 16; i += kRingThreads) reinterpret_cast<uint4*>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
       fence_proxy_async();
     }
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           const unsigned char* src = reinterpret_cast<const unsigned char*>(p.logits) + static_cast<size_t>(row) * p.ld_in * sizeof(T);
           // (a DENSE row longer than the ring is streamed twice: once for the max / sum pass, once for the write pass — the
           //  second read of the 148 rows in flight comes from the 126 MB L2)
-          for (int cc = 0; cc < ((MODE != kRingTopK && p.ring_long) ? 2 * NCH : NCH); ++cc) {
+          for (int cc = 0; cc < ((!kTopK && p.ring_long) ? 2 * NCH : NCH); ++cc) {
             const int c = cc >= NCH ? cc - NCH : cc;
             if (wraps > 0) mbar_wait(&sh.empty[slot], static_cast<uint32_t>(wraps - 1) & 1u);
             const uint32_t off = static_cast<uint32_t>(c) * kRingChunkBytes;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
       }
     } else if (warp == CW + 1) {
       // =========================================================================== aux warp
-      if constexpr (MODE == kRingTopK) {
+      if constexpr (kTopK) {
         // The finisher.  For every row: (1) its zero fill — bulk copies (TMA) of the zero chunk, issued by one thread as soon
         // as the row is known, so no store instruction of the SM is spent on the ~V zeros of a top-k filtered row; (2) when
         // the compute warps hand over the sorted candidate list: top-k cut (ties kept), top-p cut, softmax, optional
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
               for (int i = lane; i < np_out; i += 32) orow[si[i]] = sh.k.f_val[i];
             }
           } else if (lane == 0) {
-            if (p.ring_long) {
+            if (MODE == kRingTopKLong) {
               // a row longer than the ring cannot be re-run by this CTA: flag it in the caller's workspace; the follow-up
               // launch of the one-cluster-per-row kernel (general path) serves the flagged rows
               atomicOr(p.defer_bitmap + (row >> 5), 1u << (row & 31));
@@ -454,7 +457,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
       int slot0 = 0, wraps0 = 0;                                // ring position of the current row's first chunk
       // DENSE: pass A of row it + 1 runs inside pass B of row it (see below); its per-thread results are carried over
       int cur_slot = 0, cur_wraps = 0;                          // DENSE long rows: ring cursor (chunks are consumed strictly in ring order)
-      const bool long_rows = p.ring_long != 0;                   // rows longer than the ring (DENSE: streamed twice; TOPK: pass 2 from L2)
+      // rows longer than the ring (DENSE: streamed twice, run-time; TOPK: pass 2 from L2, compile-time)
+      const bool long_rows = MODE == kRingTopKLong ? true : (MODE == kRingTopK ? false : p.ring_long != 0);
       float car_m = -INFINITY, car_nan = -INFINITY, car_u = -1.f;
       f32x2 car_s2 = 0ull;
       bool carried = false;
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
         };
 
         RING_PROF(0);
-        if constexpr (MODE == kRingTopK) {
+        if constexpr (kTopK) {
           // ---- pass 1, chunk by chunk as the chunks land: the three largest VECTOR maxima of the thread (tmax >= m2 >= m3)
           //      and the vector indices of the first two.  Thread t owns vectors c * 1024 + t and c * 1024 + 512 + t.
           float tmax = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -981,7 +985,7 @@ static cudaError_t ring_launch(const NormParams& p, cudaStream_t st) {
 
 template <typename T>
 static cudaError_t ring_dispatch(const NormParams& p, cudaStream_t st) {
-  if (p.ring_mode != kRingDense) return ring_launch<T, kRingTopK>(p, st);
+  if (p.ring_mode != kRingDense) return p.ring_long ? ring_launch<T, kRingTopKLong>(p, st) : ring_launch<T, kRingTopK>(p, st);
   return p.temperature == 1.0f ? ring_launch<T, kRingDenseT1>(p, st) : ring_launch<T, kRingDense>(p, st);
 }
 

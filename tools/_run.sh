@@ -1,11 +1,10 @@
-mkdir -p gpurun_out/r3i
-o=gpurun_out/r3i
-timeout 900 python -m pytest tests/test_gpu_verify.py tests/test_gpu_engine.py tests/test_gpu_dropins.py -x -q > $o/pytest.log 2>&1; tail -3 $o/pytest.log
-python tools/verify_prof.py > $o/vprof.log 2>&1; cat $o/vprof.log
-python tools/kernel_bench.py --mode verify_dense > $o/kb.jsonl 2> $o/kb.err
-python tools/kernel_bench.py --mode verify_dense --V 50272 >> $o/kb.jsonl 2>> $o/kb.err
-python tools/kernel_bench.py --mode verify_dense --B 256 >> $o/kb.jsonl 2>> $o/kb.err
-python tools/kernel_bench.py --mode sample >> $o/kb.jsonl 2>> $o/kb.err
-python tools/kernel_bench.py --mode verify_multi >> $o/kb.jsonl 2>> $o/kb.err
-python tools/kernel_bench.py --mode verify_bild >> $o/kb.jsonl 2>> $o/kb.err
-cut -c1-160 $o/kb.jsonl
+mkdir -p gpurun_out/r3k
+o=gpurun_out/r3k
+python bench.py --steps 1600 --no-side-reports --no-cpu-baseline > $o/bench.json 2> $o/bench.err
+python - <<PY
+import json
+d=json.loads([l for l in open("$o/bench.json") if l.startswith("{")][-1])
+r=d["roofline"]
+print("ms_per_step", round(d["ms_per_step"]*1e3,2), "value", round(d["value"]), "norm", round(r["ms_per_step"]*1e3,2), "frac", round(r["frac"],3), "overlap", round(r["overlapped"]["ms_per_launch"]*1e3,2), "step frac", round(r["step"]["frac"],3), "serial", round(r["step"]["serial_ms"]*1e3,2))
+PY
+timeout 900 python -m pytest tests/test_gpu_norm.py -x -q > $o/pytest.log 2>&1; tail -2 $o/pytest.log
