@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspecdec_b200.so")
+_VARIANT = os.environ.get("SD_LIB_VARIANT", "")          # "prof": the copy with the ring kernel's timeline probes (build.py)
+LIB_PATH = os.path.join(_HERE, "libspecdec_b200.so" if not _VARIANT else f"libspecdec_b200_{_VARIANT}.so")
 
 i32, i64, f32, vp = C.c_int, C.c_int64, C.c_float, C.c_void_p
 

@@ -8,7 +8,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libspecdec_b200.so")
+# SD_LIB_VARIANT=prof: a second copy of the library with the ring kernel's in-kernel timeline probes compiled in
+# (-DSD_RING_PROF; tools/ring_prof.py) — the production library does not carry them
+VARIANT = os.environ.get("SD_LIB_VARIANT", "")
+LIB = os.path.join(HERE, "libspecdec_b200.so" if not VARIANT else f"libspecdec_b200_{VARIANT}.so")
 SOURCES = ["norm.cu", "norm_pipe.cu", "norm_pipe_f32.cu", "norm_pipe_bf16.cu", "norm_pipe_f16.cu", "norm_ring.cu", "norm_ring_f32.cu",
            "norm_ring_bf16.cu", "norm_ring_f16.cu", "verify.cu", "misc.cu", "api.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "specdec_b200.h")]
@@ -36,12 +39,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not VARIANT else f"build_{VARIANT}")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src: str) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("SD_EXTRA_NVCC_FLAGS", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DSD_RING_PROF"] if VARIANT == "prof" else []), *os.environ.get("SD_EXTRA_NVCC_FLAGS", "").split(),
+               "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

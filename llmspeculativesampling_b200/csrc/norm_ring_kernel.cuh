@@ -102,9 +102,17 @@ __device__ __forceinline__ float ex2_ftz(float x) {         // MUFU.EX2 (results
 __device__ __forceinline__ float fadd_rd(float a, float b) { return __fadd_rd(a, b); }
 
 // debug timeline (tools/ring_prof.py): prof[(cta * 8 + item) * 16 + slot] = clock64() for the first 8 items of every CTA
+// Compiled in only with -DSD_RING_PROF (python tools/ring_prof.py builds its own copy of the library): carrying the probes
+// costs the production kernels registers and issue slots.
+#ifdef SD_RING_PROF
 #define RING_PROF(slot) do { if (p.prof != nullptr && tid == 0 && it < 8) p.prof[(static_cast<long long>(blockIdx.x) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
-
 #define RING_PROF_AUX(slot) do { if (p.prof != nullptr && lane == 0 && it < 8) p.prof[(static_cast<long long>(blockIdx.x) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
+#define RING_PROF_CTA(i, expr) do { if (prof_cta != nullptr && tid == 0) prof_cta[i] = static_cast<long long>(expr); } while (0)
+#else
+#define RING_PROF(slot) do { } while (0)
+#define RING_PROF_AUX(slot) do { } while (0)
+#define RING_PROF_CTA(i, expr) do { } while (0)
+#endif
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormParams p) {
@@ -131,8 +139,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
   const int static_rows = static_cast<int>(gridDim.x);         // first item of CTA b is row b
   auto slot_ptr = [&](int slot) { return smem_raw + static_cast<size_t>(slot) * kRingChunkBytes; };
   // debug timeline, per CTA (after the per-item area): globaltimer at entry / after the dependency wait / at exit, clock64 at entry
+#ifdef SD_RING_PROF
   long long* prof_cta = p.prof != nullptr ? p.prof + (static_cast<long long>(gridDim.x) * 8 * 16 + static_cast<long long>(blockIdx.x) * 4) : nullptr;
-  if (prof_cta != nullptr && tid == 0) { prof_cta[0] = static_cast<long long>(globaltimer_ns()); prof_cta[3] = clock64(); }
+#endif
+  RING_PROF_CTA(0, globaltimer_ns());
+  RING_PROF_CTA(3, clock64());
 
   if constexpr (kTopK) {
     for (int i = tid; i < kRingChunkBytes / 16; i += kRingThreads) reinterpret_cast<uint4*>(zbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
     // eager back-to-back launches, nothing inside CUDA graphs, and early-launched dependents can hold SMs that a concurrent
     // independent launch on another stream could use — off by default (the trigger then comes after all work of the CTA).
     if (round == 0 && p.ring_trigger) pdl_launch_dependents();
-    if (round == 0 && prof_cta != nullptr && tid == 0) prof_cta[1] = static_cast<long long>(globaltimer_ns());
+    if (round == 0) RING_PROF_CTA(1, globaltimer_ns());
 
     if (warp == CW) {
       // =========================================================================== loader
@@ -945,7 +956,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
   }  // rounds
 
   if (!p.ring_trigger) pdl_launch_dependents();
-  if (prof_cta != nullptr && tid == 0) prof_cta[2] = static_cast<long long>(globaltimer_ns());
+  RING_PROF_CTA(2, globaltimer_ns());
   // the last CTA to finish re-arms the row counter for the next launch that uses this scheduler block
   if (tid == 0) {
     __threadfence();

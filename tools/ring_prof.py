@@ -3,6 +3,7 @@
     python tools/ring_prof.py [--mode topk|dense] [--rows 576] [--V 32000] [--dtype f32]
 """
 import argparse, os, sys
+os.environ["SD_LIB_VARIANT"] = "prof"          # the library copy with the probes compiled in (built on first use)
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from llmspeculativesampling_b200 import ops, build, _cabi
