@@ -7,6 +7,8 @@
 // syncs per drafted token, max_fn + sample, rollback bookkeeping, torch.cat append) and, with
 // strict = 1, the accept rule of speculative_sampling_v2 (:2152-2181).  With q == nullptr the
 // kernel is the drop-in for sampling/utils.py:213-233 (sample) on rows of p.
+#include <algorithm>
+
 #include "rowops.cuh"
 #include "specdec_internal.h"
 #include "verify_sparse.cuh"
@@ -218,6 +220,62 @@ __global__ void __launch_bounds__(kRowThreads, 1) verify_row_kernel(const Verify
   if (prof != nullptr && tok >= 0) prof[5] = clock64();          // token found (the one thread that holds it)
   if (tok == -2) {
     if (tid == 0) { p.next_tok[b] = 0; if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc; }
+  } else if (tok >= 0) {
+    verify_commit(p, b, n_acc, tok);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same with TWO CTAs per request (a cluster of 2) for batches that leave half of the SMs idle: one SM streams about
+// 25 bytes per clock through TMA, so the 2 * V * 4 bytes of a request are the bulk of its critical path; each CTA stages
+// one half of p_n and streams the matching half of q_n, the maximum and the exact weight totals of the halves are
+// exchanged through distributed shared memory (verify_row.cuh), the CTA whose half holds the target commits.
+__global__ void __launch_bounds__(kRowThreads, 1) verify_row2_kernel(const VerifyParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int V = static_cast<int>(p.V), gamma = p.gamma;
+  const int b = blockIdx.x >> 1, crank = blockIdx.x & 1;          // (1-D cluster of 2: rank = blockIdx.x % 2)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // split in units of one q chunk (1024 vectors): rank 0 takes the first ceil(chunks / 2) chunks
+  const int n_vec = V >> 2;
+  const int n_qc = (n_vec + 1023) >> 10;
+  const int vec0 = min(n_vec, ((n_qc + 1) >> 1) << 10);
+  const int v_first = crank ? vec0 : 0, v_cnt = crank ? n_vec - vec0 : vec0;
+  float* row = reinterpret_cast<float*>(smem_raw);
+  const size_t row_al = (static_cast<size_t>(vec0) * 16 + 127) & ~static_cast<size_t>(127);
+  unsigned char* qring = smem_raw + row_al;
+  RowSampleShared& sh = *reinterpret_cast<RowSampleShared*>(smem_raw + row_al + static_cast<size_t>(p.q_slots) * kRowQChunkBytes);
+  pdl_wait();
+  if (p.active != nullptr && p.active[b] == 0) return;           // (both CTAs of the cluster: no barrier is left waiting)
+  if (tid == 32) row_sample_init_barriers(sh, p.q_slots);
+  if (warp == 0) {                                               // accept scan, redundantly in both CTAs; rank 0 publishes the statistics
+    bool acc = true, tie = false;
+    if (lane < gamma) {
+      long long tok = p.draft[b * p.draft_stride + lane];
+      if (tok < 0 || tok >= V) { if (crank == 0) atomicOr(p.err_flag, kErrBadToken); tok = 0; }
+      const float pv = p.p[b * p.p_req_stride + lane * p.p_row_stride + tok];
+      const float qv = p.q[b * p.q_req_stride + lane * p.q_row_stride + tok];
+      if (qv == 0.f && crank == 0) atomicOr(p.err_flag, kErrZeroQ);
+      const float ratio = __fdiv_rn(pv, qv);
+      const float u = p.u_acc[b * p.u_acc_stride + lane];
+      const float thr = p.strict ? fminf(1.0f, ratio) : ratio;
+      acc = p.strict ? (u < thr) : !(u > thr);
+      tie = (u == thr);
+      if (p.ratios != nullptr && crank == 0) p.ratios[b * gamma + lane] = ratio;
+    }
+    const unsigned rej = __ballot_sync(0xffffffffu, !acc);
+    const int n_acc = rej ? (__ffs(rej) - 1) : gamma;
+    if (p.tie_count != nullptr && crank == 0 && tie && lane < gamma && lane <= n_acc) atomicAdd(p.tie_count, 1);
+    if (lane == 0) sh.n_acc = n_acc;
+  }
+  __syncthreads();
+  const int n_acc = sh.n_acc;
+  const bool use_q = n_acc < gamma;
+  const float* prow = p.p + b * p.p_req_stride + n_acc * p.p_row_stride + static_cast<long long>(v_first) * 4;
+  const float* qrow = use_q ? p.q + b * p.q_req_stride + n_acc * p.q_row_stride + static_cast<long long>(v_first) * 4 : nullptr;
+  const long long tok = row_residual_sample(prow, qrow, v_cnt * 4, p.u_final[b], !p.strict, row, sh, p.err_flag, nullptr, qring, p.q_slots,
+                                            true, crank, 2, v_first * 4);
+  if (tok == -2) {
+    if (tid == 0 && crank == 0) { p.next_tok[b] = 0; if (p.n_accepted != nullptr) p.n_accepted[b] = n_acc; }
   } else if (tok >= 0) {
     verify_commit(p, b, n_acc, tok);
   }
@@ -642,6 +700,33 @@ cudaError_t launch_verify(const VerifyParams& pin, cudaStream_t st) {
     sat[0].val.programmaticStreamSerializationAllowed = 1;
     scfg.attrs = sat; scfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&scfg, verify_sparse_kernel, p);
+  }
+  // two CTAs per request while that still fits the machine (aligned rows with a q side; see verify_row2_kernel)
+  if (g_verify_cluster == 0 && p.q != nullptr && row_kernel_fits(p.V) && 2 * p.B <= device_sm_count() && (p.V & 3) == 0 && p.V >= 8192 &&
+      reinterpret_cast<uintptr_t>(p.p) % 16 == 0 && reinterpret_cast<uintptr_t>(p.q) % 16 == 0 && p.p_req_stride % 4 == 0 &&
+      p.p_row_stride % 4 == 0 && p.q_req_stride % 4 == 0 && p.q_row_stride % 4 == 0) {
+    static bool attr_dev2[64] = {};
+    cudaError_t e = set_row_smem(verify_row2_kernel, attr_dev2);
+    if (e != cudaSuccess) return e;
+    const long long n_vec = p.V >> 2, n_qc = (n_vec + 1023) >> 10;
+    const long long vec0 = std::min<long long>(n_vec, ((n_qc + 1) >> 1) << 10);
+    const size_t row_al = (static_cast<size_t>(vec0) * 16 + 127) & ~static_cast<size_t>(127);
+    const long long room = static_cast<long long>(device_max_smem_optin()) - kRowStaticReserve - static_cast<long long>(row_al + sizeof(RowSampleShared));
+    const int qs = static_cast<int>(room / kRowQChunkBytes);
+    p.q_slots = qs > kRowQMaxSlots ? kRowQMaxSlots : qs;       // (half a row leaves room for the full ring)
+    cudaLaunchConfig_t ccfg = {};
+    ccfg.gridDim = dim3(static_cast<unsigned>(2 * p.B));
+    ccfg.blockDim = dim3(kRowThreads);
+    ccfg.dynamicSmemBytes = row_al + static_cast<size_t>(p.q_slots) * kRowQChunkBytes + sizeof(RowSampleShared);
+    ccfg.stream = st;
+    cudaLaunchAttribute cat[2];
+    cat[0].id = cudaLaunchAttributeClusterDimension;
+    cat[0].val.clusterDim.x = 2; cat[0].val.clusterDim.y = 1; cat[0].val.clusterDim.z = 1;
+    cat[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    cat[1].val.programmaticStreamSerializationAllowed = 1;
+    ccfg.attrs = cat; ccfg.numAttrs = pdl_enabled() ? 2 : 1;
+    p.prof = nullptr;
+    return cudaLaunchKernelEx(&ccfg, verify_row2_kernel, p);
   }
   if (g_verify_cluster == 0 && row_kernel_fits(p.V)) {                     // one CTA per request, row staged in shared memory
     static bool attr_dev[64] = {};

@@ -30,6 +30,8 @@ struct alignas(16) RowSampleShared {
   uint64_t qfull[kRowQMaxSlots], qempty[kRowQMaxSlots];
   unsigned long long wbest[kRowWarps];
   unsigned long long wsum[kRowWarps];
+  unsigned long long xbest[2][2];      // cluster of 2 (one request on two SMs): maxima of the two halves, per attempt
+  unsigned long long xtot[2];          // ... and their exact weight totals
   int n_acc, aux;
 };
 
@@ -54,7 +56,11 @@ __device__ __forceinline__ void row_sample_init_barriers(RowSampleShared& sh, in
 __device__ __forceinline__ long long row_residual_sample(const float* __restrict__ prow, const float* __restrict__ qrow, int V,
                                                          float u_final, bool fallback, float* row, RowSampleShared& sh,
                                                          int* err_flag, long long* prof = nullptr, unsigned char* qring = nullptr,
-                                                         int q_slots = 0, bool barriers_ready = false) {
+                                                         int q_slots = 0, bool barriers_ready = false, int crank = 0, int csize = 1,
+                                                         int idx_off = 0) {
+  // csize == 2: the CTA is one of a cluster of two that share the row — prow / qrow / V describe THIS CTA's part, idx_off is
+  // the vocabulary index of its first element; the maximum and the weight total are exchanged through distributed shared
+  // memory (two cluster barriers), the CTA whose part holds the target position returns the token
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_vec = (V + 3) >> 2;
   const bool vec_ok = (V & 3) == 0 && (reinterpret_cast<uintptr_t>(prow) & 15) == 0 &&
@@ -125,7 +131,7 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               bad |= !(w[j] >= 0.f) || isinf(w[j]);
-              const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(v * 4 + j));
+              const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(idx_off + v * 4 + j));
               mine = (w[j] > 0.f && pk > mine) ? pk : mine;
             }
           }
@@ -179,7 +185,7 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             bad |= !(w[j] >= 0.f) || isinf(w[j]);
-            const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(v * 4 + j));
+            const unsigned long long pk = (static_cast<unsigned long long>(f2key(w[j])) << 32) | (0xffffffffu - static_cast<uint32_t>(idx_off + v * 4 + j));
             mine = (w[j] > 0.f && pk > mine) ? pk : mine;
           }
         }
@@ -195,6 +201,16 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
     best = lane < kRowWarps ? sh.wbest[lane] : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
+    if (csize > 1) {                                            // the other half's maximum
+      cg::cluster_group cl = cg::this_cluster();
+      if (tid == 0) {
+        sh.xbest[attempt][crank] = best;
+        cl.map_shared_rank(&sh, crank ^ 1)->xbest[attempt][crank] = best;
+      }
+      cl.sync();
+      const unsigned long long b0 = sh.xbest[attempt][0], b1 = sh.xbest[attempt][1];
+      best = b0 > b1 ? b0 : b1;
+    }
     if (best != 0ull || !use_q || !fallback) break;
     // empty residual: resample from p_n itself (reference :2009-2010) — bring the row back (rare: plain loads)
     use_q = false;
@@ -258,13 +274,26 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
   __syncthreads();
   if (prof != nullptr && threadIdx.x == 0) prof[4] = clock64();   // pass 2 done
   const unsigned long long mine_w = lane < kRowWarps ? sh.wsum[lane] : 0ull;
-  const unsigned long long incl = warp_scan_incl(mine_w, lane);
-  const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long incl = warp_scan_incl(mine_w, lane);
+  unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long cta_base = 0ull;
+  if (csize > 1) {                                              // totals of the two halves, in vocabulary order
+    cg::cluster_group cl = cg::this_cluster();
+    if (tid == 0) {
+      sh.xtot[crank] = total;
+      cl.map_shared_rank(&sh, crank ^ 1)->xtot[crank] = total;
+    }
+    cl.sync();
+    cta_base = crank == 1 ? sh.xtot[0] : 0ull;
+    total = sh.xtot[0] + sh.xtot[1];
+    incl += cta_base;
+  }
   if (total == 0ull) {
-    if (tid == 0) atomicOr(err_flag, kErrEmptyRow);
+    if (tid == 0 && crank == 0) atomicOr(err_flag, kErrEmptyRow);
     return -2;
   }
   const unsigned long long target = scale_target(total, u_to_int(u_final));
+  if (target < cta_base) return -1;                             // (the target lies in the other CTA's half)
   const unsigned ball = __ballot_sync(0xffffffffu, incl > target);
   const int owner = __ffs(ball) - 1;                            // first warp whose range crosses the target
   if (warp != owner) return -1;
@@ -288,7 +317,7 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
     long long found = -1;
     float psel = 1.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { c += wv[j]; if (found < 0 && c > target) { found = v * 4 + j; psel = w[j]; } }
+    for (int j = 0; j < 4; ++j) { c += wv[j]; if (found < 0 && c > target) { found = idx_off + v * 4 + j; psel = w[j]; } }
     float guard_val = psel;
     if (use_q) guard_val = __fdiv_rn(psel, ldexpf(__ull2float_rn(total), e - kScaleBits) + 1e-6f);   // sample(max_fn(p - q)) sees the normalised value
     return guard_val < kProbGuard ? argmax : found;

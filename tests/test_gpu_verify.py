@@ -22,7 +22,9 @@ def _case(B, gamma, V, seed, k=20, p=0.9, T=0.8, noise=0.5):
 
 
 @pytest.mark.parametrize("B,gamma,V,k,p", [(16, 4, 32000, 20, 0.9), (8, 4, 50272, 0, 0.0), (12, 1, 1000, 20, 0.9),
-                                           (6, 8, 4099, 5, 0.0), (4, 16, 2048, 0, 0.9), (3, 4, 262144, 20, 0.9)])
+                                           (6, 8, 4099, 5, 0.0), (4, 16, 2048, 0, 0.9), (3, 4, 262144, 20, 0.9),
+                                           # up to SMs / 2 requests: two CTAs per request (cluster of 2); more: one CTA per request
+                                           (74, 4, 32000, 0, 0.0), (80, 3, 32000, 0, 0.0), (5, 4, 9000, 0, 0.0)])
 @pytest.mark.parametrize("strict", [False, True])
 def test_verify_bit_exact(cuda_lib, B, gamma, V, k, p, strict):
     from llmspeculativesampling_b200 import ops
