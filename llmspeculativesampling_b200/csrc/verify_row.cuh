@@ -233,32 +233,42 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
   const float scale = ldexpf(1.0f, kScaleBits - e);
   const float scale_hi = scale * 9.5367431640625e-07f;          // 2^-20 * scale (exact)
   const f32x2 sh2 = pack2(scale_hi, scale_hi), k23 = pack2(8388608.0f, 8388608.0f), m1 = pack2(-1.0f, -1.0f), k20 = pack2(1048576.0f, 1048576.0f);
-  // (a 32-bit warp reduction goes through the uniform datapath: ~30 cycles of its throughput each — 32 of them per warp made
-  //  this pass 4k cycles.  Every warp therefore only keeps per-LANE limb totals over its whole range, 2 reductions at the
-  //  end; the one warp that turns out to hold the target re-derives its per-block sums below)
-  auto limbs_of = [&](int v, uint32_t& hi, uint32_t& lo) {
-    const float4 a4 = row4[v];
-    const f32x2 pr[2] = {pack2(a4.x, a4.y), pack2(a4.z, a4.w)};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const f32x2 t1f = fma2_rd(pr[j], sh2, k23);               // 2^23 + H,  H = floor(W / 2^20),  W = r * scale < 2^40
-      const f32x2 nh = fma2(t1f, m1, k23);                      // -H
-      const f32x2 fr = fma2(pr[j], sh2, nh);                    // W / 2^20 - H  in [0, 1)  (exact)
-      const f32x2 t2f = fma2_rd(fr, k20, k23);                  // 2^23 + floor(W - 2^20 H)
-      float h0, h1, l0, l1;
-      unpack2(t1f, h0, h1);
-      unpack2(t2f, l0, l1);
-      hi += (__float_as_uint(h0) - 0x4B000000u) + (__float_as_uint(h1) - 0x4B000000u);
-      lo += (__float_as_uint(l0) - 0x4B000000u) + (__float_as_uint(l1) - 0x4B000000u);
-    }
-  };
-  unsigned long long wsum = 0ull;
+  unsigned long long blk = 0ull, wsum = 0ull;
   {
-    uint32_t acc_hi = 0u, acc_lo = 0u;                          // (<= 29 vectors per lane: 29 * 4 * 2^20 < 2^27)
-#pragma unroll 4
-    for (int v = v_begin + lane; v < v_end; v += 32) limbs_of(v, acc_hi, acc_lo);
-    const unsigned long long hs = __reduce_add_sync(0xffffffffu, acc_hi), ls = __reduce_add_sync(0xffffffffu, acc_lo);
-    wsum = (hs << 20) + ls;                                     // (32 lanes * 2^27 = 2^32: hs is kept in 64 bits)
+    // four blocks per trip: their loads and limb arithmetic are independent, and the eight warp reductions that follow
+    // are issued back to back instead of one dependent pair per block
+    constexpr int kU = 4;
+    for (int v0 = v_begin, k = 0; v0 < v_end; v0 += 32 * kU, k += kU) {
+      uint32_t acc_hi[kU], acc_lo[kU];
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+        const int v = v0 + 32 * t + lane;
+        acc_hi[t] = 0u; acc_lo[t] = 0u;
+        if (v < v_end) {
+          const float4 a4 = row4[v];
+          const f32x2 pr[2] = {pack2(a4.x, a4.y), pack2(a4.z, a4.w)};
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const f32x2 t1f = fma2_rd(pr[j], sh2, k23);         // 2^23 + H,  H = floor(W / 2^20),  W = r * scale < 2^40
+            const f32x2 nh = fma2(t1f, m1, k23);                // -H
+            const f32x2 fr = fma2(pr[j], sh2, nh);              // W / 2^20 - H  in [0, 1)  (exact)
+            const f32x2 t2f = fma2_rd(fr, k20, k23);            // 2^23 + floor(W - 2^20 H)
+            float h0, h1, l0, l1;
+            unpack2(t1f, h0, h1);
+            unpack2(t2f, l0, l1);
+            acc_hi[t] += (__float_as_uint(h0) - 0x4B000000u) + (__float_as_uint(h1) - 0x4B000000u);
+            acc_lo[t] += (__float_as_uint(l0) - 0x4B000000u) + (__float_as_uint(l1) - 0x4B000000u);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+        const uint32_t hs = __reduce_add_sync(0xffffffffu, acc_hi[t]), ls = __reduce_add_sync(0xffffffffu, acc_lo[t]);
+        const unsigned long long bs = (static_cast<unsigned long long>(hs) << 20) + ls;
+        if (lane == k + t) blk = bs;                            // (at most 29 blocks per warp: the row fits shared memory)
+        wsum += bs;
+      }
+    }
   }
   if (lane == 0) sh.wsum[warp] = wsum;
   __syncthreads();
@@ -288,18 +298,7 @@ __device__ __forceinline__ long long row_residual_sample(const float* __restrict
   const int owner = __ffs(ball) - 1;                            // first warp whose range crosses the target
   if (warp != owner) return -1;
   const unsigned long long base = __shfl_sync(0xffffffffu, incl - mine_w, owner);
-  // the owning warp: exact sums of its blocks of 32 vectors (lane k keeps block k), the block that crosses the target, then
-  // the element inside it (vocabulary order)
-  unsigned long long blk = 0ull;
-  {
-    int k = 0;
-    for (int v0 = v_begin; v0 < v_end; v0 += 32, ++k) {
-      uint32_t acc_hi = 0u, acc_lo = 0u;
-      if (v0 + lane < v_end) limbs_of(v0 + lane, acc_hi, acc_lo);
-      const uint32_t hs = __reduce_add_sync(0xffffffffu, acc_hi), ls = __reduce_add_sync(0xffffffffu, acc_lo);
-      if (lane == k) blk = (static_cast<unsigned long long>(hs) << 20) + ls;   // (at most 29 blocks per warp: the row fits shared memory)
-    }
-  }
+  // the owning warp: block that crosses the target, then the element inside it (vocabulary order)
   const unsigned long long bincl = warp_scan_incl(blk, lane) + base;
   const unsigned bb = __ballot_sync(0xffffffffu, bincl > target);
   const int kb = __ffs(bb) - 1;
