@@ -772,7 +772,8 @@ def main():
                               "serial_frac": step_bytes / (serial_ms * 1e-3) / 1e9 / peak,
                               "note": "whole step (kernel 1 + kernel 2, SURVEY 8d bytes from the actual accept counts) over the timed ms_per_step"}},
     }
-    if not args.no_side_reports:
+    side_reports = not args.no_side_reports and world == 1    # (side reports and the CPU baseline: rank 0 at N = 1 only)
+    if side_reports:
         try:
             line["roofline"]["verify_dense"] = dense_verify_report(dev, ops)
         except Exception as e:                                # noqa: BLE001
@@ -781,7 +782,7 @@ def main():
             line["gpu_aten_baseline"] = gpu_aten_baseline(logits[0], dev)
         except Exception as e:                                # noqa: BLE001
             line["gpu_aten_baseline"] = {"error": f"{type(e).__name__}: {e}"[:200]}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         per = 16
         cores = os.cpu_count() or 1
         a1, _, dt1 = time_oracle(1, 1, per, 1)
@@ -796,7 +797,7 @@ def main():
                                 "sample": f"{n_steps} steps x {per} requests of the same workload ({n_steps * per * (2 * GAMMA + 1)} rows "
                                           f"+ verify) through oracle/ref_ops.py (the reference's ATen op chain, row by row), "
                                           f"torch threads={best_threads} of {cores} host cores; {dt_c:.1f} s of CPU work"}
-        if not args.no_side_reports:
+        if side_reports:
             try:
                 line["config1"] = config1_side_report()
             except Exception as e:                            # noqa: BLE001
