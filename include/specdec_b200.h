@@ -105,10 +105,13 @@ int sd_norm_probs(const void* logits, int dtype, int64_t rows, int64_t V, int64_
  * selects the one-cluster-per-row kernel. */
 #define SD_NORM_WORKSPACE_BYTES (16 + 65536 / 8)
 
-/* `flags` of the two norm entry points.  By default, for 0 < top_k <= 128 and 16-byte aligned rows the persistent,
- * warp-specialised pipeline kernel runs if a `workspace` is given (one CTA per SM: a memory warp streams slices in by TMA and zero-fills the
- * output while compute groups select; rows it cannot serve — massive ties — are re-run on the general path by the same
- * cluster before the kernel ends); every other case uses the one-cluster-per-row kernel. */
+/* `flags` of the two norm entry points.  By default, with a `workspace` and 16-byte aligned rows, persistent kernels run:
+ *  - the ring kernel (one CTA per SM streams whole rows through a shared-memory ring of 16 KB TMA chunks) for
+ *    0 < top_k <= 128 (rows that fit the ring, or of >= 24 chunks) and for the dense default top_k = 0, top_p = 0 (rows up
+ *    to 1 MB);
+ *  - the cluster pipeline (one cluster per row slice, DSMEM candidate exchange) for the top-k rows in between.
+ * Rows their fast selection cannot serve — massive ties — are re-run on the general path inside the same call.  Every other
+ * case (top-p only, top_k > 128, unaligned rows, no workspace) uses the one-cluster-per-row kernel. */
 #define SD_NORM_DEFAULT 0
 #define SD_NORM_NO_PIPELINE 1   /* one-cluster-per-row kernel even where the pipeline applies                 */
 #define SD_NORM_NO_RING 4       /* skip the ring kernel (one CTA per SM, whole rows through a shared-memory ring): use the
