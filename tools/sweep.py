@@ -19,6 +19,9 @@ sys.path.insert(0, ROOT)
 from llmspeculativesampling_b200 import build, ops  # noqa: E402
 
 
+PIPELINE = True
+
+
 def point(V, gamma, B, dtype, peak, mode):
     rows = B * (2 * gamma + 1)
     es = torch.tensor([], dtype=dtype).element_size()
@@ -36,14 +39,14 @@ def point(V, gamma, B, dtype, peak, mode):
     c = cmp_rows.view()
     err = ops.ErrFlag("cuda")                                # own scheduler workspace: usable inside the graph capture
     for i in range(n_sets):
-        ops.norm_sample(ins[i], T, k, p, u, probs_out=outs[i], tok_out=tok, compact=c, err=err)
+        ops.norm_sample(ins[i], T, k, p, u, probs_out=outs[i], tok_out=tok, compact=c, err=err, pipeline=PIPELINE)
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
     gr = torch.cuda.CUDAGraph()
     with torch.cuda.stream(side):
         with torch.cuda.graph(gr, stream=side):
             for i in range(n_sets):
-                ops.norm_sample(ins[i], T, k, p, u, probs_out=outs[i], tok_out=tok, compact=c, err=err)
+                ops.norm_sample(ins[i], T, k, p, u, probs_out=outs[i], tok_out=tok, compact=c, err=err, pipeline=PIPELINE)
     torch.cuda.synchronize()
     reps = max(3, int(0.02 / max(per_set * n_sets / 5e12, 1e-6)))
     reps = min(reps, 200)
@@ -65,9 +68,13 @@ def point(V, gamma, B, dtype, peak, mode):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--subset", default="all", choices=["all", "headline"],
-                    help="headline: the B >= 64 points of V = 32000 / 50272 only (the multi-GPU run)")
+    ap.add_argument("--subset", default="all", choices=["all", "headline", "draft"],
+                    help="headline: the B >= 64 points of V = 32000 / 50272 only (the multi-GPU run); draft: the launch shape of "
+                         "an engine's draft step (one row per request: gamma = 0)")
+    ap.add_argument("--no-ring", action="store_true", help="cluster pipeline / one-cluster-per-row kernels instead of the ring kernel")
     a = ap.parse_args()
+    global PIPELINE
+    PIPELINE = "cluster" if a.no_ring else True
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     if world > 1:                                             # N GPUs: every rank runs the same points (replicas, no collective
@@ -80,7 +87,13 @@ def main():
     except OSError:
         peak = 6650.0
     pts = []
-    if a.subset == "headline":
+    if a.subset == "draft":
+        for dtype in (torch.float32, torch.bfloat16):
+            for mode in ("topk", "dense"):
+                for V in (32000, 50272, 131072):
+                    for B in (16, 32, 64, 128):
+                        pts.append((V, 0, B, dtype, mode))
+    elif a.subset == "headline":
         for dtype in (torch.float32, torch.bfloat16):
             for mode in ("topk", "dense"):
                 for V in (32000, 50272):
