@@ -535,8 +535,8 @@ def main():
 
     side3 = torch.cuda.Stream()
 
-    def pipelined():
-        """PIPE_STEPS steps, independent batches in flight.  --pipeline 1: kernel 1 of step j+1 is launched right behind
+    def pipelined(n_steps: int = PIPE_STEPS):
+        """n_steps steps (PIPE_STEPS by default), independent batches in flight.  --pipeline 1: kernel 1 of step j+1 is launched right behind
         kernel 1 of step j on one stream, kernel 2 of step j runs beside it on a second stream (it needs a few KB of
         compact lists and a handful of thread blocks).  --pipeline 2 (default): kernel 1 of consecutive steps additionally
         alternates between TWO streams (each with its own scheduler workspace): the persistent CTAs of step j+1 take over
@@ -548,7 +548,7 @@ def main():
         if two:
             side3.wait_stream(main_s)
         ev_v = {}
-        for j in range(PIPE_STEPS):
+        for j in range(n_steps):
             i = j % n_sets
             s_n = side3 if (two and j % 2 == 1) else main_s
             if j - n_sets in ev_v:
@@ -568,13 +568,17 @@ def main():
                 verify(i)
                 ev_v[j] = torch.cuda.Event()
                 ev_v[j].record(side2)
-        for j in range(PIPE_STEPS - n_sets, PIPE_STEPS):
+        for j in range(max(0, n_steps - n_sets), n_steps):
             main_s.wait_event(ev_v[j])
         if two:
             main_s.wait_stream(side3)
 
     use_pipe = bool(args.pipeline) and not args.fused
     g_pipe = capture(pipelined) if use_pipe else None
+    # the steps that do not fill a PIPE_STEPS graph run from a shorter pipelined graph (PIPE_STEPS is a multiple of n_sets, so
+    # its first step continues the rotation of the input sets), not one by one
+    n_rem = args.steps % PIPE_STEPS if use_pipe else 0
+    g_pipe_rem = capture(lambda: pipelined(n_rem)) if n_rem >= 2 else None
     torch.cuda.synchronize()
 
     def barrier():
@@ -588,11 +592,16 @@ def main():
             while n - s >= PIPE_STEPS:
                 g_pipe.replay()
                 s += PIPE_STEPS
+            if g_pipe_rem is not None and n - s == n_rem:
+                g_pipe_rem.replay()
+                s += n_rem
         while s < n:
             g_serial[(first + s) % n_sets].replay()
             s += 1
 
     run_steps(max(args.warmup, PIPE_STEPS if use_pipe else 0))
+    if g_pipe_rem is not None:
+        g_pipe_rem.replay()                                   # (warm-up of the remainder graph as well)
     barrier()
     acc_total.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -605,7 +614,7 @@ def main():
     err.check()
     accepted = int(acc_total[0].item())
     assert int(acc_total[1].item()) == args.steps * B, "kernel 2 must have verified every request of every step"
-    pipelined_steps = (args.steps // PIPE_STEPS) * PIPE_STEPS if use_pipe else 0
+    pipelined_steps = ((args.steps // PIPE_STEPS) * PIPE_STEPS + (n_rem if g_pipe_rem is not None else 0)) if use_pipe else 0
 
     # ---- sub-measurements (self-sized: >= 200 launches whatever --steps is), all from CUDA graphs replayed back to back:
     #      the strictly serial step (latency of one batch), kernel 1 alone, kernel 2 alone
@@ -692,7 +701,7 @@ def main():
 
     for ev in ev_free:
         ev.record(cur)
-    e2e_steps = max(4, min(args.steps, 60))
+    e2e_steps = 60                                          # (own, fixed length: ~80 ms; a short --steps would mostly time the fill of the two-buffer pipeline)
     e2e_run(4)
     barrier()
     t0 = time.perf_counter()
