@@ -61,8 +61,9 @@ struct alignas(16) RingTopKScratch {
   float f_val[kRingCap];               // ... and the final probabilities of the row it is finishing
 };
 struct alignas(16) RingDenseScratch {
-  float wm[kRingComputeWarps];
-  double ws[kRingComputeWarps];
+  uint64_t comb[2];                    // the 16 warp results of a row are in place (16 compute warps -> each other), by item parity
+  float wm[2][kRingComputeWarps];      // (double buffered by item parity: a warp may be a whole pass ahead of the slowest reader)
+  double ws[2][kRingComputeWarps];
   unsigned long long piece[2][kRingMaxPieces];
   float info_c2[2];
 };
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
       sh.n_fail = 0;
       sh.end_reason = kRingEndDone;
       if constexpr (kTopK) { sh.k.cand_cnt = 0; sh.k.cand_over = 0; }   // (a dense launch does not allocate the top-k scratch)
+      else { mbar_init(&sh.d.comb[0], CW); mbar_init(&sh.d.comb[1], CW); }
       fence_barrier_init();
     }
     if (round > 0) {
@@ -798,33 +800,18 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           float s_t;
           { float sa, sb; unpack2(s2, sa, sb); s_t = sa + sb; }
           RING_PROF(1);
-          // ---- combine: warp, then CTA (every thread folds the 16 warp results itself: one barrier)
+          // ---- combine: warp, then CTA.  The 16 warp results meet on an mbarrier (arrive now, wait later): between the two a
+          //      warp already scans the first chunks of the NEXT row (they sit in the ring's spare slots), so the serial
+          //      reduction chain of the combine does not leave the SM's issue slots empty
+          const int par = it & 1;
           {
             const float Mw = warp_max(m_t);
             const float sc = (m_t == -INFINITY) ? 0.f : s_t * ex2_ftz((m_t - Mw) * kLog2e);
             const double Sw = warp_sum(static_cast<double>(sc));
-            if (lane == 0) { sh.d.wm[warp] = Mw; sh.d.ws[warp] = Sw; }
+            if (lane == 0) { sh.d.wm[par][warp] = Mw; sh.d.ws[par][warp] = Sw; }
+            __syncwarp();
+            if (lane == 0) ring_arrive(&sh.d.comb[par]);
           }
-          ring_named_bar(1, CT);
-          // (lane w of every warp folds warp w's pair; the warp-wide butterflies have the same order in all warps, so M and z
-          //  are bit-identical across the CTA)
-          const float mw = lane < CW ? sh.d.wm[lane] : -INFINITY;
-          const float M = warp_max(mw);
-          const double zw = (lane < CW && mw > -INFINITY) ? sh.d.ws[lane] * static_cast<double>(ex2_ftz((mw - M) * kLog2e)) : 0.0;
-          const double z = warp_sum(zw);
-          const float logz = logf(static_cast<float>(z));
-          if (!(z > 0.0) || isinf(logz) || logz != logz) { if (tid == 0) atomicOr(p.err_flag, kErrNanLogit); }   // (uniform condition)
-          const float c2 = -logz * kLog2e;
-          const bool do_sample = u_row >= 0.f;                   // row-uniform
-          const int par = it & 1;
-          if (it >= 2) mbar_wait(&sh.tfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);   // sampler is done with item it - 2
-          if (warp == 0) sh.d.info_c2[par] = c2;                   // (whole warp, same value: no single-lane branch in front of the warp reductions below)
-          // sampler weights  w = floor(p * 2^(40 - e)),  e = frexp exponent of the row maximum exp2(c2)
-          const float scale = ldexpf(1.0f, kScaleBits - frexp_exp(ex2_ftz(c2)));
-          const float scale_hi = scale * 9.5367431640625e-07f;              // 2^-20 * scale (exact)
-          const f32x2 nM2 = pack2(-M, -M), c22 = pack2(c2, c2), sh2 = pack2(scale_hi, scale_hi);
-          const f32x2 k23 = pack2(8388608.0f, 8388608.0f), m1 = pack2(-1.0f, -1.0f), k20 = pack2(1048576.0f, 1048576.0f);
-          RING_PROF(2);
           // the row after this one (the loader published it while it issued this row's loads): its pass A is interleaved below
           int next_row = -1;
           if (!long_rows) {
@@ -835,6 +822,32 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
           if (slot0n >= NS) { slot0n -= NS; ++wraps0n; }
           m_t = -INFINITY; nan_acc = -INFINITY; s2 = pack2(0.f, 0.f);
           if (next_row >= 0) car_u = p.u != nullptr ? __ldg(p.u + next_row) : -1.f;
+          int na = 0;                                            // chunks of the next row already scanned
+          if (next_row >= 0) {
+            // (only chunks that can land without a release from this row; 16-bit rows only: they are bound by the SM —
+            //  measured -6 % at 576 rows —, fp32 rows by HBM, where delaying pass B's stores and slot releases costs 6 %)
+            const int pre = sizeof(T) == 2 ? min(min(2, NS - NCH), NCH) : 0;
+            for (; na < pre; ++na) pass_a(na, slot0n, wraps0n, false);
+          }
+          mbar_wait(&sh.d.comb[par], static_cast<uint32_t>(it >> 1) & 1u);
+          // (lane w of every warp folds warp w's pair; the warp-wide butterflies have the same order in all warps, so M and z
+          //  are bit-identical across the CTA)
+          const float mw = lane < CW ? sh.d.wm[par][lane] : -INFINITY;
+          const float M = warp_max(mw);
+          const double zw = (lane < CW && mw > -INFINITY) ? sh.d.ws[par][lane] * static_cast<double>(ex2_ftz((mw - M) * kLog2e)) : 0.0;
+          const double z = warp_sum(zw);
+          const float logz = logf(static_cast<float>(z));
+          if (!(z > 0.0) || isinf(logz) || logz != logz) { if (tid == 0) atomicOr(p.err_flag, kErrNanLogit); }   // (uniform condition)
+          const float c2 = -logz * kLog2e;
+          const bool do_sample = u_row >= 0.f;                   // row-uniform
+          if (it >= 2) mbar_wait(&sh.tfree[par], (static_cast<uint32_t>(it >> 1) - 1u) & 1u);   // sampler is done with item it - 2
+          if (warp == 0) sh.d.info_c2[par] = c2;                   // (whole warp, same value: no single-lane branch in front of the warp reductions below)
+          // sampler weights  w = floor(p * 2^(40 - e)),  e = frexp exponent of the row maximum exp2(c2)
+          const float scale = ldexpf(1.0f, kScaleBits - frexp_exp(ex2_ftz(c2)));
+          const float scale_hi = scale * 9.5367431640625e-07f;              // 2^-20 * scale (exact)
+          const f32x2 nM2 = pack2(-M, -M), c22 = pack2(c2, c2), sh2 = pack2(scale_hi, scale_hi);
+          const f32x2 k23 = pack2(8388608.0f, 8388608.0f), m1 = pack2(-1.0f, -1.0f), k20 = pack2(1048576.0f, 1048576.0f);
+          RING_PROF(2);
           // ---- pass B: probabilities out (16-byte streaming stores), exact weight sums per piece, slots released.
           //      With fewer than 3 spare ring slots next to a row (fp32 V = 50272: none) the next row's chunk c can only be
           //      requested once this row's chunk c + NCH - NS has been released: its pass A then lags `lag` chunks behind
@@ -912,10 +925,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
             }
             __syncwarp();
             if (lane == 0) ring_arrive(&sh.empty[slot]);
-            if (next_row >= 0 && c >= lag) pass_a(c - lag, slot0n, wraps0n, false);
+            if (next_row >= 0 && c >= lag && na < NCH) { pass_a(na, slot0n, wraps0n, false); ++na; }
           }
           if (next_row >= 0)
-            for (int c = NCH - lag; c < NCH; ++c) pass_a(c, slot0n, wraps0n, false);
+            for (; na < NCH; ++na) pass_a(na, slot0n, wraps0n, false);
           __syncwarp();
           if (lane == 0) ring_arrive(&sh.row_done[par]);       // (release: this warp's stores and piece sums first)
           carried = next_row >= 0;
@@ -937,6 +950,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) norm_ring_kernel(const NormPa
         for (int s = 0; s < NS; ++s) { mbar_inval(&sh.full[s]); mbar_inval(&sh.empty[s]); }
         for (int i = 0; i < kRingItemRing; ++i) mbar_inval(&sh.rowfull[i]);
         for (int i = 0; i < 2; ++i) { mbar_inval(&sh.row_done[i]); mbar_inval(&sh.tfree[i]); mbar_inval(&sh.sorted[i]); mbar_inval(&sh.sfree[i]); }
+        if constexpr (!kTopK) { mbar_inval(&sh.d.comb[0]); mbar_inval(&sh.d.comb[1]); }
       }
       __syncthreads();
     }
